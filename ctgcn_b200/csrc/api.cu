@@ -1,0 +1,224 @@
+// extern "C" surface of libctgcn_b200.so (declared in include/ctgcn_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace ctgcn {
+
+static thread_local char g_err[1024] = "";
+std::atomic<int64_t> g_launches{0};
+static std::atomic<int> g_gru_impl{CTGCN_IMPL_AUTO};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// tcgen05 path (gru_tc.cu); returns 1 when the shape is not supported by it
+int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* w_ih,
+                  const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
+                  int mode, float* y, int64_t yrs, int64_t yss, void* ws, size_t ws_bytes, cudaStream_t st)
+    __attribute__((weak));
+
+}  // namespace ctgcn
+
+using namespace ctgcn;
+
+extern "C" int ctgcn_version(void) { return 100; }
+extern "C" const char* ctgcn_last_error(void) { return g_err; }
+extern "C" int64_t ctgcn_launch_count(void) { return g_launches.load(); }
+
+extern "C" int ctgcn_device_check(void) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+        set_error("no CUDA device available");
+        return CTGCN_ENODEV;
+    }
+    if (prop.major != 10) {
+        set_error("device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+        return CTGCN_ENODEV;
+    }
+    return CTGCN_OK;
+}
+
+extern "C" int ctgcn_set_gru_impl(int impl) {
+    CTGCN_REQUIRE(impl >= CTGCN_IMPL_AUTO && impl <= CTGCN_IMPL_TCGEN05, "set_gru_impl: unknown implementation %d", impl);
+    g_gru_impl.store(impl);
+    return CTGCN_OK;
+}
+
+extern "C" int ctgcn_cumspmm_fwd(const ctgcn_plan* plan, const float* x, int64_t ldx, int d, float* u, void* stream) {
+    CTGCN_REQUIRE(plan && x && u, "cumspmm_fwd: NULL argument");
+    CTGCN_REQUIRE(ldx >= d, "cumspmm_fwd: ldx < d");
+    return launch_cumspmm(plan, x, ldx, d, u, true, (cudaStream_t)stream);
+}
+
+// ---- GRU: workspace = k-major copies of the two weight matrices (SIMT path) | tcgen05 packed weights
+static size_t gru_ws_simt(int d_in, int h) { return align_up((size_t)3 * h * (d_in + h) * sizeof(float), 256); }
+static size_t gru_ws_tc(int d_in, int h) { return align_up((size_t)3 * h * (d_in + h) * 2 * sizeof(uint16_t), 256) + 1024; }
+
+extern "C" size_t ctgcn_gru_workspace_bytes(int d_in, int h) {
+    if (d_in <= 0 || h <= 0) return 0;
+    return gru_ws_simt(d_in, h) + gru_ws_tc(d_in, h);
+}
+
+extern "C" int ctgcn_gru_seq_fwd(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h,
+                                 const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                 const float* ln_w, const float* ln_b, float eps, int mode, float* y, int64_t yrs,
+                                 int64_t yss, void* workspace, size_t workspace_bytes, void* stream) {
+    CTGCN_REQUIRE(seq && w_ih && w_hh && ln_w && ln_b && y, "gru_seq_fwd: NULL argument");
+    CTGCN_REQUIRE((b_ih == nullptr) == (b_hh == nullptr), "gru_seq_fwd: b_ih and b_hh must both be given or both NULL");
+    CTGCN_REQUIRE(n >= 0 && steps >= 1 && d_in >= 1 && h >= 1, "gru_seq_fwd: bad sizes n=%lld steps=%d d_in=%d h=%d",
+                  (long long)n, steps, d_in, h);
+    CTGCN_REQUIRE(mode == CTGCN_GRU_SUM_LN || mode == CTGCN_GRU_EACH_LN, "gru_seq_fwd: unknown mode %d", mode);
+    if (workspace_bytes < ctgcn_gru_workspace_bytes(d_in, h) || !workspace) {
+        set_error("gru_seq_fwd: workspace of %zu bytes, need %zu", workspace_bytes, ctgcn_gru_workspace_bytes(d_in, h));
+        return CTGCN_ENOMEM;
+    }
+    if (n == 0) return CTGCN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int impl = g_gru_impl.load();
+    if (impl != CTGCN_IMPL_SIMT && launch_gru_tc) {
+        char* tc_ws = (char*)workspace + gru_ws_simt(d_in, h);
+        int rc = launch_gru_tc(seq, srs, sss, n, steps, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss,
+                               tc_ws, gru_ws_tc(d_in, h), st);
+        if (rc <= 0) return rc;  // done or failed
+        CTGCN_REQUIRE(impl == CTGCN_IMPL_AUTO, "gru_seq_fwd: tcgen05 path does not support d_in=%d h=%d", d_in, h);
+    } else {
+        CTGCN_REQUIRE(impl != CTGCN_IMPL_TCGEN05, "gru_seq_fwd: tcgen05 path not built");
+    }
+    float* wt_ih = (float*)workspace;
+    float* wt_hh = wt_ih + (size_t)3 * h * d_in;
+    int rc = launch_transpose(w_ih, 3 * h, d_in, wt_ih, st);
+    if (rc) return rc;
+    rc = launch_transpose(w_hh, 3 * h, h, wt_hh, st);
+    if (rc) return rc;
+    return launch_gru_simt(seq, srs, sss, n, steps, d_in, h, wt_ih, wt_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, st);
+}
+
+// ---- CoreDiffusion.forward: cumulative SpMM → U [n, K, d_in] (workspace) → GRU over cores + Σ + LayerNorm
+extern "C" size_t ctgcn_core_diffusion_workspace_bytes(const ctgcn_plan* plan, int d_in, int h) {
+    if (!plan || d_in <= 0 || h <= 0) return 0;
+    return align_up((size_t)plan->n_rows * plan->k * d_in * sizeof(float), 256) + ctgcn_gru_workspace_bytes(d_in, h);
+}
+
+extern "C" int ctgcn_core_diffusion_fwd(const ctgcn_plan* plan, const float* x, int64_t ldx, int d_in, int h,
+                                        const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                        const float* ln_w, const float* ln_b, float eps, float* y, int64_t ldy,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+    CTGCN_REQUIRE(plan && x && y, "core_diffusion_fwd: NULL argument");
+    CTGCN_REQUIRE(plan->n_rows == plan->n_cols, "core_diffusion_fwd: adjacency plan must be square");
+    CTGCN_REQUIRE(ldx >= d_in && ldy >= h, "core_diffusion_fwd: leading dimension too small");
+    const size_t need = ctgcn_core_diffusion_workspace_bytes(plan, d_in, h);
+    if (!workspace || workspace_bytes < need) {
+        set_error("core_diffusion_fwd: workspace of %zu bytes, need %zu", workspace_bytes, need);
+        return CTGCN_ENOMEM;
+    }
+    float* u = (float*)workspace;
+    const size_t u_bytes = align_up((size_t)plan->n_rows * plan->k * d_in * sizeof(float), 256);
+    int rc = launch_cumspmm(plan, x, ldx, d_in, u, true, (cudaStream_t)stream);
+    if (rc) return rc;
+    return ctgcn_gru_seq_fwd(u, (int64_t)plan->k * d_in, d_in, plan->n_rows, plan->k, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w,
+                             ln_b, eps, CTGCN_GRU_SUM_LN, y, ldy, 0, (char*)workspace + u_bytes, workspace_bytes - u_bytes,
+                             stream);
+}
+
+// ---- MLP layers
+extern "C" size_t ctgcn_linear_workspace_bytes(int64_t d_in, int64_t d_out) {
+    if (d_in <= 0 || d_out <= 0) return 0;
+    return align_up((size_t)d_in * d_out * sizeof(float), 256);
+}
+
+extern "C" int ctgcn_linear_fwd(const float* x, int64_t ldx, int64_t n, int64_t d_in, const float* w, const float* b,
+                                int64_t d_out, int act, float* y, int64_t ldy, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+    CTGCN_REQUIRE(x && w && y, "linear_fwd: NULL argument");
+    CTGCN_REQUIRE(n >= 0 && d_in >= 1 && d_out >= 1 && ldx >= d_in && ldy >= d_out, "linear_fwd: bad sizes");
+    CTGCN_REQUIRE(act == CTGCN_ACT_NONE || act == CTGCN_ACT_SELU, "linear_fwd: unknown activation %d", act);
+    if (!workspace || workspace_bytes < ctgcn_linear_workspace_bytes(d_in, d_out)) {
+        set_error("linear_fwd: workspace of %zu bytes, need %zu", workspace_bytes, ctgcn_linear_workspace_bytes(d_in, d_out));
+        return CTGCN_ENOMEM;
+    }
+    if (n == 0) return CTGCN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* wt = (float*)workspace;
+    int rc = launch_transpose(w, d_out, d_in, wt, st);
+    if (rc) return rc;
+    return launch_linear_simt(x, ldx, n, d_in, wt, b, d_out, act, y, ldy, st);
+}
+
+extern "C" int ctgcn_spmm_linear_fwd(const ctgcn_plan* xp, const float* w, const float* b, int64_t d_out, int act, float* y,
+                                     int64_t ldy, void* workspace, size_t workspace_bytes, void* stream) {
+    CTGCN_REQUIRE(xp && w && y, "spmm_linear_fwd: NULL argument");
+    CTGCN_REQUIRE(xp->k == 1, "spmm_linear_fwd: the feature plan must hold exactly one matrix (k=%d)", xp->k);
+    CTGCN_REQUIRE(d_out >= 1 && ldy >= d_out, "spmm_linear_fwd: bad sizes");
+    CTGCN_REQUIRE(act == CTGCN_ACT_NONE || act == CTGCN_ACT_SELU, "spmm_linear_fwd: unknown activation %d", act);
+    const int64_t d_in = xp->n_cols;
+    if (!workspace || workspace_bytes < ctgcn_linear_workspace_bytes(d_in, d_out)) {
+        set_error("spmm_linear_fwd: workspace of %zu bytes, need %zu", workspace_bytes,
+                  ctgcn_linear_workspace_bytes(d_in, d_out));
+        return CTGCN_ENOMEM;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* wt = (float*)workspace;
+    int rc = launch_transpose(w, d_out, d_in, wt, st);
+    if (rc) return rc;
+    return launch_spmm_linear(xp, wt, b, d_out, act, y, ldy, st);
+}
+
+// ---- host helper: exact core numbers (Batagelj–Zaversnik bucket peeling, O(n + m))
+extern "C" int ctgcn_kcore_numbers(int64_t n, const int64_t* rowptr, const int32_t* col, int32_t* core) {
+    CTGCN_REQUIRE(n >= 0 && rowptr && core && (col || rowptr[n] == 0), "kcore_numbers: NULL argument");
+    if (n == 0) return CTGCN_OK;
+    std::vector<int32_t> deg(n), pos(n), vert(n);
+    int32_t md = 0;
+    for (int64_t v = 0; v < n; ++v) {
+        deg[v] = (int32_t)(rowptr[v + 1] - rowptr[v]);
+        md = deg[v] > md ? deg[v] : md;
+    }
+    std::vector<int64_t> bin(md + 2, 0);
+    for (int64_t v = 0; v < n; ++v) bin[deg[v]]++;
+    int64_t start = 0;
+    for (int32_t d = 0; d <= md; ++d) {
+        int64_t c = bin[d];
+        bin[d] = start;
+        start += c;
+    }
+    for (int64_t v = 0; v < n; ++v) {
+        pos[v] = (int32_t)bin[deg[v]];
+        vert[pos[v]] = (int32_t)v;
+        bin[deg[v]]++;
+    }
+    for (int32_t d = md; d >= 1; --d) bin[d] = bin[d - 1];
+    bin[0] = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t v = vert[i];
+        core[v] = deg[v];
+        for (int64_t e = rowptr[v]; e < rowptr[v + 1]; ++e) {
+            const int32_t u = col[e];
+            if (u < 0 || u >= n) {
+                set_error("kcore_numbers: column index out of range");
+                return CTGCN_EINVAL;
+            }
+            if (deg[u] > deg[v]) {
+                const int32_t du = deg[u], pu = pos[u];
+                const int32_t pw = (int32_t)bin[du], w = vert[pw];
+                if (u != w) {
+                    pos[u] = pw;
+                    vert[pu] = w;
+                    pos[w] = pu;
+                    vert[pw] = u;
+                }
+                bin[du]++;
+                deg[u]--;
+            }
+        }
+    }
+    return CTGCN_OK;
+}

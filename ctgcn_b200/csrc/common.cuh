@@ -1,0 +1,77 @@
+// Shared helpers for the ctgcn_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include <string>
+
+#include "../../include/ctgcn_b200.h"
+
+namespace ctgcn {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define CTGCN_CUDA_OK(expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            ctgcn::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,             \
+                             cudaGetErrorString(_e));                                         \
+            return CTGCN_ECUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+#define CTGCN_LAUNCH_OK(name)                                                                 \
+    do {                                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess) {                                                              \
+            ctgcn::set_error("launch of %s failed at %s:%d: %s", name, __FILE__, __LINE__,    \
+                             cudaGetErrorString(_e));                                         \
+            return CTGCN_ECUDA;                                                               \
+        }                                                                                     \
+        ctgcn::count_launch();                                                                \
+    } while (0)
+
+#define CTGCN_REQUIRE(cond, ...)                                                              \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            ctgcn::set_error(__VA_ARGS__);                                                    \
+            return CTGCN_EINVAL;                                                              \
+        }                                                                                     \
+    } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace ctgcn
+
+struct ctgcn_plan {
+    int64_t n_rows = 0, n_cols = 0;
+    int k = 0;
+    int64_t entries = 0;        // stored entries of the union CSR
+    int64_t nnz_raw_sum = 0;    // Σ_i stored nnz of the K input matrices ("aggregated edges")
+    int64_t nnz_coalesced = 0;  // Σ_i nnz after summing duplicates
+    int64_t n_oneshot = 0;
+    int device = 0;
+    int32_t* rowptr = nullptr;  // [n_rows + 1]
+    int32_t* col = nullptr;     // [entries]
+    float* val = nullptr;       // [entries]
+    uint8_t* lvl = nullptr;     // [entries]  bits 0..6 level, bit 7 one-shot
+    size_t bytes = 0;
+};
+
+// kernels' host launchers (defined in the respective .cu files)
+namespace ctgcn {
+int launch_cumspmm(const ctgcn_plan* p, const float* x, int64_t ldx, int d, float* u, bool relu, cudaStream_t st);
+int launch_spmm_linear(const ctgcn_plan* p, const float* wt, const float* b, int64_t d_out, int act, float* y,
+                       int64_t ldy, cudaStream_t st);
+int launch_transpose(const float* src, int64_t rows, int64_t cols, float* dst, cudaStream_t st);
+int launch_linear_simt(const float* x, int64_t ldx, int64_t n, int64_t d_in, const float* wt, const float* b,
+                       int64_t d_out, int act, float* y, int64_t ldy, cudaStream_t st);
+int launch_gru_simt(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h,
+                    const float* wt_ih, const float* wt_hh, const float* b_ih, const float* b_hh, const float* ln_w,
+                    const float* ln_b, float eps, int mode, float* y, int64_t yrs, int64_t yss, cudaStream_t st);
+}  // namespace ctgcn

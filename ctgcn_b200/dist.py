@@ -1,0 +1,116 @@
+"""Snapshot-parallel execution of CTGCN.forward over torch.distributed (one process per GPU, NCCL).
+
+Sharding: snapshot t is owned by rank t mod G — MLP_t / CDN_t weights, x_t and the graph plan
+of adj_list[t] are disjoint per snapshot (reference models.py:225-231, 243-247), so there is no data-path
+collective until the stack at models.py:248.  There, ONE exchange moves the per-snapshot embeddings so that
+every rank holds all T snapshots of ITS node slice ([N/G, T, D]); the temporal GRU + LayerNorm
+(models.py:249-250) is node-wise independent and runs on that slice.  ``exchange='all_to_all'`` (default)
+sends each rank only its slice; ``exchange='all_gather'`` is the literal all-gather of whole snapshots.
+A second collective gathers the output only if ``model.gather_output`` is set.
+
+The tensor-shuffling helpers below are device-agnostic so that the host logic is testable with gloo on CPU.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as td
+
+
+def world_size() -> int:
+    return td.get_world_size() if td.is_available() and td.is_initialized() else 1
+
+
+def rank() -> int:
+    return td.get_rank() if td.is_available() and td.is_initialized() else 0
+
+
+def owned_snapshots(T: int, G: int, r: int):
+    return list(range(r, T, G))
+
+
+def node_slices(n: int, G: int):
+    """Balanced contiguous node ranges [(start, stop)] for the G ranks."""
+    base, rem = divmod(n, G)
+    out, s = [], 0
+    for g in range(G):
+        e = s + base + (1 if g < rem else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
+def exchange_to_node_slices(hx_local: torch.Tensor, T: int, group=None, mode: str = "all_to_all") -> torch.Tensor:
+    """hx_local [N, Tl, D]: this rank's snapshots (slot j ↔ snapshot rank + G·j, Tl = ceil(T/G), unused slots
+    arbitrary) → seq [rows_of_this_rank, T, D] holding every snapshot of this rank's node slice."""
+    G, r = td.get_world_size(group), td.get_rank(group)
+    n, tl, d = hx_local.shape
+    assert tl == (T + G - 1) // G, (tl, T, G)
+    slices = node_slices(n, G)
+    my0, my1 = slices[r]
+    rows = my1 - my0
+    if mode == "all_to_all":
+        recv = hx_local.new_empty((rows * G, tl, d))
+        td.all_to_all_single(recv, hx_local.contiguous(), output_split_sizes=[rows] * G,
+                             input_split_sizes=[e - s for s, e in slices], group=group)
+        parts = recv.view(G, rows, tl, d)
+    elif mode == "all_gather":
+        full = hx_local.new_empty((G, n, tl, d))
+        td.all_gather_into_tensor(full, hx_local.contiguous(), group=group)
+        parts = full[:, my0:my1]
+    else:
+        raise ValueError("exchange must be 'all_to_all' or 'all_gather'")
+    # parts[g, n, j] is snapshot t = g + G·j  →  seq[n, t]
+    seq = parts.permute(1, 2, 0, 3).reshape(rows, tl * G, d)
+    return seq[:, :T].contiguous()
+
+
+def gather_node_slices(out_slice: torch.Tensor, n: int, group=None) -> torch.Tensor:
+    """out_slice [rows_r, T, D] on every rank → [N, T, D] on every rank."""
+    G = td.get_world_size(group)
+    slices = node_slices(n, G)
+    max_rows = max(e - s for s, e in slices)
+    _, T, d = out_slice.shape
+    pad = out_slice.new_zeros((max_rows, T, d))
+    pad[: out_slice.shape[0]] = out_slice
+    full = out_slice.new_empty((G, max_rows, T, d))
+    td.all_gather_into_tensor(full, pad, group=group)
+    return torch.cat([full[g, : e - s] for g, (s, e) in enumerate(slices)], dim=0)
+
+
+def ctgcn_forward_sharded(model, x_list, adj_list):
+    """CTGCN.forward under snapshot parallelism.  x_list[t] / adj_list[t] are only touched for owned t
+    (entries for other snapshots may be None).  Returns the reference's [T, N, D] view when
+    ``model.gather_output`` else this rank's slice [T, rows, D]; model_type 'S' adds the list of MLP outputs
+    (None for snapshots owned by other ranks)."""
+    from .layers import _guard
+
+    G, r = world_size(), rank()
+    T = len(x_list)
+    owned = owned_snapshots(T, G, r)
+    tl = (T + G - 1) // G
+    dev = model.norm.weight.device
+    trans_list = [None] * T
+    hx_local, n = None, None
+    for j, t in enumerate(owned):
+        trans = model.mlp_list[t](x_list[t])
+        trans_list[t] = trans
+        if hx_local is None:
+            n = trans.shape[0]
+            hx_local = torch.zeros(n, tl, model.output_dim, dtype=torch.float32, device=dev)
+        model.duffision_list[t].forward_into(trans, adj_list[t], out=hx_local[:, j, :])
+    if hx_local is None:  # more ranks than snapshots: this rank owns nothing but still takes part
+        n = int(getattr(model, "node_num", 0)) or _infer_rows(x_list, adj_list)
+        hx_local = torch.zeros(n, tl, model.output_dim, dtype=torch.float32, device=dev)
+    seq = exchange_to_node_slices(hx_local, T, mode=getattr(model, "exchange", "all_to_all"))
+    out = model._temporal(seq)
+    if getattr(model, "gather_output", True):
+        out = gather_node_slices(out, n)
+    out = _guard(out, model).transpose(0, 1)
+    return out if model.model_type == 'C' else (out, trans_list)
+
+
+def _infer_rows(x_list, adj_list):
+    for x in x_list:
+        if x is not None:
+            return x.shape[0]
+    raise ValueError("cannot infer the node count: this rank owns no snapshot and x_list holds no tensor")

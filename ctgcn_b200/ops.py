@@ -1,0 +1,142 @@
+"""Tensor-level wrappers over the C-ABI (torch tensors in, torch tensors out; torch only owns memory/streams)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .plan import GraphPlan
+
+_vp = C.c_void_p
+
+
+def _ptr(t):
+    return _vp(0) if t is None else _vp(t.data_ptr())
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32_rows(t: torch.Tensor, name: str) -> torch.Tensor:
+    """2-D fp32 CUDA tensor whose last dim is contiguous (row stride free)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.CtgcnError(f"{name} must be a CUDA tensor (ctgcn_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() != 2:
+        raise _lib.CtgcnError(f"{name} must be 2-D, got shape {tuple(t.shape)}")
+    if t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t
+
+
+def _vec(t, name):
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != torch.float32:
+        raise _lib.CtgcnError(f"{name} must be an fp32 CUDA tensor")
+    return t.detach().contiguous()
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def cumspmm(plan: GraphPlan, x: torch.Tensor) -> torch.Tensor:
+    """relu(cumsum_i A_i x) for all K cores → [N, K, D]  (layers.py:41-48)."""
+    x = _f32_rows(x, "x")
+    if x.shape[0] != plan.n_cols:
+        raise _lib.CtgcnError(f"x has {x.shape[0]} rows, the plan expects {plan.n_cols}")
+    u = torch.empty(plan.n_rows, plan.k, x.shape[1], dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib.ctgcn_cumspmm_fwd(plan.handle, _ptr(x), x.stride(0), x.shape[1], _ptr(u), _stream()),
+                   "ctgcn_cumspmm_fwd")
+    return u
+
+
+def gru_seq(seq: torch.Tensor, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps: float, mode: int, out: torch.Tensor = None):
+    """GRU over dim 1 of seq [N, L, D_in] (any row/step strides) + LayerNorm.
+
+    mode GRU_SUM_LN → [N, H] = LN(Σ_s h_s); GRU_EACH_LN → [N, L, H] = LN(h_s).
+    """
+    if seq.dim() != 3 or not seq.is_cuda or seq.dtype != torch.float32 or seq.stride(2) != 1:
+        raise _lib.CtgcnError("seq must be a 3-D fp32 CUDA tensor with a contiguous last dim")
+    n, steps, d_in = seq.shape
+    h = w_hh.shape[1]
+    w_ih, w_hh, b_ih, b_hh, ln_w, ln_b = (_vec(t, nm) for t, nm in
+                                           ((w_ih, "w_ih"), (w_hh, "w_hh"), (b_ih, "b_ih"), (b_hh, "b_hh"),
+                                            (ln_w, "ln_w"), (ln_b, "ln_b")))
+    if tuple(w_ih.shape) != (3 * h, d_in) or tuple(w_hh.shape) != (3 * h, h):
+        raise _lib.CtgcnError(f"GRU weight shapes {tuple(w_ih.shape)}, {tuple(w_hh.shape)} do not match d_in={d_in}, h={h}")
+    if out is None:
+        out = torch.empty((n, h) if mode == _lib.GRU_SUM_LN else (n, steps, h), dtype=torch.float32, device=seq.device)
+    yrs = out.stride(0)
+    yss = out.stride(1) if mode == _lib.GRU_EACH_LN else 0
+    if out.stride(-1) != 1:
+        raise _lib.CtgcnError("out must have a contiguous last dim")
+    ws_bytes = _lib.lib.ctgcn_gru_workspace_bytes(d_in, h)
+    ws = _workspace(ws_bytes, seq.device)
+    with torch.cuda.device(seq.device):
+        _lib.check(_lib.lib.ctgcn_gru_seq_fwd(_ptr(seq), seq.stride(0), seq.stride(1), n, steps, d_in, h, _ptr(w_ih),
+                                              _ptr(w_hh), _ptr(b_ih), _ptr(b_hh), _ptr(ln_w), _ptr(ln_b), float(eps), mode,
+                                              _ptr(out), yrs, yss, _ptr(ws), ws_bytes, _stream()), "ctgcn_gru_seq_fwd")
+    return out
+
+
+def core_diffusion(plan: GraphPlan, x, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps: float, out: torch.Tensor = None):
+    """layers.CoreDiffusion.forward on one plan → [N, H] (written into `out`, any row stride, if given)."""
+    x = _f32_rows(x, "x")
+    d_in = x.shape[1]
+    h = w_hh.shape[1]
+    if x.shape[0] != plan.n_cols:
+        raise _lib.CtgcnError(f"x has {x.shape[0]} rows, the plan expects {plan.n_cols}")
+    w_ih, w_hh, b_ih, b_hh, ln_w, ln_b = (_vec(t, nm) for t, nm in
+                                           ((w_ih, "w_ih"), (w_hh, "w_hh"), (b_ih, "b_ih"), (b_hh, "b_hh"),
+                                            (ln_w, "ln_w"), (ln_b, "ln_b")))
+    if tuple(w_ih.shape) != (3 * h, d_in):
+        raise _lib.CtgcnError(f"w_ih shape {tuple(w_ih.shape)} does not match input width {d_in} / hidden {h}")
+    if out is None:
+        out = torch.empty(plan.n_rows, h, dtype=torch.float32, device=x.device)
+    if out.stride(1) != 1 or tuple(out.shape) != (plan.n_rows, h):
+        raise _lib.CtgcnError("out must be [N, H] with a contiguous last dim")
+    ws_bytes = _lib.lib.ctgcn_core_diffusion_workspace_bytes(plan.handle, d_in, h)
+    ws = _workspace(ws_bytes, x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib.ctgcn_core_diffusion_fwd(plan.handle, _ptr(x), x.stride(0), d_in, h, _ptr(w_ih), _ptr(w_hh),
+                                                     _ptr(b_ih), _ptr(b_hh), _ptr(ln_w), _ptr(ln_b), float(eps), _ptr(out),
+                                                     out.stride(0), _ptr(ws), ws_bytes, _stream()),
+                   "ctgcn_core_diffusion_fwd")
+    return out
+
+
+def linear(x, w, b, act: int):
+    """act(x wᵀ + b) for dense x [N, d_in]."""
+    x = _f32_rows(x, "x")
+    w, b = _vec(w, "weight"), _vec(b, "bias")
+    d_out, d_in = w.shape
+    if x.shape[1] != d_in:
+        raise _lib.CtgcnError(f"x width {x.shape[1]} != weight in_features {d_in}")
+    y = torch.empty(x.shape[0], d_out, dtype=torch.float32, device=x.device)
+    ws_bytes = _lib.lib.ctgcn_linear_workspace_bytes(d_in, d_out)
+    ws = _workspace(ws_bytes, x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib.ctgcn_linear_fwd(_ptr(x), x.stride(0), x.shape[0], d_in, _ptr(w), _ptr(b), d_out, act, _ptr(y),
+                                             y.stride(0), _ptr(ws), ws_bytes, _stream()), "ctgcn_linear_fwd")
+    return y
+
+
+def spmm_linear(x_plan: GraphPlan, w, b, act: int):
+    """act(x wᵀ + b) for a sparse x given as a K=1 plan of shape [N, d_in]."""
+    w, b = _vec(w, "weight"), _vec(b, "bias")
+    d_out, d_in = w.shape
+    if x_plan.n_cols != d_in:
+        raise _lib.CtgcnError(f"sparse x width {x_plan.n_cols} != weight in_features {d_in}")
+    y = torch.empty(x_plan.n_rows, d_out, dtype=torch.float32, device=w.device)
+    ws_bytes = _lib.lib.ctgcn_linear_workspace_bytes(d_in, d_out)
+    ws = _workspace(ws_bytes, w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.lib.ctgcn_spmm_linear_fwd(x_plan.handle, _ptr(w), _ptr(b), d_out, act, _ptr(y), y.stride(0), _ptr(ws),
+                                                  ws_bytes, _stream()), "ctgcn_spmm_linear_fwd")
+    return y

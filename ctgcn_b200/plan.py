@@ -1,0 +1,159 @@
+"""Graph plans: the reference's per-snapshot ``adj_list`` (K torch sparse COO matrices, helper.py:51-82)
+merged once into a level-tagged union CSR on the device (ctgcn_plan_create_coo).
+
+The reference hands the SAME ``adj_list`` objects to ``model(x_list, adj_list)`` on every batch of every
+epoch (embedding.py:346), so plans are cached per list identity and validated by the storage pointers of
+their index tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_CACHE_SIZE = 256
+
+
+class GraphPlan:
+    """Owner of one opaque ``ctgcn_plan*``."""
+
+    def __init__(self, handle: int, device: torch.device):
+        self._h = C.c_void_p(handle)
+        self.device = device
+        st = (C.c_int64 * 8)()
+        _lib.check(_lib.lib.ctgcn_plan_stats(self._h, st), "ctgcn_plan_stats")
+        (self.n_rows, self.n_cols, self.k, self.entries, self.nnz_raw_sum, self.nnz_coalesced, self.n_oneshot,
+         self.device_bytes) = [int(v) for v in st]
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise _lib.CtgcnError("plan already destroyed")
+        return self._h
+
+    def destroy(self):
+        if getattr(self, "_h", None) is not None:
+            _lib.lib.ctgcn_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    def arrays(self):
+        """Copies of (rowptr, col, val, level) as torch tensors (tests / inspection only)."""
+        out = [torch.empty(cnt, dtype=dt, device=self.device)
+               for dt, cnt in zip((torch.int32, torch.int32, torch.float32, torch.uint8),
+                                  (self.n_rows + 1, self.entries, self.entries, self.entries))]
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib.ctgcn_plan_arrays(self.handle, *[C.c_void_p(t.data_ptr()) for t in out],
+                                                  C.c_void_p(stream)), "ctgcn_plan_arrays")
+        return out
+
+
+def _coo_parts(m, device):
+    """(rows int64, cols int64, vals fp32, shape) of one matrix as contiguous device tensors."""
+    if isinstance(m, torch.Tensor):
+        if m.layout != torch.sparse_coo:
+            raise TypeError("adjacency / sparse feature matrices must be torch sparse COO tensors")
+        idx, val = m._indices(), m._values()
+        shape = tuple(m.shape)
+    else:  # scipy sparse
+        mc = m.tocoo()
+        idx = torch.from_numpy(np.vstack((mc.row, mc.col)).astype(np.int64))
+        val = torch.from_numpy(mc.data.astype(np.float32))
+        shape = mc.shape
+    idx = idx.to(device=device, dtype=torch.int64)
+    val = val.to(device=device, dtype=torch.float32).contiguous()
+    return idx[0].contiguous(), idx[1].contiguous(), val, shape
+
+
+def build_plan_coo(mats, device) -> GraphPlan:
+    """ctgcn_plan_create_coo over a list of K COO matrices of one common shape."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.CtgcnError("graph plans live on a CUDA device; got " + str(device))
+    k = len(mats)
+    if not 1 <= k <= _lib.MAX_CORES:
+        raise _lib.CtgcnError(f"adj_list must hold 1..{_lib.MAX_CORES} matrices, got {k}")
+    parts = [_coo_parts(m, device) for m in mats]
+    shape = parts[0][3]
+    for p in parts:
+        if tuple(p[3]) != tuple(shape):
+            raise _lib.CtgcnError("all matrices of one adj_list must share one shape")
+    rows = (C.c_void_p * k)(*[p[0].data_ptr() for p in parts])
+    cols = (C.c_void_p * k)(*[p[1].data_ptr() for p in parts])
+    vals = (C.c_void_p * k)(*[p[2].data_ptr() for p in parts])
+    nnz = (C.c_int64 * k)(*[p[2].numel() for p in parts])
+    out = C.c_void_p()
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib.ctgcn_plan_create_coo(shape[0], shape[1], k, rows, cols, vals, nnz, 1, C.c_void_p(stream),
+                                                  C.byref(out)), "ctgcn_plan_create_coo")
+    return GraphPlan(out.value, device)
+
+
+def build_plan_csr(n_rows, n_cols, k, rowptr, col, val, level, nnz_raw_sum, device) -> GraphPlan:
+    """ctgcn_plan_create_csr from host (numpy) or device (torch) arrays of an already merged union CSR."""
+    device = torch.device(device)
+    on_device = isinstance(rowptr, torch.Tensor) and rowptr.is_cuda
+    if on_device:
+        arrs = [rowptr.to(torch.int32).contiguous(), col.to(torch.int32).contiguous(),
+                val.to(torch.float32).contiguous(), level.to(torch.uint8).contiguous()]
+        ptrs = [a.data_ptr() for a in arrs]
+    else:
+        arrs = [np.ascontiguousarray(rowptr, dtype=np.int32), np.ascontiguousarray(col, dtype=np.int32),
+                np.ascontiguousarray(val, dtype=np.float32), np.ascontiguousarray(level, dtype=np.uint8)]
+        ptrs = [a.ctypes.data for a in arrs]
+    out = C.c_void_p()
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib.ctgcn_plan_create_csr(n_rows, n_cols, k, *[C.c_void_p(p) for p in ptrs], int(nnz_raw_sum),
+                                                  1 if on_device else 0, C.c_void_p(stream), C.byref(out)),
+                   "ctgcn_plan_create_csr")
+    return GraphPlan(out.value, device)
+
+
+_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
+
+
+def _signature(mats):
+    sig = []
+    for m in mats:
+        if isinstance(m, torch.Tensor):
+            sig.append((m._indices().data_ptr(), m._values().data_ptr(), m._nnz(), m._values()._version))
+        else:
+            sig.append((id(m), m.nnz))
+    return tuple(sig)
+
+
+def plan_for(adj_list, device) -> GraphPlan:
+    """Cached plan of one snapshot's adj_list (or of a single sparse feature matrix wrapped in a list)."""
+    if isinstance(adj_list, GraphPlan):
+        return adj_list
+    key = (id(adj_list), str(device))
+    if isinstance(adj_list, torch.Tensor) or hasattr(adj_list, "tocoo"):
+        mats = [adj_list]  # a single sparse matrix (MLP input features)
+    else:
+        mats = list(adj_list)
+    sig = _signature(mats)
+    hit = _cache.get(key)
+    if hit is not None and hit[0] == sig:
+        _cache.move_to_end(key)
+        return hit[1]
+    plan = build_plan_coo(mats, device)
+    _cache[key] = (sig, plan, adj_list)  # keep the list alive so that id() stays unique while cached
+    while len(_cache) > _CACHE_SIZE:
+        _cache.popitem(last=False)
+    return plan
+
+
+def clear_cache():
+    _cache.clear()

@@ -1,0 +1,138 @@
+/* ctgcn_b200 — C-ABI of the B200-native CTGCN forward hot path.
+ *
+ * The reference (jhljx/CTGCN) is pure Python: its "operator API" for this path is the
+ * torch.nn.Module surface of layers.py / models.py, whose arithmetic is delegated to torch
+ * library calls.  Each entry point below replaces one group of those call sites (cited as
+ * reference file:line, relative to the reference repo root).  Python modules with the
+ * reference's exact signatures (ctgcn_b200/layers.py, ctgcn_b200/models.py) bind these
+ * through ctypes; see INTEGRATION.md for the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative CTGCN_E* code on failure; the message is
+ *    available (thread-local) from ctgcn_last_error().  Nothing throws across the ABI.
+ *  - all tensor pointers are DEVICE pointers to fp32 row-major data unless the name says host;
+ *    `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - compute entry points never allocate, never free caller memory and never synchronise the
+ *    stream.  Scratch comes from a caller-owned workspace whose size is queried first.
+ *  - the library owns only opaque plan handles (ctgcn_plan) and their device arrays.
+ */
+#ifndef CTGCN_B200_H
+#define CTGCN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTGCN_OK 0
+#define CTGCN_EINVAL (-1)   /* bad argument / unsupported shape           */
+#define CTGCN_ECUDA (-2)    /* a CUDA runtime call or kernel launch failed */
+#define CTGCN_ENOMEM (-3)   /* workspace too small / allocation failed     */
+#define CTGCN_ENODEV (-4)   /* no usable sm_100 device                     */
+
+#define CTGCN_MAX_CORES 64
+
+/* activation codes for ctgcn_linear_fwd / ctgcn_spmm_linear_fwd (layers.py:98-99,104-105) */
+#define CTGCN_ACT_NONE 0
+#define CTGCN_ACT_SELU 1
+
+/* output modes of ctgcn_gru_seq_fwd */
+#define CTGCN_GRU_SUM_LN 0  /* y[n,:]   = LayerNorm(sum_s h_s)   layers.py:59-62  */
+#define CTGCN_GRU_EACH_LN 1 /* y[n,s,:] = LayerNorm(h_s)         models.py:249-250 */
+
+/* implementation selector (ctgcn_set_gru_impl): both are CUDA; AUTO picks tcgen05 when shapes allow */
+#define CTGCN_IMPL_AUTO 0
+#define CTGCN_IMPL_SIMT 1
+#define CTGCN_IMPL_TCGEN05 2
+
+typedef struct ctgcn_plan ctgcn_plan;
+
+int ctgcn_version(void);
+const char* ctgcn_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t ctgcn_launch_count(void);
+int ctgcn_device_check(void); /* 0 iff the current device is compute capability 10.x */
+
+/* ---------------------------------------------------------------- graph plan
+ * Replaces the per-call work torch.sparse.mm does on the reference's adj_list
+ * (layers.py:41-45: K uncoalesced COO matrices, helper.py:51-82 / utils.py:89-95).
+ * The K matrices of ONE snapshot are merged once into a "union CSR": every distinct (row,col)
+ * is stored once with the first core index it belongs to ("level"); entries that are not a
+ * suffix of the core list (e.g. the +I diagonal that helper.py:72 adds to the first matrix only,
+ * or any non-nested / per-core-weighted entry) are stored as "one-shot" entries of their level.
+ * Duplicate COO entries inside one matrix are summed (torch.sparse.mm semantics).
+ *
+ * rows/cols: K pointers to int64 index arrays, vals: K pointers to fp32, nnz: K counts (host array).
+ * on_device != 0: index/value arrays are device pointers, else host pointers.
+ * n_rows x n_cols is the (common) shape; the adjacency case has n_rows == n_cols.
+ * Synchronises the stream (one-off build). */
+int ctgcn_plan_create_coo(int64_t n_rows, int64_t n_cols, int k, const int64_t* const* rows,
+                          const int64_t* const* cols, const float* const* vals, const int64_t* nnz,
+                          int on_device, void* stream, ctgcn_plan** out);
+
+/* Same plan from an already merged CSR: rowptr[n_rows+1] int32, col/val/level per entry; level byte =
+ * first core index (bits 0..6) | 0x80 for one-shot entries; entries of a row sorted by level.
+ * nnz_raw_sum is recorded for statistics only (sum of the K matrices' stored non-zeros). */
+int ctgcn_plan_create_csr(int64_t n_rows, int64_t n_cols, int k, const int32_t* rowptr, const int32_t* col,
+                          const float* val, const uint8_t* level, int64_t nnz_raw_sum, int on_device,
+                          void* stream, ctgcn_plan** out);
+int ctgcn_plan_destroy(ctgcn_plan* plan);
+/* stats[0..7] = n_rows, n_cols, k, entries in the union CSR, sum of raw nnz, sum of coalesced nnz,
+ *               one-shot entries, device bytes held */
+int ctgcn_plan_stats(const ctgcn_plan* plan, int64_t stats[8]);
+/* copy the plan arrays into caller-owned DEVICE buffers (any may be NULL to skip): rowptr[n_rows+1],
+ * col/val/level[entries].  For tests / inspection; asynchronous on `stream`. */
+int ctgcn_plan_arrays(const ctgcn_plan* plan, int32_t* rowptr, int32_t* col, float* val, uint8_t* level, void* stream);
+
+/* ---------------------------------------------------------------- cumulative k-core SpMM
+ * layers.py:41-48:  S_i = S_{i-1} + A_i x ; U_i = relu(S_i)   for i = 0..K-1, in ONE pass over the
+ * union CSR.  x: [n_cols, d] with row stride ldx (elements); u: [n_rows, K, d] contiguous. */
+int ctgcn_cumspmm_fwd(const ctgcn_plan* plan, const float* x, int64_t ldx, int d, float* u, void* stream);
+
+/* ---------------------------------------------------------------- GRU over a short sequence + LayerNorm
+ * layers.py:59-62 (sequence = core axis, mode SUM_LN) and models.py:249-250 (sequence = snapshot axis,
+ * mode EACH_LN).  nn.GRU(num_layers=1, batch_first=True), h0 = 0, PyTorch packing [r;z;n]:
+ *   w_ih [3H, d_in], w_hh [3H, H], b_ih/b_hh [3H] or NULL (bias=False).
+ * seq element (n, s, j) is read at seq[n*seq_row_stride + s*seq_step_stride + j].
+ * SUM_LN : y[n*y_row_stride + j];  EACH_LN: y[n*y_row_stride + s*y_step_stride + j].
+ * workspace: ctgcn_gru_workspace_bytes(d_in, h) bytes (packed weights). */
+size_t ctgcn_gru_workspace_bytes(int d_in, int h);
+int ctgcn_gru_seq_fwd(const float* seq, int64_t seq_row_stride, int64_t seq_step_stride, int64_t n, int steps,
+                      int d_in, int h, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                      const float* ln_w, const float* ln_b, float eps, int mode, float* y, int64_t y_row_stride,
+                      int64_t y_step_stride, void* workspace, size_t workspace_bytes, void* stream);
+int ctgcn_set_gru_impl(int impl);
+
+/* ---------------------------------------------------------------- CoreDiffusion.forward (layers.py:38-63)
+ * y[n_rows, h] (row stride ldy) = LayerNorm(sum_i GRU(relu(cumsum_i A_i x))).
+ * workspace: ctgcn_core_diffusion_workspace_bytes(plan, d_in, h). */
+size_t ctgcn_core_diffusion_workspace_bytes(const ctgcn_plan* plan, int d_in, int h);
+int ctgcn_core_diffusion_fwd(const ctgcn_plan* plan, const float* x, int64_t ldx, int d_in, int h,
+                             const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                             const float* ln_w, const float* ln_b, float eps, float* y, int64_t ldy,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- MLP layers (layers.py:95-106)
+ * dense:  y[n, d_out] = act(x[n, d_in] w^T + b),  w [d_out, d_in] (nn.Linear layout), b may be NULL.
+ * workspace: ctgcn_linear_workspace_bytes(d_in, d_out). */
+size_t ctgcn_linear_workspace_bytes(int64_t d_in, int64_t d_out);
+int ctgcn_linear_fwd(const float* x, int64_t ldx, int64_t n, int64_t d_in, const float* w, const float* b,
+                     int64_t d_out, int act, float* y, int64_t ldy, void* workspace, size_t workspace_bytes,
+                     void* stream);
+/* sparse COO input (the one-hot identity of helper.py:169-172, the 'combine'/'adj' degree features of
+ * helper.py:136-155): x given as a K=1 plan of shape [n, d_in].  Same workspace size query. */
+int ctgcn_spmm_linear_fwd(const ctgcn_plan* x_plan, const float* w, const float* b, int64_t d_out, int act,
+                          float* y, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- host helper (no GPU needed)
+ * Exact k-core numbers by bucket peeling (replaces networkx.core_number used at
+ * preprocessing/structure_generation.py:35 for the synthetic generators).  CSR of an undirected simple
+ * graph: rowptr int64[n+1], col int32[rowptr[n]]; core_out int32[n]. */
+int ctgcn_kcore_numbers(int64_t n, const int64_t* rowptr, const int32_t* col, int32_t* core_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTGCN_B200_H */

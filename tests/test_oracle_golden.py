@@ -1,0 +1,89 @@
+"""The oracle restatements against the golden vectors generated from the unmodified reference
+(oracle/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, oracle_np, oracle_torch
+
+TOL = 5e-6  # fp32 reference vs fp64 restatement / same-op torch port
+
+
+def _tsd(sd):
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
+
+
+def _coo(mats):
+    return [oracle_torch.to_torch_coo(m) for m in mats]
+
+
+@pytest.mark.parametrize("name", cases.golden_names("core_diffusion"))
+def test_core_diffusion(name):
+    c = cases.load_case(name)
+    y64 = oracle_np.core_diffusion(c["x"], c["adj"], c["sd"])
+    assert cases.relerr(y64, c["expected"]["y"]) < TOL
+    if c["adj"][0].shape[0] <= 400:
+        yt = oracle_torch.core_diffusion(torch.from_numpy(c["x"]), _coo(c["adj"]), _tsd(c["sd"])).numpy()
+        assert cases.relerr(yt, c["expected"]["y"]) < TOL
+    u = oracle_np.cumulative_core_sums(c["x"].astype(np.float64), c["adj"])
+    np.testing.assert_allclose(u.sum(axis=2), c["expected"]["u_sum"], rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", cases.golden_names("mlp"))
+def test_mlp(name):
+    c = cases.load_case(name)
+    m = c["meta"]
+    y64 = oracle_np.mlp(c["x"], c["sd"], "", m["layer_num"], m["act"])
+    assert cases.relerr(y64, c["expected"]["y"]) < TOL
+    xt = torch.from_numpy(c["x"]) if isinstance(c["x"], np.ndarray) else oracle_torch.to_torch_coo(c["x"])
+    yt = oracle_torch.mlp(xt, _tsd(c["sd"]), "", m["layer_num"], m["act"]).numpy()
+    assert cases.relerr(yt, c["expected"]["y"]) < TOL
+
+
+@pytest.mark.parametrize("name", cases.golden_names("cdn"))
+def test_cdn(name):
+    c = cases.load_case(name)
+    y64 = oracle_np.cdn(c["x"], c["adj"], c["sd"], "", c["meta"]["diffusion_num"])
+    assert cases.relerr(y64, c["expected"]["y"]) < TOL
+
+
+def _model_out(c, res):
+    m = c["meta"]
+    out, trans = res if m["model_type"] == "S" else (res, None)
+    out = np.stack([np.asarray(o) for o in out]) if isinstance(out, (list, tuple)) else np.asarray(out)
+    if out.ndim == 2:
+        out = out[None]
+    if trans is not None:
+        trans = np.stack([np.asarray(t) for t in trans]) if isinstance(trans, (list, tuple)) else np.asarray(trans)[None]
+    rs = m["row_stride"]
+    return out[:, ::rs], None if trans is None else trans[:, ::rs]
+
+
+@pytest.mark.parametrize("name", cases.golden_names("cgcn") + cases.golden_names("ctgcn"))
+def test_models(name):
+    c = cases.load_case(name)
+    m = c["meta"]
+    if m["n"] > 500 and m["hid"] > 100:
+        pytest.skip("large UCI case: covered by make_golden.py at generation time and by the GPU parity test")
+    if m["kind"] == "ctgcn":
+        res = oracle_np.ctgcn(c["x_list"], c["adj_lists"], c["sd"], m["trans_num"], m["diffusion_num"], m["model_type"], m["act"])
+    else:
+        xs, adj = (c["x_list"][0], c["adj_lists"][0]) if m["single"] else (c["x_list"], c["adj_lists"])
+        res = oracle_np.cgcn(xs, adj, c["sd"], m["trans_num"], m["diffusion_num"], m["model_type"], m["act"])
+    y, tr = _model_out(c, res)
+    assert cases.relerr(y, c["expected"]["y"]) < TOL
+    if tr is not None:
+        assert cases.relerr(tr, c["expected"]["trans"]) < TOL
+
+
+def test_build_core_adj_list_semantics():
+    import scipy.sparse as sp
+    a3 = sp.csr_matrix(np.array([[0, 1, 0], [1, 0, 0], [0, 0, 0]], dtype=float))
+    a2 = a3.copy()                       # identical to the previous level → dropped (helper.py:74-76)
+    a1 = sp.csr_matrix(np.array([[0, 1, 1], [1, 0, 0], [1, 0, 0]], dtype=float))
+    adj, mc = oracle_np.build_core_adj_list([a1, a2, a3])
+    assert mc == 3 and len(adj) == 2
+    assert (adj[0].toarray() == a3.toarray() + np.eye(3)).all()   # +I on the first (densest-index) entry only
+    assert (adj[1].toarray() == a1.toarray()).all()
+    adj2, mc2 = oracle_np.build_core_adj_list([a1, a2, a3], max_core=2)  # sticky max_core keeps files [:2]
+    assert mc2 == 2 and len(adj2) == 2 and (adj2[0].toarray() == a2.toarray() + np.eye(3)).all()
