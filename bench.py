@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the CTGCN forward hot path on B200 (the contract the driver relies on).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg4|cfg2|tiny] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N … bench.py --gpus N …
+
+One "step" = one CTGCN.forward over the T synthetic snapshots of the workload (MLP_t → CoreDiffusion_t for
+every snapshot, exchange, temporal GRU + LayerNorm).  metric = edges-aggregated/s where
+E_agg = Σ_t Σ_layers Σ_i nnz(A_{t,i}): the stored non-zeros the reference's K torch.sparse.mm
+calls per layer consume, credited although the union-pass kernel reads every distinct edge once.
+
+  value      device-resident inputs, CUDA events, max over ranks
+  e2e        same step through the public module API from pinned HOST buffers: H2D of the step's features
+             and D2H of the output embeddings inside the timed region
+  roofline   dominant kernel class, timed live by the library's per-launch CUDA events (ctgcn_prof_*)
+  cpu_baseline  oracle/oracle_torch.py (same torch CPU library calls as the reference) on the host cores,
+             bounded sample, thread count swept
+Multi-GPU: snapshot t lives on rank t mod G (strong scaling: the workload is fixed as G grows).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # BASELINE.json configs[3]: the configuration the metric's targets are quoted on; fits one B200
+    "cfg4": dict(kind="er", n=1_000_000, m=10_000_000, K=10, T=8, D=128,
+                 name="synthetic ER 1M nodes / 10M edges, K=10 cores, T=8 snapshots, 128-d"),
+    # BASELINE.json configs[1]
+    "cfg2": dict(kind="er", n=100_000, m=1_000_000, K=5, T=8, D=128,
+                 name="synthetic ER 100K nodes / 1M edges, K=5 cores, T=8 snapshots, 128-d"),
+    "tiny": dict(kind="er", n=4_000, m=30_000, K=4, T=8, D=128, name="tiny ER smoke workload"),
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]),
+                    tf_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU baseline
+def cpu_reference_sample(cfg, seconds_budget=25.0):
+    """Time the torch-CPU port of the reference path (oracle/oracle_torch.py: torch.sparse.mm ×K, nn.GRU, LayerNorm,
+    nn.Linear — the same library calls the reference makes) on ONE snapshot's MLP + CoreDiffusion, thread count swept."""
+    import numpy as np
+    import torch
+    from ctgcn_b200 import synth
+    from oracle import cases, oracle_torch
+
+    n = min(cfg["n"], 100_000)
+    m = int(cfg["m"] * (n / cfg["n"]))
+    snap = synth.make_snapshot(cfg["kind"], n, m, cfg["K"], seed=0)
+    adj = snap.coo_list("cpu")
+    d = cfg["D"]
+    x = synth.features(n, d, 1000)
+    sd = {k: torch.from_numpy(v) for k, v in cases.ctgcn_params(np.random.default_rng(0), d, d, d, 1, 1, 1, "C").items()}
+
+    def run():
+        with torch.no_grad():
+            h = oracle_torch.mlp(x, sd, "mlp_list.0.", 1, "L")
+            return oracle_torch.cdn(h, adj, sd, "duffision_list.0.", 1)
+
+    cores = os.cpu_count() or 1
+    cand = sorted({c for c in (1, 2, 4, 8, 16, 32, 64, 128, cores) if c <= cores})
+    best, best_thr, spent = None, None, 0.0
+    for thr in cand:
+        torch.set_num_threads(thr)
+        t0 = time.perf_counter()
+        run()                                    # warm-up for this thread count
+        warm = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        run()
+        dt = time.perf_counter() - t0
+        spent += warm + dt
+        if best is None or dt < best:
+            best, best_thr = dt, thr
+        if spent > seconds_budget:
+            break
+    sample = (f"1 snapshot MLP+CoreDiffusion fwd, {cfg['kind'].upper()} N={n} m={m} K={snap.k} D={d} "
+              f"(E_agg={snap.edges_aggregated}); best of thread counts {cand} = {best_thr} threads on {cores} cores; "
+              f"same density/K as the workload" + ("" if n == cfg["n"] else f", node count reduced from {cfg['n']}"))
+    return dict(value=snap.edges_aggregated / best, unit="edges-aggregated/s", cores=best_thr, kind="port", sample=sample,
+                seconds=best, host_cores=cores)
+
+
+def run_reference_arm(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    times = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base = cpu_reference_sample(cfg, seconds_budget=12.0 if i else 25.0)
+        if i >= args.warmup:
+            times.append(base["seconds"])
+        if sum(times) > 150:
+            break
+    t = sum(times) / len(times)
+    val = base["value"] * base["seconds"] / t
+    line = {"metric": "edges-aggregated/s, CTGCN CoreDiffusion forward", "value": val, "unit": "edges-aggregated/s",
+            "impl": "reference", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": t * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["name"]},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": val, "unit": "edges-aggregated/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line["cpu_baseline"]["value"] = val
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="cfg4", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--gru-impl", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="all_to_all", choices=["all_to_all", "all_gather"])
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as td
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        td.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        td.barrier()
+    import ctgcn_b200 as pkg
+    from ctgcn_b200 import _lib, dist, synth
+
+    assert _lib.lib.ctgcn_device_check() == 0, _lib.last_error()
+    _lib.set_gru_impl({"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tcgen05": _lib.IMPL_TCGEN05}[args.gru_impl])
+    peaks = load_peaks()
+    T, n, d, K = cfg["T"], cfg["n"], cfg["D"], cfg["K"]
+
+    # ---- workload: this rank's snapshots (graph rng seed = t, features seed = 1000 + t, weights seed 0)
+    owned = dist.owned_snapshots(T, world, rank)
+    t_setup = time.perf_counter()
+    plans, x_host, x_dev, stats = [None] * T, [None] * T, [None] * T, {}
+    for t in owned:
+        snap = synth.make_snapshot(cfg["kind"], n, cfg["m"], K, seed=t)
+        plans[t] = snap.plan(dev)
+        x_host[t] = synth.features(n, d, 1000 + t).pin_memory()
+        x_dev[t] = x_host[t].to(dev)
+        stats[t] = dict(k=snap.k, entries=snap.entries, e_agg=snap.edges_aggregated)
+        del snap
+    torch.manual_seed(0)
+    model = pkg.CTGCN(d, d, d, 1, 1, T, model_type="C", trans_activate_type="L").to(dev).eval()
+    model.gather_output = False      # every rank keeps (and, in e2e, reads back) its node slice of the output
+    model.exchange = args.exchange
+    model.node_num = n
+    setup_s = time.perf_counter() - t_setup
+
+    def tot(v):
+        if world == 1:
+            return v
+        tt = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        td.all_reduce(tt)
+        return tt.item()
+
+    e_agg_local = sum(s["e_agg"] for s in stats.values())
+    e_agg = tot(e_agg_local)                                   # one CoreDiffusion layer per snapshot in this workload
+    entries_total = tot(sum(s["entries"] for s in stats.values()))
+
+    def step_resident():
+        with torch.no_grad():
+            return model(x_dev, plans)
+
+    out_pinned = {}
+
+    def step_e2e():
+        xs = [None] * T
+        for t in owned:
+            xs[t] = x_host[t].to(dev, non_blocking=True)
+        with torch.no_grad():
+            out = model(xs, plans)
+        key = tuple(out.shape)
+        if key not in out_pinned:
+            out_pinned[key] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+        out_pinned[key].copy_(out, non_blocking=True)
+        return out
+
+    def timed(fn, steps, warmup, prof=False):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+        if prof:
+            _lib.prof_collect(reset=True)
+            _lib.prof_enable(True)
+        l0 = _lib.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        launches = _lib.launch_count() - l0
+        kern = None
+        if prof:
+            _lib.prof_enable(False)
+            kern = _lib.prof_collect(reset=True)
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            td.all_reduce(tt, op=td.ReduceOp.MAX)
+            ms = tt.item()
+        return ms, launches, kern
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches, kern = timed(step_resident, args.steps, args.warmup, prof=True)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _, _ = timed(step_e2e, args.steps, 1)
+    launches_total = int(tot(launches))
+
+    # ---- correctness guard on the measured configuration: finite output of the right shape
+    out = step_resident()
+    rows = dist.node_slices(n, world)[rank]
+    assert tuple(out.shape) == (T, rows[1] - rows[0], d) and bool(torch.isfinite(out).all())
+
+    if rank != 0:
+        if world > 1:
+            td.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel class (this rank's launches; every rank runs the same kernels)
+    L = len(owned)
+    spmm_bytes = sum(s["entries"] * (9 + 4 * d) + n * 4 + s["k"] * n * 4 * d for s in stats.values()) / max(L, 1)
+    gru_core_flops = sum(n * s["k"] * 6 * d * (d + d) for s in stats.values())
+    rows_n = rows[1] - rows[0]
+    gru_temporal_flops = rows_n * T * 6 * d * (d + d)
+    by_kernel = {}
+    if kern["spmm"]["launches"]:
+        avg = kern["spmm"]["ms"] / kern["spmm"]["launches"]
+        by_kernel["cumspmm"] = {"bound": "hbm", "achieved": spmm_bytes / (avg * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                                "avg_ms": avg, "launches": kern["spmm"]["launches"], "share_of_step": kern["spmm"]["ms"] / ms,
+                                "algorithmic_bytes_per_launch": spmm_bytes}
+    if kern["gru"]["launches"]:
+        flops = (gru_core_flops + gru_temporal_flops) * args.steps
+        by_kernel["gru_seq"] = {"bound": "tensor", "achieved": flops / (kern["gru"]["ms"] * 1e-3) / 1e12, "peak": peaks["tf_sustained"],
+                                "unit": "TFLOP/s", "avg_ms": kern["gru"]["ms"] / kern["gru"]["launches"],
+                                "launches": kern["gru"]["launches"], "share_of_step": kern["gru"]["ms"] / ms,
+                                "algorithmic_flops_per_step": gru_core_flops + gru_temporal_flops}
+    for v in by_kernel.values():
+        v["frac"] = v["achieved"] / v["peak"]
+        v["traffic"] = None
+    other_ms = {k: v["ms"] for k, v in kern.items() if k not in ("spmm", "gru")}
+    dominant = max(by_kernel, key=lambda k: by_kernel[k]["share_of_step"]) if by_kernel else None
+    roofline = dict(by_kernel[dominant], kernel=dominant, peak_source=peaks["source"]) if dominant else None
+
+    ms_step = ms / args.steps
+    value = e_agg / (ms_step * 1e-3)
+    h2d = tot(len(owned) * n * d * 4)
+    d2h = T * n * d * 4
+    line = {
+        "metric": "edges-aggregated/s, CTGCN CoreDiffusion forward", "value": value, "unit": "edges-aggregated/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["name"], "config": args.config, "parallelism": f"snapshot-parallel x{world}, exchange={args.exchange}",
+                   "layers": "MLP 1x(128->128,'L') + CDN 1 layer + temporal GRU", "edges_aggregated_per_step": e_agg,
+                   "union_entries_total": entries_total, "cores_per_snapshot": [s["k"] for s in stats.values()],
+                   "l2": "per-step inputs (features + graph plans + per-core sums) exceed the 126 MB L2 several times over; no flush",
+                   "gru_impl": args.gru_impl, "setup_s": round(setup_s, 1)},
+        "e2e": {"value": e_agg / (ms_e2e / args.steps * 1e-3), "unit": "edges-aggregated/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": launches_total,
+        "clocks": clocks,
+        "roofline": roofline,
+        "roofline_by_kernel": by_kernel,
+        "other_kernel_ms": other_ms,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        base = cpu_reference_sample(cfg)
+        line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -36,6 +36,8 @@ SIGNATURES = {
     "ctgcn_last_error": (C.c_char_p, []),
     "ctgcn_launch_count": (_i64, []),
     "ctgcn_device_check": (C.c_int, []),
+    "ctgcn_prof_enable": (C.c_int, [_i32]),
+    "ctgcn_prof_collect": (C.c_int, [_p, _p, _i32]),
     "ctgcn_plan_create_coo": (C.c_int, [_i64, _i64, _i32, _p, _p, _p, _p, _i32, _p, _p]),
     "ctgcn_plan_create_csr": (C.c_int, [_i64, _i64, _i32, _p, _p, _p, _p, _i64, _i32, _p, _p]),
     "ctgcn_plan_destroy": (C.c_int, [_p]),
@@ -71,6 +73,20 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(lib.ctgcn_launch_count())
+
+
+PROF_CLASSES = ("spmm", "gru", "linear", "pack", "spmm_linear")
+
+
+def prof_enable(on: bool) -> None:
+    check(lib.ctgcn_prof_enable(1 if on else 0), "ctgcn_prof_enable")
+
+
+def prof_collect(reset: bool = True) -> dict:
+    ms = (C.c_double * len(PROF_CLASSES))()
+    cnt = (C.c_int64 * len(PROF_CLASSES))()
+    check(lib.ctgcn_prof_collect(ms, cnt, 1 if reset else 0), "ctgcn_prof_collect")
+    return {n: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, n in enumerate(PROF_CLASSES)}
 
 
 def set_gru_impl(impl: int) -> None:

@@ -1,6 +1,6 @@
 """In-tree build of libctgcn_b200.so (hand-written CUDA for sm_100a behind a C-ABI).
 
-    python -m ctgcn_b200.build [--force] [--verbose]
+    python ctgcn_b200/build.py [--force] [--verbose]     (run by path: the package itself needs the .so)
 
 nvcc cross-compiles without a GPU.  The .so stays next to this file (git-ignored, but it
 travels with gpurun snapshots) so that the GPU box loads exactly what was built here.

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -11,6 +12,30 @@ namespace ctgcn {
 static thread_local char g_err[1024] = "";
 std::atomic<int64_t> g_launches{0};
 static std::atomic<int> g_gru_impl{CTGCN_IMPL_AUTO};
+
+// ---- per-kernel-class timing
+static std::atomic<int> g_prof_on{0};
+struct ProfRec {
+    int cls;
+    cudaEvent_t a, b;
+};
+static std::vector<ProfRec> g_prof_recs;
+static std::mutex g_prof_mu;
+
+ProfScope::ProfScope(int cls, cudaStream_t st) : cls_(cls), st_(st) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    cudaEvent_t a;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&stop_) != cudaSuccess) {
+        stop_ = nullptr;
+        return;
+    }
+    cudaEventRecord(a, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_recs.push_back({cls, a, stop_});
+}
+ProfScope::~ProfScope() {
+    if (stop_) cudaEventRecord(stop_, st_);
+}
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -43,6 +68,36 @@ extern "C" int ctgcn_device_check(void) {
     if (prop.major != 10) {
         set_error("device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
         return CTGCN_ENODEV;
+    }
+    return CTGCN_OK;
+}
+
+extern "C" int ctgcn_prof_enable(int on) {
+    g_prof_on.store(on ? 1 : 0);
+    return CTGCN_OK;
+}
+
+extern "C" int ctgcn_prof_collect(double* ms, int64_t* counts, int reset) {
+    CTGCN_REQUIRE(ms && counts, "prof_collect: NULL argument");
+    CTGCN_CUDA_OK(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int c = 0; c < PROF_NCLASS; ++c) {
+        ms[c] = 0.0;
+        counts[c] = 0;
+    }
+    for (auto& r : g_prof_recs) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+            ms[r.cls] += t;
+            counts[r.cls] += 1;
+        }
+    }
+    if (reset) {
+        for (auto& r : g_prof_recs) {
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+        g_prof_recs.clear();
     }
     return CTGCN_OK;
 }

@@ -46,6 +46,17 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Optional per-kernel-class device timing (ctgcn_prof_*): CUDA events recorded on the launching stream
+// around each launch while enabled; read back (with a device synchronise) by ctgcn_prof_collect.
+enum ProfClass { PROF_SPMM = 0, PROF_GRU = 1, PROF_LINEAR = 2, PROF_PACK = 3, PROF_SPMM_LINEAR = 4, PROF_NCLASS = 5 };
+struct ProfScope {
+    ProfScope(int cls, cudaStream_t st);
+    ~ProfScope();
+    int cls_;
+    cudaStream_t st_;
+    cudaEvent_t stop_ = nullptr;
+};
+
 }  // namespace ctgcn
 
 struct ctgcn_plan {

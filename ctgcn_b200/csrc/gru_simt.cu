@@ -298,6 +298,7 @@ int launch_gru_simt(const float* seq, int64_t srs, int64_t sss, int64_t n, int s
                     const float* wt_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
                     int mode, float* y, int64_t yrs, int64_t yss, cudaStream_t st) {
     constexpr size_t kMaxSmem = 227 * 1024;
+    ProfScope prof(PROF_GRU, st);
     if (gru_smem_bytes<8>(d_in, h) <= kMaxSmem)
         return launch_gru_t<8>(seq, srs, sss, n, steps, d_in, h, wt_ih, wt_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, st);
     CTGCN_REQUIRE(gru_smem_bytes<4>(d_in, h) <= kMaxSmem, "gru: d_in=%d, h=%d needs more than 227 KB of shared memory", d_in, h);
@@ -308,6 +309,7 @@ int launch_linear_simt(const float* x, int64_t ldx, int64_t n, int64_t d_in, con
                        int act, float* y, int64_t ldy, cudaStream_t st) {
     dim3 grid((unsigned)((n + 63) / 64), (unsigned)((d_out + FBW - 1) / FBW));
     CTGCN_REQUIRE(grid.y <= 65535, "linear: d_out too large");
+    ProfScope prof(PROF_LINEAR, st);
     linear_kernel<<<grid, THREADS, 0, st>>>(x, ldx, n, d_in, wt, b, d_out, act, y, ldy);
     CTGCN_LAUNCH_OK("linear_kernel");
     return CTGCN_OK;

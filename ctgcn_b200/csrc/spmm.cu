@@ -270,6 +270,7 @@ int launch_scalar(const ctgcn_plan* p, const float* x, int64_t ldx, int d, float
 
 int launch_cumspmm(const ctgcn_plan* p, const float* x, int64_t ldx, int d, float* u, bool relu, cudaStream_t st) {
     CTGCN_REQUIRE(d >= 1 && d <= 1024, "cumspmm: feature width %d outside [1,1024]", d);
+    ProfScope prof(PROF_SPMM, st);
     const bool vec_ok = (d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(u) & 15) == 0);
     if (vec_ok) {
@@ -289,6 +290,7 @@ int launch_cumspmm(const ctgcn_plan* p, const float* x, int64_t ldx, int d, floa
 
 int launch_spmm_linear(const ctgcn_plan* p, const float* wt, const float* b, int64_t d_out, int act, float* y, int64_t ldy,
                        cudaStream_t st) {
+    ProfScope prof(PROF_SPMM_LINEAR, st);
     const unsigned blocks = (unsigned)((p->n_rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     spmm_linear_kernel<4><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p->rowptr, p->col, p->val, wt, b, d_out, act, p->n_rows, y,
                                                                   ldy);
@@ -299,6 +301,7 @@ int launch_spmm_linear(const ctgcn_plan* p, const float* wt, const float* b, int
 int launch_transpose(const float* src, int64_t rows, int64_t cols, float* dst, cudaStream_t st) {
     dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
     CTGCN_REQUIRE(grid.y <= 65535, "transpose: too many rows (%lld)", (long long)rows);
+    ProfScope prof(PROF_PACK, st);
     transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(src, rows, cols, dst);
     CTGCN_LAUNCH_OK("transpose_kernel");
     return CTGCN_OK;

@@ -54,9 +54,9 @@ def exchange_to_node_slices(hx_local: torch.Tensor, T: int, group=None, mode: st
                              input_split_sizes=[e - s for s, e in slices], group=group)
         parts = recv.view(G, rows, tl, d)
     elif mode == "all_gather":
-        full = hx_local.new_empty((G, n, tl, d))
+        full = hx_local.new_empty((G * n, tl, d))
         td.all_gather_into_tensor(full, hx_local.contiguous(), group=group)
-        parts = full[:, my0:my1]
+        parts = full.view(G, n, tl, d)[:, my0:my1]
     else:
         raise ValueError("exchange must be 'all_to_all' or 'all_gather'")
     # parts[g, n, j] is snapshot t = g + G·j  →  seq[n, t]
@@ -72,8 +72,9 @@ def gather_node_slices(out_slice: torch.Tensor, n: int, group=None) -> torch.Ten
     _, T, d = out_slice.shape
     pad = out_slice.new_zeros((max_rows, T, d))
     pad[: out_slice.shape[0]] = out_slice
-    full = out_slice.new_empty((G, max_rows, T, d))
+    full = out_slice.new_empty((G * max_rows, T, d))
     td.all_gather_into_tensor(full, pad, group=group)
+    full = full.view(G, max_rows, T, d)
     return torch.cat([full[g, : e - s] for g, (s, e) in enumerate(slices)], dim=0)
 
 

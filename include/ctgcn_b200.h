@@ -55,6 +55,14 @@ const char* ctgcn_last_error(void);
 int64_t ctgcn_launch_count(void);
 int ctgcn_device_check(void); /* 0 iff the current device is compute capability 10.x */
 
+/* Per-kernel-class device timing for bench.py's roofline: while enabled, every launch is bracketed by CUDA
+ * events on its stream.  ctgcn_prof_collect synchronises the device and returns, per class
+ * (0 cumulative SpMM, 1 GRU(+LayerNorm), 2 dense linear, 3 weight packing/transposes, 4 sparse-input linear),
+ * the summed milliseconds and launch counts since the last reset.  Arrays of CTGCN_PROF_NCLASS entries. */
+#define CTGCN_PROF_NCLASS 5
+int ctgcn_prof_enable(int on);
+int ctgcn_prof_collect(double* ms, int64_t* counts, int reset);
+
 /* ---------------------------------------------------------------- graph plan
  * Replaces the per-call work torch.sparse.mm does on the reference's adj_list
  * (layers.py:41-45: K uncoalesced COO matrices, helper.py:51-82 / utils.py:89-95).

@@ -183,3 +183,19 @@ def build_core_adj_list(core_mats, max_core=-1):
                 out.append(m)
         prev = m
     return out, max_core
+
+
+def core_diffusion_rows(x, adj_list, sd, rows, prefix="", dtype=np.float64, eps=1e-5):
+    """core_diffusion restricted to a subset of output rows (full-size spot checks): same arithmetic as
+    layers.py:38-63, evaluated only for `rows` (A_i[rows] · x needs all of x but only |rows| sums)."""
+    x = np.asarray(x, dtype=dtype)
+    outs, acc = [], None
+    for a in adj_list:
+        prod = sp.csr_matrix(a).astype(dtype)[rows] @ x
+        acc = prod if acc is None else acc + prod
+        outs.append(acc)
+    u = np.maximum(np.stack(outs, axis=1), 0)
+    hs = gru_sequence(u,
+                      _p(sd, prefix, "rnn.weight_ih_l0", dtype), _p(sd, prefix, "rnn.weight_hh_l0", dtype),
+                      _p(sd, prefix, "rnn.bias_ih_l0", dtype), _p(sd, prefix, "rnn.bias_hh_l0", dtype))
+    return layer_norm(hs.sum(axis=1), _p(sd, prefix, "norm.weight", dtype), _p(sd, prefix, "norm.bias", dtype), eps)

@@ -1,0 +1,56 @@
+"""The C-ABI shared library loads on a CPU-only box and exports every symbol include/ctgcn_b200.h declares;
+argument validation and the host-only helper work without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "ctgcn_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ctgcn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    names = _declared()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib.lib, n), f"{n} declared in include/ctgcn_b200.h but not exported"
+    assert set(names) == set(lib.SIGNATURES), set(names) ^ set(lib.SIGNATURES)
+    assert lib.lib.ctgcn_version() == 100
+
+
+def test_argument_validation_without_gpu(lib):
+    L = lib.lib
+    out = C.c_void_p()
+    nnz = (C.c_int64 * 1)(0)
+    assert L.ctgcn_plan_create_coo(0, 0, 1, None, None, None, nnz, 0, None, C.byref(out)) == lib.EINVAL
+    assert "empty shape" in lib.last_error()
+    assert L.ctgcn_plan_create_coo(4, 4, 65, None, None, None, nnz, 0, None, C.byref(out)) == lib.EINVAL
+    assert L.ctgcn_set_gru_impl(7) == lib.EINVAL
+    assert L.ctgcn_set_gru_impl(lib.IMPL_AUTO) == 0
+    assert L.ctgcn_gru_workspace_bytes(128, 128) > 0
+    assert L.ctgcn_linear_workspace_bytes(10, 20) >= 800
+    assert L.ctgcn_cumspmm_fwd(None, None, 0, 4, None, None) == lib.EINVAL
+    assert L.ctgcn_plan_destroy(None) == 0
+
+
+def test_kcore_numbers_match_networkx(lib):
+    import networkx as nx
+    from ctgcn_b200 import synth
+    rng = np.random.default_rng(3)
+    n = 400
+    u, v = synth.er_edges(n, 3000, rng)
+    core = synth.core_numbers(n, u, v)
+    g = nx.Graph()
+    g.add_nodes_from(range(n))
+    g.add_edges_from(zip(u.tolist(), v.tolist()))
+    ref = nx.core_number(g)
+    assert core.tolist() == [ref[i] for i in range(n)]
+    # star + isolated nodes
+    core2 = synth.core_numbers(6, np.array([0, 0, 0]), np.array([1, 2, 3]))
+    assert core2.tolist() == [1, 1, 1, 1, 0, 0]

@@ -1,0 +1,111 @@
+"""Host-side logic that needs no GPU: synthetic generator vs the reference input contract, sharding helpers,
+module surface (constructor signatures, attribute names, state_dict keys)."""
+import inspect
+
+import networkx as nx
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from oracle import cases, oracle_np
+
+
+def _nx_core_mats(n, u, v):
+    g = nx.Graph()
+    g.add_nodes_from(range(n))
+    g.add_edges_from(zip(u.tolist(), v.tolist()))
+    core = nx.core_number(g)
+    mats = []
+    for k in range(1, max(core.values()) + 1):
+        sub = nx.k_core(g, k=k, core_number=core)
+        sub.add_nodes_from(range(n))
+        mats.append(sp.csr_matrix(nx.to_scipy_sparse_array(sub, nodelist=range(n), dtype=np.float64)))
+    return mats
+
+
+@pytest.mark.parametrize("kind,k", [("er", 3), ("er", 50), ("powerlaw", 4)])
+def test_synth_snapshot_matches_reference_contract(lib, kind, k):
+    from ctgcn_b200 import synth
+    n, m = 300, 2500
+    rng = np.random.default_rng(11)
+    u, v = (synth.er_edges if kind == "er" else synth.powerlaw_edges)(n, m, rng)
+    snap = synth.snapshot_from_edges(n, u, v, k)
+    mats = _nx_core_mats(n, u, v)
+    full, _ = oracle_np.build_core_adj_list(mats)          # every distinct level, densest first
+    want = full[:k]
+    if len(full) > k:                                       # truncated list: the K highest distinct levels
+        assert snap.k == k
+    else:
+        assert snap.k == len(full)
+    got = snap.coo_list()
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert abs(a.to_dense().numpy() - b.toarray()).max() == 0
+    assert snap.nnz_per_core == [int(b.nnz) for b in want]
+    assert snap.edges_aggregated == sum(int(b.nnz) for b in want)
+    # entries of a row are sorted by level; the diagonal is a one-shot level-0 entry
+    for r in range(n):
+        lv = snap.level[snap.rowptr[r]:snap.rowptr[r + 1]] & 127
+        assert (np.diff(lv.astype(int)) >= 0).all()
+    assert int((snap.level & 128).astype(bool).sum()) == n
+
+
+def test_sharding_helpers():
+    from ctgcn_b200 import dist
+    assert dist.node_slices(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert dist.node_slices(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
+    assert dist.owned_snapshots(8, 8, 3) == [3]
+    assert dist.owned_snapshots(16, 8, 3) == [3, 11]
+    assert dist.owned_snapshots(7, 2, 1) == [1, 3, 5]
+    assert dist.world_size() == 1 and dist.rank() == 0
+    cover = [t for r in range(3) for t in dist.owned_snapshots(7, 3, r)]
+    assert sorted(cover) == list(range(7))
+
+
+def test_module_surface_matches_reference(lib):
+    """Signatures (reference layers.py:16,75; models.py:16,141,204) and state_dict keys (pinned in the goldens by
+    load_state_dict(strict=True) into the reference classes)."""
+    import ctgcn_b200 as pkg
+    sig = lambda c: list(inspect.signature(c.__init__).parameters)[1:]
+    assert sig(pkg.CoreDiffusion) == ["input_dim", "output_dim", "core_num", "bias", "rnn_type"]
+    assert sig(pkg.MLP) == ["input_dim", "hidden_dim", "output_dim", "layer_num", "bias", "activate_type"]
+    assert sig(pkg.CDN) == ["input_dim", "hidden_dim", "output_dim", "diffusion_num", "bias", "rnn_type"]
+    assert sig(pkg.CGCN) == ["input_dim", "hidden_dim", "output_dim", "trans_num", "diffusion_num", "bias", "rnn_type",
+                             "model_type", "trans_activate_type"]
+    assert sig(pkg.CTGCN) == ["input_dim", "hidden_dim", "output_dim", "trans_num", "diffusion_num", "duration", "bias",
+                              "rnn_type", "model_type", "trans_activate_type"]
+    for name in cases.golden_names("ctgcn") + cases.golden_names("cgcn"):
+        m = cases.load_meta(name)
+        cls = pkg.CTGCN if m["kind"] == "ctgcn" else pkg.CGCN
+        args = (m["d_in"], m["hid"], m["d_out"], m["trans_num"], m["diffusion_num"]) + ((m["T"],) if m["kind"] == "ctgcn" else ())
+        mod = cls(*args, model_type=m["model_type"], trans_activate_type=m["act"])
+        assert sorted(mod.state_dict().keys()) == m["state_dict_keys"], name
+        assert mod.method_name == ("CTGCN-" if m["kind"] == "ctgcn" else "CGCN-") + m["model_type"]
+    with pytest.raises(AssertionError):
+        pkg.MLP(4, 4, 4, 0)
+    with pytest.raises(AssertionError):
+        pkg.CoreDiffusion(4, 4, rnn_type="RNN")
+    with pytest.raises(NotImplementedError):
+        pkg.CoreDiffusion(4, 4, rnn_type="LSTM")
+    with pytest.raises(ValueError):
+        pkg.CDN(4, 4, 4, 0)
+
+
+def test_same_seed_same_default_init_as_torch_modules(lib):
+    """Construction order mirrors the reference (linear → rnn → norm; mlp_t, cdn_t interleaved; rnn; norm), so one
+    seed gives one initialisation.  Checked against the same sequence of torch constructors."""
+    import torch.nn as nn
+    import ctgcn_b200 as pkg
+    torch.manual_seed(5)
+    mod = pkg.CoreDiffusion(12, 8)
+    torch.manual_seed(5)
+    lin, rnn = nn.Linear(12, 8), nn.GRU(12, 8, batch_first=True)
+    assert torch.equal(mod.linear.weight, lin.weight) and torch.equal(mod.rnn.weight_hh_l0, rnn.weight_hh_l0)
+
+
+def test_cpu_tensors_fail_loudly(lib):
+    import ctgcn_b200 as pkg
+    mlp = pkg.MLP(4, 4, 4, 1)
+    with pytest.raises(lib.CtgcnError):
+        mlp(torch.zeros(3, 4))

@@ -1,0 +1,313 @@
+"""Parity of the CUDA path (through the C-ABI) against the golden vectors generated from the unmodified
+reference, the oracle restatements, and size-independent properties at benchmark sizes.
+
+Tolerance (BASELINE.json north_star): outputs match the reference to 1e-4 relative in fp32.  Pinned here as
+relL2 ≤ 1e-4 AND allclose(rtol=1e-4, atol=1e-4·max|ref|)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from oracle import cases, oracle_np, oracle_torch
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+
+
+def close(got, ref, tag=""):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (tag, got.shape, ref.shape)
+    assert np.isfinite(got).all(), tag
+    err = cases.relerr(got, ref)
+    assert err <= REL, f"{tag}: relL2 {err:.3e} > {REL}"
+    np.testing.assert_allclose(got, ref, rtol=REL, atol=REL * max(1e-30, np.abs(ref).max()), err_msg=tag)
+    return err
+
+
+def tsd(sd, dev):
+    return {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in sd.items()}
+
+
+def coo(mats, dev):
+    return [oracle_torch.to_torch_coo(m).to(dev) for m in mats]
+
+
+def xin(x, dev):
+    return torch.from_numpy(x).to(dev) if isinstance(x, np.ndarray) else oracle_torch.to_torch_coo(x).to(dev)
+
+
+@pytest.fixture(scope="module", params=["simt", "auto"])
+def impl(request, lib, cuda_device):
+    lib.set_gru_impl(lib.IMPL_SIMT if request.param == "simt" else lib.IMPL_AUTO)
+    yield request.param
+    lib.set_gru_impl(lib.IMPL_AUTO)
+
+
+# ----------------------------------------------------------------------------- plan builder
+def expand_plan(plan):
+    """Rebuild the K dense matrices a plan represents (host side, for checking)."""
+    rowptr, col, val, lvl = [t.cpu().numpy() for t in plan.arrays()]
+    n, m, k = plan.n_rows, plan.n_cols, plan.k
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    mats = np.zeros((k, n, m))
+    for r, c, v, l in zip(rows, col, val, lvl):
+        f = l & 127
+        if l & 128:
+            mats[f, r, c] += v
+        else:
+            mats[f:, r, c] += v
+    return mats, (rowptr, col, val, lvl)
+
+
+@pytest.mark.parametrize("name", ["cd_nested_k5", "cd_nested_k16", "cd_nested_weighted", "cd_general", "cd_nested_k1"])
+def test_plan_from_coo_represents_the_list(name, lib, cuda_device):
+    from ctgcn_b200 import plan as P
+    c = cases.load_case(name)
+    plan = P.build_plan_coo(coo(c["adj"], cuda_device), cuda_device)
+    mats, (rowptr, col, val, lvl) = expand_plan(plan)
+    for i, a in enumerate(c["adj"]):
+        ref = sp.csr_matrix(a).astype(np.float32).toarray()  # duplicates summed
+        np.testing.assert_allclose(mats[i], ref, rtol=1e-6, atol=1e-7, err_msg=f"{name} core {i}")
+    assert plan.nnz_raw_sum == sum(a.nnz for a in c["adj"])
+    assert plan.nnz_coalesced == sum(sp.csr_matrix(a).nnz for a in c["adj"]) or name == "cd_general"
+    for r in range(plan.n_rows):  # level-sorted rows
+        lv = (lvl[rowptr[r]:rowptr[r + 1]] & 127).astype(int)
+        assert (np.diff(lv) >= 0).all()
+    if name.startswith("cd_nested"):
+        # nested list + identity on the first entry: one entry per distinct edge, n one-shot diagonals (K > 1)
+        union = sum(sp.csr_matrix(abs(a)) for a in c["adj"])
+        assert plan.entries == union.nnz
+        assert plan.n_oneshot == (plan.n_rows if plan.k > 1 else 0)
+
+
+def test_plan_from_csr_equals_plan_from_coo(lib, cuda_device):
+    from ctgcn_b200 import plan as P, synth
+    snap = synth.make_snapshot("er", 3000, 20000, 6, seed=5)
+    p1 = snap.plan(cuda_device)
+    p2 = P.build_plan_coo([a.to(cuda_device) for a in snap.coo_list()], cuda_device)
+    for a, b in zip(p1.arrays(), p2.arrays()):
+        assert torch.equal(a, b)
+    assert p1.nnz_raw_sum == p2.nnz_raw_sum == snap.edges_aggregated
+    assert p2.entries == snap.entries
+
+
+def test_plan_errors(lib, cuda_device):
+    from ctgcn_b200 import plan as P
+    bad = torch.sparse_coo_tensor(torch.tensor([[0, 5], [1, 1]]), torch.ones(2), (6, 6)).to(cuda_device)
+    bad._indices()[0, 1] = 9  # out of range row
+    with pytest.raises(lib.CtgcnError, match="out of range"):
+        P.build_plan_coo([bad], cuda_device)
+    with pytest.raises(lib.CtgcnError):
+        P.build_plan_csr(4, 4, 2, np.array([0, 2, 2, 2, 2]), np.array([1, 2]), np.ones(2), np.array([1, 0]), 2, cuda_device)
+    empty = torch.sparse_coo_tensor(torch.zeros((2, 0), dtype=torch.long), torch.zeros(0), (5, 5)).to(cuda_device)
+    p = P.build_plan_coo([empty, empty], cuda_device)
+    assert p.entries == 0
+
+
+# ----------------------------------------------------------------------------- kernels vs goldens
+@pytest.mark.parametrize("name", cases.golden_names("core_diffusion"))
+def test_cumspmm_against_fp64_oracle(name, lib, cuda_device):
+    from ctgcn_b200 import ops, plan as P
+    c = cases.load_case(name)
+    plan = P.build_plan_coo(coo(c["adj"], cuda_device), cuda_device)
+    u = ops.cumspmm(plan, torch.from_numpy(c["x"]).to(cuda_device)).cpu().numpy()      # [N, K, D]
+    ref = oracle_np.cumulative_core_sums(c["x"].astype(np.float64), [sp.coo_matrix(a).astype(np.float32) for a in c["adj"]])
+    close(u.transpose(1, 0, 2), ref, name)
+    np.testing.assert_allclose(u.sum(axis=2).T, c["expected"]["u_sum"], rtol=2e-5, atol=2e-4)
+
+
+@pytest.mark.parametrize("name", cases.golden_names("core_diffusion"))
+def test_core_diffusion_golden(name, impl, lib, cuda_device):
+    import ctgcn_b200 as pkg
+    c = cases.load_case(name)
+    m = c["meta"]
+    mod = pkg.CoreDiffusion(m["d_in"], m["d_out"], bias=m["bias"]).to(cuda_device)
+    mod.load_state_dict(tsd(c["sd"], cuda_device), strict=True)
+    adj = coo(c["adj"], cuda_device)
+    with torch.no_grad():
+        y = mod(torch.from_numpy(c["x"]).to(cuda_device), adj)
+        y2 = mod(torch.from_numpy(c["x"]).to(cuda_device), adj)     # cached plan, deterministic
+    assert torch.equal(y, y2)
+    close(y.cpu().numpy(), c["expected"]["y"], f"{name}[{impl}]")
+
+
+@pytest.mark.parametrize("name", cases.golden_names("mlp"))
+def test_mlp_golden(name, lib, cuda_device):
+    import ctgcn_b200 as pkg
+    c = cases.load_case(name)
+    m = c["meta"]
+    mod = pkg.MLP(m["d_in"], m["hid"], m["d_out"], m["layer_num"], bias=m["bias"], activate_type=m["act"]).to(cuda_device)
+    mod.load_state_dict(tsd(c["sd"], cuda_device), strict=True)
+    with torch.no_grad():
+        y = mod(xin(c["x"], cuda_device))
+    close(y.cpu().numpy(), c["expected"]["y"], name)
+
+
+@pytest.mark.parametrize("name", cases.golden_names("cdn"))
+def test_cdn_golden(name, impl, lib, cuda_device):
+    import ctgcn_b200 as pkg
+    c = cases.load_case(name)
+    m = c["meta"]
+    mod = pkg.CDN(m["d_in"], m["hid"], m["d_out"], m["diffusion_num"]).to(cuda_device)
+    mod.load_state_dict(tsd(c["sd"], cuda_device), strict=True)
+    with torch.no_grad():
+        y = mod(torch.from_numpy(c["x"]).to(cuda_device), coo(c["adj"], cuda_device))
+    close(y.cpu().numpy(), c["expected"]["y"], f"{name}[{impl}]")
+
+
+@pytest.mark.parametrize("name", cases.golden_names("cgcn") + cases.golden_names("ctgcn"))
+def test_model_golden(name, impl, lib, cuda_device):
+    import ctgcn_b200 as pkg
+    c = cases.load_case(name)
+    m = c["meta"]
+    T = m["T"]
+    if m["kind"] == "ctgcn":
+        mod = pkg.CTGCN(m["d_in"], m["hid"], m["d_out"], m["trans_num"], m["diffusion_num"], T, model_type=m["model_type"],
+                        trans_activate_type=m["act"])
+    else:
+        mod = pkg.CGCN(m["d_in"], m["hid"], m["d_out"], m["trans_num"], m["diffusion_num"], model_type=m["model_type"],
+                       trans_activate_type=m["act"])
+    mod = mod.to(cuda_device)
+    mod.load_state_dict(tsd(c["sd"], cuda_device), strict=True)
+    xs = [xin(x, cuda_device) for x in c["x_list"]]
+    adj = [coo(a, cuda_device) for a in c["adj_lists"]]
+    with torch.no_grad():
+        res = mod(xs[0], adj[0]) if m.get("single") else mod(xs, adj)
+    out, trans = res if m["model_type"] == "S" else (res, None)
+    if m["kind"] == "ctgcn":
+        assert tuple(out.shape) == (T, m["n"], m["d_out"]) and not out.is_contiguous() or T == 1   # transposed view
+    out = torch.stack(list(out)) if isinstance(out, (list, tuple)) else out
+    out = out[None] if out.dim() == 2 else out
+    rs = m["row_stride"]
+    close(out.cpu().numpy()[:, ::rs], c["expected"]["y"], f"{name}[{impl}]")
+    if trans is not None:
+        trans = torch.stack(list(trans)) if isinstance(trans, (list, tuple)) else trans[None]
+        close(trans.cpu().numpy()[:, ::rs], c["expected"]["trans"], f"{name}.trans")
+
+
+# ----------------------------------------------------------------------------- GRU kernel alone
+@pytest.mark.parametrize("n,steps,d_in,h,bias", [(300, 5, 128, 128, True), (77, 1, 128, 128, True), (130, 12, 128, 128, False),
+                                                 (65, 3, 500, 128, True), (40, 4, 20, 24, True), (257, 7, 64, 32, True),
+                                                 (129, 2, 256, 256, True)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gru_seq_kernel(n, steps, d_in, h, bias, mode, impl, lib, cuda_device):
+    from ctgcn_b200 import ops
+    rng = np.random.default_rng(n + steps)
+    sd = cases.gru_params(rng, "rnn.", d_in, h, bias)
+    sd.update(cases.norm_params(rng, "norm.", h))
+    seq = np.maximum(rng.standard_normal((n, steps, d_in)) * 3, 0).astype(np.float32)
+    hs = oracle_np.gru_sequence(seq.astype(np.float64), sd["rnn.weight_ih_l0"].astype(np.float64),
+                                sd["rnn.weight_hh_l0"].astype(np.float64),
+                                None if not bias else sd["rnn.bias_ih_l0"].astype(np.float64),
+                                None if not bias else sd["rnn.bias_hh_l0"].astype(np.float64))
+    pre = hs.sum(axis=1) if mode == 0 else hs
+    ref = oracle_np.layer_norm(pre, sd["norm.weight"].astype(np.float64), sd["norm.bias"].astype(np.float64))
+    d = tsd(sd, cuda_device)
+    # strided input (a [N, L, D] view into a wider buffer) and strided output exercise the stride arguments
+    buf = torch.zeros(n, steps + 1, d_in + 4, device=cuda_device)
+    buf[:, :steps, :d_in] = torch.from_numpy(seq).to(cuda_device)
+    out = torch.full((n, steps + 2, h) if mode else (n, h + 3), 7.0, device=cuda_device)
+    view = out[:, 1:steps + 1, :] if mode else out[:, :h]
+    ops.gru_seq(buf[:, :steps, :d_in], d["rnn.weight_ih_l0"], d["rnn.weight_hh_l0"], d.get("rnn.bias_ih_l0"),
+                d.get("rnn.bias_hh_l0"), d["norm.weight"], d["norm.bias"], 1e-5, mode, out=view)
+    close(view.cpu().numpy(), ref, f"gru n={n} L={steps} {d_in}->{h} mode={mode} [{impl}]")
+    assert (out[:, 0] == 7.0).all() if mode else (out[:, h:] == 7.0).all()   # nothing written outside the view
+
+
+# ----------------------------------------------------------------------------- edge cases
+def test_empty_and_isolated(lib, cuda_device, impl):
+    import ctgcn_b200 as pkg
+    n, d = 70, 32
+    empty = sp.coo_matrix((n, n), dtype=np.float32)
+    one = sp.coo_matrix(([2.0], ([3], [9])), shape=(n, n), dtype=np.float32)
+    rng = np.random.default_rng(1)
+    sd = cases.core_diffusion_params(rng, "", d, d)
+    x = cases.features(2, n, d)
+    mod = pkg.CoreDiffusion(d, d).to(cuda_device)
+    mod.load_state_dict(tsd(sd, cuda_device))
+    for adj in ([empty], [empty, empty, empty], [one, empty, one]):
+        with torch.no_grad():
+            y = mod(torch.from_numpy(x).to(cuda_device), coo(adj, cuda_device))
+        close(y.cpu().numpy(), oracle_np.core_diffusion(x, adj, sd), f"K={len(adj)}")
+
+
+def test_k64_chain(lib, cuda_device, impl):
+    """Maximum list length (America-Air has 64 cores, reference README.md:175)."""
+    import ctgcn_b200 as pkg
+    n, d, k = 200, 32, 64
+    rng = np.random.default_rng(9)
+    mats, acc = [], sp.eye(n, format="csr", dtype=np.float32) * 0
+    for i in range(k):
+        r, c = rng.integers(0, n, 12), rng.integers(0, n, 12)
+        acc = acc + sp.coo_matrix((np.ones(12, dtype=np.float32), (r, c)), shape=(n, n)).tocsr()
+        acc.data[:] = 1.0
+        mats.append((acc + sp.eye(n, dtype=np.float32)).tocoo() if i == 0 else acc.tocoo())
+    sd = cases.core_diffusion_params(rng, "", d, d)
+    x = (0.05 * cases.features(3, n, d)).astype(np.float32)
+    mod = pkg.CoreDiffusion(d, d).to(cuda_device)
+    mod.load_state_dict(tsd(sd, cuda_device))
+    with torch.no_grad():
+        y = mod(torch.from_numpy(x).to(cuda_device), coo(mats, cuda_device))
+    close(y.cpu().numpy(), oracle_np.core_diffusion(x, mats, sd), "K=64")
+    with pytest.raises(lib.CtgcnError):
+        mod(torch.from_numpy(x).to(cuda_device), coo(mats + mats[:1], cuda_device))   # 65 matrices
+
+
+def test_shape_errors(lib, cuda_device):
+    import ctgcn_b200 as pkg
+    mod = pkg.CoreDiffusion(16, 16).to(cuda_device)
+    adj = coo([sp.eye(10, format="coo", dtype=np.float32)], cuda_device)
+    with pytest.raises(lib.CtgcnError):
+        mod(torch.zeros(11, 16, device=cuda_device), adj)
+    with pytest.raises(lib.CtgcnError):
+        mod(torch.zeros(10, 8, device=cuda_device), adj)
+    out = mod(torch.zeros(10, 16, device=cuda_device), adj)      # grad mode on: forward works, backward refuses
+    with pytest.raises(NotImplementedError):
+        out.sum().backward()
+
+
+# ----------------------------------------------------------------------------- benchmark-size properties
+def test_cfg2_size_properties(lib, cuda_device, impl):
+    """ER 100 K nodes / 1 M edges, K=5, 128-d (BASELINE.json configs[1]), one snapshot."""
+    import ctgcn_b200 as pkg
+    from ctgcn_b200 import ops, synth
+    n, d, k = 100_000, 128, 5
+    snap = synth.make_snapshot("er", n, 1_000_000, k, seed=0)
+    plan = snap.plan(cuda_device)
+    # (1) checksum: x = 1 → U[r, i, :] = Σ_{j≤i} rowsum(A_j)[r], exact small integers
+    ones = torch.ones(n, d, device=cuda_device)
+    u = ops.cumspmm(plan, ones)
+    lev = snap.level & 127
+    one = (snap.level & 128) != 0
+    rows = np.repeat(np.arange(n), np.diff(snap.rowptr))
+    want = np.zeros((n, snap.k))
+    for i in range(snap.k):
+        a_i = np.bincount(rows[np.where(one, lev == i, lev <= i)], minlength=n)
+        want[:, i] = a_i + (want[:, i - 1] if i else 0)
+    assert torch.equal(u[:, :, 0].cpu(), torch.from_numpy(want).float())
+    assert torch.equal(u[:, :, 0], u[:, :, d - 1])
+    # (2) linearity on the relu-inactive cone (x ≥ 0, weights ≥ 0)
+    x1 = synth.features(n, d, 1).abs().to(cuda_device)
+    x2 = synth.features(n, d, 2).abs().to(cuda_device)
+    lhs = ops.cumspmm(plan, 2.0 * x1 + 0.5 * x2)
+    rhs = 2.0 * ops.cumspmm(plan, x1) + 0.5 * ops.cumspmm(plan, x2)
+    assert cases.relerr(lhs.cpu().numpy(), rhs.cpu().numpy()) < 1e-6
+    # (3) full CoreDiffusion on random rows against the fp64 oracle
+    sd = cases.core_diffusion_params(np.random.default_rng(0), "", d, d)
+    mod = pkg.CoreDiffusion(d, d).to(cuda_device)
+    mod.load_state_dict(tsd(sd, cuda_device))
+    x = synth.features(n, d, 1000)
+    with torch.no_grad():
+        y = mod(x.to(cuda_device), plan)
+    pick = np.random.default_rng(4).choice(n, 256, replace=False)
+    mats = [sp.coo_matrix((a._values().numpy(), a._indices().numpy()), shape=(n, n)) for a in snap.coo_list()]
+    ref = oracle_np.core_diffusion_rows(x.numpy(), mats, sd, pick)
+    close(y[torch.from_numpy(pick).to(cuda_device)].cpu().numpy(), ref, f"cfg2 rows [{impl}]")
+    # (4) LayerNorm invariants on every row: mean ≈ β-weighted … use γ=1, β=0 copy
+    mod.norm.weight.data.fill_(1.0)
+    mod.norm.bias.data.zero_()
+    with torch.no_grad():
+        z = mod(x.to(cuda_device), plan)
+    assert z.mean(dim=1).abs().max().item() < 1e-5
+    assert (z.var(dim=1, unbiased=False) - 1).abs().max().item() < 1e-3
