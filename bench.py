@@ -269,11 +269,15 @@ def main():
             _lib.prof_enable(True)
         l0 = _lib.launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if prof:
+            torch.cuda.profiler.start()      # ncu --profile-from-start off captures exactly the timed region
         ev0.record()
         for _ in range(steps):
             fn()
         ev1.record()
         torch.cuda.synchronize()
+        if prof:
+            torch.cuda.profiler.stop()
         if world > 1:
             td.barrier()
         torch.cuda.synchronize()

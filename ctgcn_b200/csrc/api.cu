@@ -48,7 +48,7 @@ void set_error(const char* fmt, ...) {
 int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* w_ih,
                   const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
                   int mode, float* y, int64_t yrs, int64_t yss, void* ws, size_t ws_bytes, cudaStream_t st)
-    __attribute__((weak));
+;
 
 }  // namespace ctgcn
 
@@ -116,7 +116,7 @@ extern "C" int ctgcn_cumspmm_fwd(const ctgcn_plan* plan, const float* x, int64_t
 
 // ---- GRU: workspace = k-major copies of the two weight matrices (SIMT path) | tcgen05 packed weights
 static size_t gru_ws_simt(int d_in, int h) { return align_up((size_t)3 * h * (d_in + h) * sizeof(float), 256); }
-static size_t gru_ws_tc(int d_in, int h) { return align_up((size_t)3 * h * (d_in + h) * 2 * sizeof(uint16_t), 256) + 1024; }
+static size_t gru_ws_tc(int d_in, int h) { return align_up((size_t)3 * h * (d_in + h) * 2 * sizeof(uint16_t), 256) + 4096; }
 
 extern "C" size_t ctgcn_gru_workspace_bytes(int d_in, int h) {
     if (d_in <= 0 || h <= 0) return 0;
@@ -139,14 +139,12 @@ extern "C" int ctgcn_gru_seq_fwd(const float* seq, int64_t srs, int64_t sss, int
     if (n == 0) return CTGCN_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int impl = g_gru_impl.load();
-    if (impl != CTGCN_IMPL_SIMT && launch_gru_tc) {
+    if (impl != CTGCN_IMPL_SIMT) {
         char* tc_ws = (char*)workspace + gru_ws_simt(d_in, h);
         int rc = launch_gru_tc(seq, srs, sss, n, steps, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss,
                                tc_ws, gru_ws_tc(d_in, h), st);
         if (rc <= 0) return rc;  // done or failed
         CTGCN_REQUIRE(impl == CTGCN_IMPL_AUTO, "gru_seq_fwd: tcgen05 path does not support d_in=%d h=%d", d_in, h);
-    } else {
-        CTGCN_REQUIRE(impl != CTGCN_IMPL_TCGEN05, "gru_seq_fwd: tcgen05 path not built");
     }
     float* wt_ih = (float*)workspace;
     float* wt_hh = wt_ih + (size_t)3 * h * d_in;

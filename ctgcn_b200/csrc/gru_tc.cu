@@ -1,0 +1,671 @@
+// tcgen05 (5th-gen tensor core) GRU over a short sequence + Σ/LayerNorm epilogue — the compute-bound half of
+// CoreDiffusion.forward (layers.py:59-62) and the temporal GRU of CTGCN.forward (models.py:249-250).
+//
+// Numerics: the parity bar is 1e-4 relative in fp32 and single-pass bf16/tf32 tensor-core products miss it
+// (2.7e-3 / 3.3e-4).  Every fp32 operand is therefore split a = hi + lo (two bf16 planes, 16
+// significant bits) and each product is issued as three MMAs  hi·hi + lo·hi + hi·lo  accumulated in fp32 in
+// TMEM (error ≈ 2^-17 per product, ~1e-5 on the layer output).
+//
+// One persistent CTA per SM owns 128-node tiles for the WHOLE sequence (h and Σh never leave the SM):
+//   warp 0     weight producer: the packed [64 gate-rows × 64 k] hi/lo chunks (16 KB, exact shared-memory images,
+//              built once per call by pack_weights_kernel) stream from L2 through a 5-stage ring with
+//              cp.async.bulk + mbarrier complete_tx
+//   warp 1     MMA issuer (one elected lane): tcgen05.mma cta_group::1 kind::f16, M=128 N=64 K=16, operands
+//              described by no-swizzle K-major shared-memory descriptors, accumulators in TMEM
+//   warps 2-9  workers: stage the step's input rows (fp32 → bf16 hi/lo planes in UMMA core-matrix layout),
+//              read accumulators with tcgen05.ld, apply the gates, write h back as the next step's A operand,
+//              keep Σh (or emit LayerNorm(h_s)) and finally LayerNorm.
+// A step is processed in two halves of 64 hidden features so that the 512 TMEM columns hold two accumulator
+// sets (r,z,in,hn × 64 columns each): the gate math of one half overlaps the MMAs of the other.
+//
+// Shapes: H = 128, d_in ∈ {64, 128} (everything the 128-d configurations need); other shapes use gru_simt.cu.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace ctgcn {
+namespace {
+
+constexpr int H = 128;
+constexpr int TILE_M = 128;
+constexpr int CHUNK_N = 64, CHUNK_K = 64;
+constexpr int CHUNK_PLANE = CHUNK_N * CHUNK_K * 2;  // 8 KB: one bf16 plane of a weight chunk
+constexpr int CHUNK_BYTES = 2 * CHUNK_PLANE;        // hi + lo
+constexpr int STAGES = 5;
+constexpr int NUM_WORKER_WARPS = 8;
+constexpr int THREADS = 32 * (2 + NUM_WORKER_WARPS);
+constexpr uint32_t TMEM_COLS = 512;
+
+// ---- shared memory map (bytes)
+constexpr int A_PLANE = TILE_M * H * 2;             // 32 KB: one bf16 plane of a 128×128 operand tile
+constexpr int SM_U = 0;                             // U hi | U lo
+constexpr int SM_H = SM_U + 2 * A_PLANE;            // h hi | h lo
+constexpr int SM_W = SM_H + 2 * A_PLANE;            // weight ring
+constexpr int SM_BIAS = SM_W + STAGES * CHUNK_BYTES;  // [4][H] fp32: b_r(+), b_z(+), b_in, b_hn
+constexpr int SM_LN = SM_BIAS + 4 * H * 4;          // ln_w | ln_b
+constexpr int SM_RED = SM_LN + 2 * H * 4;           // [2 buffers][2 column halves][128 rows] fp32
+constexpr int SM_BAR = SM_RED + 2 * 2 * TILE_M * 4;
+constexpr int NUM_BARS = 2 * STAGES + 7;
+constexpr int SM_TMEM_PTR = SM_BAR + NUM_BARS * 8;
+constexpr int SMEM_BYTES = SM_TMEM_PTR + 16;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+enum Bar { BAR_W_FULL = 0, BAR_W_EMPTY = STAGES, BAR_U_READY = 2 * STAGES, BAR_U_FREE, BAR_H_READY, BAR_ACC_FULL0,
+           BAR_ACC_FULL1, BAR_ACC_FREE0, BAR_ACC_FREE1 };
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            printf("ctgcn gru_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+                   bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// K-major, no-swizzle ("interleaved") operand: 8-row × 16-byte core matrices; LBO = byte distance between the two
+// 8-element K halves of one K=16 MMA, SBO = byte distance between consecutive 8-row groups.  Descriptor version 1.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ bf16 split
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+    const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+    hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+}
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+    split2(v[0], v[1], hi.x, lo.x);
+    split2(v[2], v[3], hi.y, lo.y);
+    split2(v[4], v[5], hi.z, lo.z);
+    split2(v[6], v[7], hi.w, lo.w);
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float (&v)[8]) {
+    v[0] = bf_lo(hi.x) + bf_lo(lo.x);
+    v[1] = bf_hi(hi.x) + bf_hi(lo.x);
+    v[2] = bf_lo(hi.y) + bf_lo(lo.y);
+    v[3] = bf_hi(hi.y) + bf_hi(lo.y);
+    v[4] = bf_lo(hi.z) + bf_lo(lo.z);
+    v[5] = bf_hi(hi.z) + bf_hi(lo.z);
+    v[6] = bf_lo(hi.w) + bf_lo(lo.w);
+    v[7] = bf_hi(hi.w) + bf_hi(lo.w);
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// Chunk order = consumption order of one step: part ∈ {X half0, X half1, H half0, H half1}, gate ∈ {r, z, n},
+// k-chunk.  X parts read W_ih [3H, d_in], H parts W_hh [3H, H].  Chunk image: bf16 hi plane then lo plane, element
+// (n, k) at (k/8)·1024 + n·16 + (k%8)·2  (no-swizzle K-major core matrices, LBO = 1024, SBO = 128).
+__global__ void pack_weights_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                                    const float* __restrict__ b_ih, const float* __restrict__ b_hh, int d_in,
+                                    uint8_t* __restrict__ packed, float* __restrict__ bias4) {
+    const int kcx = d_in / CHUNK_K, kch = H / CHUNK_K;
+    const int nchunks = 2 * 3 * kcx + 2 * 3 * kch;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 4 * H) {
+        const int g = t / H, f = t % H;
+        float v = 0.f;
+        if (b_ih) {
+            if (g == 0) v = b_ih[f] + b_hh[f];
+            if (g == 1) v = b_ih[H + f] + b_hh[H + f];
+            if (g == 2) v = b_ih[2 * H + f];
+            if (g == 3) v = b_hh[2 * H + f];
+        }
+        bias4[t] = v;
+    }
+    if (t >= nchunks * CHUNK_N * (CHUNK_K / 8)) return;
+    const int c = t / (CHUNK_N * 8), rem = t % (CHUNK_N * 8);
+    const int kb = rem / CHUNK_N, n = rem % CHUNK_N;
+    int part, g, kc;
+    const int nx = 2 * 3 * kcx;
+    const float* w;
+    int ld;
+    if (c < nx) {
+        part = c / (3 * kcx);
+        g = (c / kcx) % 3;
+        kc = c % kcx;
+        w = w_ih;
+        ld = d_in;
+    } else {
+        const int cc = c - nx;
+        part = cc / (3 * kch);
+        g = (cc / kch) % 3;
+        kc = cc % kch;
+        w = w_hh;
+        ld = H;
+    }
+    const float* src = w + (int64_t)(g * H + part * CHUNK_N + n) * ld + kc * CHUNK_K + kb * 8;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = src[i];
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    uint8_t* dst = packed + (size_t)c * CHUNK_BYTES + kb * 1024 + n * 16;
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + CHUNK_PLANE) = lo;
+}
+
+// ------------------------------------------------------------------------------------------------ roles
+struct Params {
+    const float* seq;
+    int64_t srs, sss, n;
+    int steps, d_in;
+    const uint8_t* packed;
+    const float* bias4;
+    const float* ln_w;
+    const float* ln_b;
+    float eps;
+    float* y;
+    int64_t yrs, yss;
+    int num_tiles;
+};
+
+__device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+__device__ __forceinline__ float tanh_fast(float v) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * v)); }
+
+// One weight chunk = 4 K-steps × 3 split products, all into one 64-column accumulator.
+__device__ __forceinline__ void issue_chunk(uint32_t a_hi, uint32_t a_lo, uint32_t b_chunk, uint32_t d_tmem, bool fresh) {
+    constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, CHUNK_N);
+#pragma unroll
+    for (int ks = 0; ks < CHUNK_K / 16; ++ks) {
+        const uint64_t ah = umma_desc(a_hi + ks * 2 * (TILE_M * 16), TILE_M * 16, 128);
+        const uint64_t al = umma_desc(a_lo + ks * 2 * (TILE_M * 16), TILE_M * 16, 128);
+        const uint64_t bh = umma_desc(b_chunk + ks * 2 * (CHUNK_N * 16), CHUNK_N * 16, 128);
+        const uint64_t bl = umma_desc(b_chunk + CHUNK_PLANE + ks * 2 * (CHUNK_N * 16), CHUNK_N * 16, 128);
+        umma_bf16(d_tmem, ah, bh, idesc, (fresh && ks == 0) ? 0u : 1u);
+        umma_bf16(d_tmem, al, bh, idesc, 1u);
+        umma_bf16(d_tmem, ah, bl, idesc, 1u);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = sbase + SM_BAR;
+    auto bar = [&](int i) { return bar0 + 8u * i; };
+    const int kcx = p.d_in / CHUNK_K;          // k-chunks of the input part
+    constexpr int kch = H / CHUNK_K;           // k-chunks of the recurrent part
+    const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar(BAR_W_FULL + s), 1);
+            mbar_init(bar(BAR_W_EMPTY + s), 1);
+        }
+        mbar_init(bar(BAR_U_READY), NUM_WORKER_WARPS);
+        mbar_init(bar(BAR_U_FREE), 1);
+        mbar_init(bar(BAR_H_READY), NUM_WORKER_WARPS);
+        mbar_init(bar(BAR_ACC_FULL0), 1);
+        mbar_init(bar(BAR_ACC_FULL1), 1);
+        mbar_init(bar(BAR_ACC_FREE0), NUM_WORKER_WARPS);
+        mbar_init(bar(BAR_ACC_FREE1), NUM_WORKER_WARPS);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < 4 * H; i += THREADS) reinterpret_cast<float*>(smem + SM_BIAS)[i] = p.bias4[i];
+    for (int i = threadIdx.x; i < H; i += THREADS) {
+        reinterpret_cast<float*>(smem + SM_LN)[i] = p.ln_w[i];
+        reinterpret_cast<float*>(smem + SM_LN)[H + i] = p.ln_b[i];
+    }
+    if (warp == 1) tmem_alloc(sbase + SM_TMEM_PTR, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM_PTR);
+
+    if (warp == 0) {
+        // ===================================================== weight producer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            const int nx = 2 * 3 * kcx, nh = 2 * 3 * kch;
+            for (int t = 0; t < my_tiles; ++t) {
+                for (int i = 0; i < p.steps; ++i) {
+                    const int nchunks = nx + (i > 0 ? nh : 0);
+                    for (int c = 0; c < nchunks; ++c) {
+                        mbar_wait(bar(BAR_W_EMPTY + stage), phase ^ 1);
+                        mbar_expect_tx(bar(BAR_W_FULL + stage), CHUNK_BYTES);
+                        bulk_g2s(sbase + SM_W + stage * CHUNK_BYTES, p.packed + (size_t)c * CHUNK_BYTES, CHUNK_BYTES,
+                                 bar(BAR_W_FULL + stage));
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, gs = 0;
+            const uint32_t u_hi = sbase + SM_U, u_lo = u_hi + A_PLANE, h_hi = sbase + SM_H, h_lo = h_hi + A_PLANE;
+            auto run_part = [&](uint32_t a_hi, uint32_t a_lo, int kchunks, int half, bool recurrent) {
+                for (int g = 0; g < 3; ++g) {
+                    // accumulator column block: r, z shared by both parts; the n gate keeps W_in·x and W_hn·h apart
+                    const int blk = (g < 2) ? g : (recurrent ? 3 : 2);
+                    const uint32_t d = tmem + half * 256 + blk * 64;
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        mbar_wait(bar(BAR_W_FULL + stage), phase);
+                        tc_fence_after();
+                        const bool fresh = (kc == 0) && (!recurrent || g == 2);
+                        issue_chunk(a_hi + kc * (CHUNK_K / 8) * (TILE_M * 16), a_lo + kc * (CHUNK_K / 8) * (TILE_M * 16),
+                                    sbase + SM_W + stage * CHUNK_BYTES, d, fresh);
+                        umma_commit(bar(BAR_W_EMPTY + stage));
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            };
+            for (int t = 0; t < my_tiles; ++t) {
+                for (int i = 0; i < p.steps; ++i, ++gs) {
+                    const uint32_t par = gs & 1;
+                    mbar_wait(bar(BAR_U_READY), par);
+                    mbar_wait(bar(BAR_ACC_FREE0), par ^ 1);
+                    tc_fence_after();
+                    run_part(u_hi, u_lo, kcx, 0, false);
+                    if (i == 0) umma_commit(bar(BAR_ACC_FULL0));
+                    mbar_wait(bar(BAR_ACC_FREE1), par ^ 1);
+                    tc_fence_after();
+                    run_part(u_hi, u_lo, kcx, 1, false);
+                    umma_commit(bar(BAR_U_FREE));
+                    if (i == 0) {
+                        umma_commit(bar(BAR_ACC_FULL1));
+                    } else {
+                        mbar_wait(bar(BAR_H_READY), par ^ 1);
+                        tc_fence_after();
+                        run_part(h_hi, h_lo, kch, 0, true);
+                        umma_commit(bar(BAR_ACC_FULL0));
+                        run_part(h_hi, h_lo, kch, 1, true);
+                        umma_commit(bar(BAR_ACC_FULL1));
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================================================== workers
+        const int ww = warp - 2;
+        const int q = warp & 3;          // TMEM lane quarter this warp may access
+        const int ch = ww >> 2;          // which 32 of a half's 64 features this thread owns
+        const int m = 32 * q + lane;     // row inside the tile
+        const uint32_t tmem_lane = tmem + ((uint32_t)(32 * q) << 16);
+        const float* bias = reinterpret_cast<const float*>(smem + SM_BIAS);
+        const float* lnw = reinterpret_cast<const float*>(smem + SM_LN);
+        float* red = reinterpret_cast<float*>(smem + SM_RED);
+        uint8_t* u_hi = smem + SM_U;
+        uint8_t* h_hi = smem + SM_H;
+        const int kb_per_thread = (p.d_in / 8) / 2;
+        uint32_t gs = 0;
+
+        // LayerNorm over the row: this thread holds 64 of its 128 values, the partner warp (other ch) the rest
+        auto layer_norm_store = [&](const float (&v)[64], float* dst_row, bool valid) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) s += v[j];
+            red[ch * TILE_M + m] = s;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float mean = (s + red[(ch ^ 1) * TILE_M + m]) * (1.f / H);
+            float sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const float dlt = v[j] - mean;
+                sq = fmaf(dlt, dlt, sq);
+            }
+            red[2 * TILE_M + ch * TILE_M + m] = sq;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float rstd = rsqrtf((sq + red[2 * TILE_M + (ch ^ 1) * TILE_M + m]) * (1.f / H) + p.eps);
+            if (valid) {
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 32; j4 += 4) {
+                        const int f = hf * 64 + ch * 32 + j4;
+                        float4 o;
+                        o.x = (v[hf * 32 + j4 + 0] - mean) * rstd * lnw[f + 0] + lnw[H + f + 0];
+                        o.y = (v[hf * 32 + j4 + 1] - mean) * rstd * lnw[f + 1] + lnw[H + f + 1];
+                        o.z = (v[hf * 32 + j4 + 2] - mean) * rstd * lnw[f + 2] + lnw[H + f + 2];
+                        o.w = (v[hf * 32 + j4 + 3] - mean) * rstd * lnw[f + 3] + lnw[H + f + 3];
+                        *reinterpret_cast<float4*>(dst_row + f) = o;
+                    }
+                }
+            }
+        };
+
+        for (int t = 0; t < my_tiles; ++t) {
+            const int64_t row = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + m;
+            const bool valid = row < p.n;
+            float acc_out[64];   // Σ_s h_s (SUM_LN) / h_s of the current step (EACH_LN) for this thread's 64 features
+#pragma unroll
+            for (int j = 0; j < 64; ++j) acc_out[j] = 0.f;
+
+            for (int i = 0; i < p.steps; ++i, ++gs) {
+                const uint32_t par = gs & 1;
+                // ---- (1) stage this step's input rows: fp32 → bf16 hi/lo planes, 8 k-elements (16 B) per store
+                mbar_wait(bar(BAR_U_FREE), par ^ 1);
+                {
+                    const float* src = p.seq + row * p.srs + (int64_t)i * p.sss;
+                    for (int kb0 = 0; kb0 < kb_per_thread; kb0 += 4) {
+                        float4 v[8];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int kb = ch * kb_per_thread + kb0 + u;
+                            if (valid) {
+                                v[2 * u] = __ldg(reinterpret_cast<const float4*>(src + kb * 8));
+                                v[2 * u + 1] = __ldg(reinterpret_cast<const float4*>(src + kb * 8 + 4));
+                            } else {
+                                v[2 * u] = v[2 * u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int kb = ch * kb_per_thread + kb0 + u;
+                            const float f8[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w,
+                                                 v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
+                            uint4 hi, lo;
+                            split8(f8, hi, lo);
+                            *reinterpret_cast<uint4*>(u_hi + kb * (TILE_M * 16) + m * 16) = hi;
+                            *reinterpret_cast<uint4*>(u_hi + A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
+                        }
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(BAR_U_READY));
+
+                // ---- (2) gates, one half (64 hidden features) at a time; this thread owns 32 of them, 8 per pass
+                float h0[32];   // first half of h_i, published only when no MMA reads h_{i-1} any more
+                auto put_h8 = [&](const float (&f8)[8], int f) {
+                    uint4 hi, lo;
+                    split8(f8, hi, lo);
+                    const int kb = f >> 3;
+                    *reinterpret_cast<uint4*>(h_hi + kb * (TILE_M * 16) + m * 16) = hi;
+                    *reinterpret_cast<uint4*>(h_hi + A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
+                };
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    mbar_wait(bar(BAR_ACC_FULL0 + hf), par);
+                    tc_fence_after();
+                    if (hf == 1) {
+#pragma unroll
+                        for (int j8 = 0; j8 < 32; j8 += 8) {
+                            const float f8[8] = {h0[j8], h0[j8 + 1], h0[j8 + 2], h0[j8 + 3], h0[j8 + 4], h0[j8 + 5], h0[j8 + 6], h0[j8 + 7]};
+                            put_h8(f8, ch * 32 + j8);
+                        }
+                    }
+#pragma unroll
+                    for (int sub = 0; sub < 4; ++sub) {
+                        const int f0 = hf * 64 + ch * 32 + sub * 8;             // first of 8 features
+                        const uint32_t col = hf * 256 + ch * 32 + sub * 8;      // + blk*64
+                        float gr[8], gz[8], gi[8], gh[8], hold[8];
+                        tmem_ld8(tmem_lane + col, gr);
+                        tmem_ld8(tmem_lane + col + 64, gz);
+                        tmem_ld8(tmem_lane + col + 128, gi);
+                        if (i > 0) {
+                            tmem_ld8(tmem_lane + col + 192, gh);
+                            const int kb = f0 >> 3;
+                            const uint4 hi = *reinterpret_cast<const uint4*>(h_hi + kb * (TILE_M * 16) + m * 16);
+                            const uint4 lo = *reinterpret_cast<const uint4*>(h_hi + A_PLANE + kb * (TILE_M * 16) + m * 16);
+                            join8(hi, lo, hold);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) gh[j] = hold[j] = 0.f;
+                        }
+                        tmem_ld_wait();
+                        float hn8[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int f = f0 + j;
+                            const float r = sigmoid_fast(gr[j] + bias[f]);
+                            const float z = sigmoid_fast(gz[j] + bias[H + f]);
+                            const float nn = tanh_fast(gi[j] + bias[2 * H + f] + r * (gh[j] + bias[3 * H + f]));
+                            hn8[j] = nn + z * (hold[j] - nn);
+                        }
+                        if (hf == 0) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) h0[sub * 8 + j] = hn8[j];
+                        } else {
+                            put_h8(hn8, f0);   // all MMAs of this step are complete: h may be overwritten in place
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (MODE == CTGCN_GRU_SUM_LN) acc_out[hf * 32 + sub * 8 + j] += hn8[j];
+                            else acc_out[hf * 32 + sub * 8 + j] = hn8[j];
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(BAR_ACC_FREE0 + hf));
+                }
+                // ---- (3) h_i is complete in shared memory: the next step's recurrent MMAs may read it
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(BAR_H_READY));
+                if (MODE == CTGCN_GRU_EACH_LN) layer_norm_store(acc_out, p.y + row * p.yrs + (int64_t)i * p.yss, valid);
+            }
+            if (MODE == CTGCN_GRU_SUM_LN) layer_norm_store(acc_out, p.y + row * p.yrs, valid);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ self test
+// out[128×64] = A[128×64] · B[64×64]ᵀ through exactly the operand layouts, descriptors, bulk copy and TMEM loads
+// the GRU kernel uses (one weight chunk, 12 MMAs).  Exposed as ctgcn_selftest_umma for the GPU test-suite.
+__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __restrict__ a, const uint8_t* __restrict__ bchunk,
+                                                                float* __restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    constexpr int A_PL = TILE_M * CHUNK_K * 2;  // 16 KB plane
+    const uint32_t sa = sbase, sb = sbase + 2 * A_PL, bar_w = sb + CHUNK_BYTES, bar_d = bar_w + 8, tptr = bar_d + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, m = threadIdx.x;
+    if (threadIdx.x == 0) {
+        mbar_init(bar_w, 1);
+        mbar_init(bar_d, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tptr, 64);
+    for (int kb = 0; kb < CHUNK_K / 8; ++kb) {
+        float f8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f8[e] = a[m * CHUNK_K + kb * 8 + e];
+        uint4 hi, lo;
+        split8(f8, hi, lo);
+        *reinterpret_cast<uint4*>(smem + kb * (TILE_M * 16) + m * 16) = hi;
+        *reinterpret_cast<uint4*>(smem + A_PL + kb * (TILE_M * 16) + m * 16) = lo;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + 2 * A_PL + CHUNK_BYTES + 16);
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar_w, CHUNK_BYTES);
+        bulk_g2s(sb, bchunk, CHUNK_BYTES, bar_w);
+        mbar_wait(bar_w, 0);
+        tc_fence_after();
+        issue_chunk(sa, sa + A_PL, sb, tmem, true);
+        umma_commit(bar_d);
+    }
+    mbar_wait(bar_d, 0);
+    tc_fence_after();
+    const uint32_t tl = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+#pragma unroll
+    for (int c = 0; c < 64; c += 16) {
+        float v[16];
+        tmem_ld16(tl + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) out[m * 64 + c + j] = v[j];
+    }
+    (void)lane;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
+}  // namespace
+
+// returns 0 = done, <0 = error, 1 = shape not supported by this path
+int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* w_ih,
+                  const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
+                  int mode, float* y, int64_t yrs, int64_t yss, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (h != H || (d_in != 64 && d_in != 128)) return 1;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (!al16(seq) || !al16(y) || (srs & 3) || (sss & 3) || (yrs & 3) || (yss & 3)) return 1;
+    const int nchunks = 2 * 3 * (d_in / CHUNK_K) + 2 * 3 * (H / CHUNK_K);
+    const size_t packed_bytes = (size_t)nchunks * CHUNK_BYTES;
+    CTGCN_REQUIRE(ws && ws_bytes >= packed_bytes + 4 * H * sizeof(float), "gru_tc: workspace too small");
+    uint8_t* packed = (uint8_t*)ws;
+    float* bias4 = (float*)(packed + packed_bytes);
+    {
+        ProfScope prof(PROF_PACK, st);
+        const int threads = nchunks * CHUNK_N * (CHUNK_K / 8);
+        pack_weights_kernel<<<(threads + 255) / 256, 256, 0, st>>>(w_ih, w_hh, b_ih, b_hh, d_in, packed, bias4);
+        CTGCN_LAUNCH_OK("pack_weights_kernel");
+    }
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        CTGCN_CUDA_OK(cudaGetDevice(&dev));
+        CTGCN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_kernel<CTGCN_GRU_SUM_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_kernel<CTGCN_GRU_EACH_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    }
+    Params p;
+    p.seq = seq;
+    p.srs = srs;
+    p.sss = sss;
+    p.n = n;
+    p.steps = steps;
+    p.d_in = d_in;
+    p.packed = packed;
+    p.bias4 = bias4;
+    p.ln_w = ln_w;
+    p.ln_b = ln_b;
+    p.eps = eps;
+    p.y = y;
+    p.yrs = yrs;
+    p.yss = yss;
+    p.num_tiles = (int)((n + TILE_M - 1) / TILE_M);
+    const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
+    ProfScope prof(PROF_GRU, st);
+    if (mode == CTGCN_GRU_SUM_LN)
+        gru_tc_kernel<CTGCN_GRU_SUM_LN><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+    else
+        gru_tc_kernel<CTGCN_GRU_EACH_LN><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+    CTGCN_LAUNCH_OK("gru_tc_kernel");
+    return CTGCN_OK;
+}
+
+}  // namespace ctgcn
+
+using namespace ctgcn;
+
+// out[128,64] = a[128,64] · b[64,64]ᵀ on the tensor cores with the split-bf16 scheme (test hook).
+// workspace: 16 KB + 2 KB device scratch.
+extern "C" int ctgcn_selftest_umma(const float* a, const float* b, float* out, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+    CTGCN_REQUIRE(a && b && out && workspace && workspace_bytes >= CHUNK_BYTES + 4 * H * sizeof(float),
+                  "selftest_umma: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    // reuse the weight packer: with d_in = 64 the first chunk (part 0, gate r, kc 0) is rows 0..63 × k 0..63 of w_ih.
+    // b is [64,64]; the packer reads w_ih as [3H, 64] but chunk 0 only touches its first 64 rows.
+    uint8_t* packed = (uint8_t*)workspace;
+    float* bias4 = (float*)(packed + CHUNK_BYTES);
+    pack_weights_kernel<<<(CHUNK_N * 8 + 255) / 256, 256, 0, st>>>(b, b, nullptr, nullptr, 64, packed, bias4);
+    CTGCN_LAUNCH_OK("pack_weights_kernel(selftest)");
+    const int smem = 2 * TILE_M * CHUNK_K * 2 + CHUNK_BYTES + 64;
+    CTGCN_CUDA_OK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    umma_selftest_kernel<<<1, 128, smem, st>>>(a, packed, out);
+    CTGCN_LAUNCH_OK("umma_selftest_kernel");
+    return CTGCN_OK;
+}

@@ -191,6 +191,26 @@ def test_model_golden(name, impl, lib, cuda_device):
         close(trans.cpu().numpy()[:, ::rs], c["expected"]["trans"], f"{name}.trans")
 
 
+# ----------------------------------------------------------------------------- tcgen05 building block
+def test_umma_selftest(lib, cuda_device):
+    """One weight chunk through the exact operand layouts / descriptors / bulk copy / TMEM loads of the GRU kernel:
+    out = A·Bᵀ with the split-bf16 (hi·hi + lo·hi + hi·lo) scheme must match fp64 to ~2^-16."""
+    import ctypes as C
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((128, 64)).astype(np.float32)
+    b = (rng.standard_normal((64, 64)) * 0.1).astype(np.float32)
+    ta, tb = torch.from_numpy(a).to(cuda_device), torch.from_numpy(b).to(cuda_device)
+    out = torch.zeros(128, 64, device=cuda_device)
+    ws = torch.zeros(32768, dtype=torch.uint8, device=cuda_device)
+    rc = lib.lib.ctgcn_selftest_umma(C.c_void_p(ta.data_ptr()), C.c_void_p(tb.data_ptr()), C.c_void_p(out.data_ptr()),
+                                     C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    lib.check(rc, "ctgcn_selftest_umma")
+    torch.cuda.synchronize()
+    ref = a.astype(np.float64) @ b.astype(np.float64).T
+    err = cases.relerr(out.cpu().numpy(), ref)
+    assert err < 3e-5, err
+
+
 # ----------------------------------------------------------------------------- GRU kernel alone
 @pytest.mark.parametrize("n,steps,d_in,h,bias", [(300, 5, 128, 128, True), (77, 1, 128, 128, True), (130, 12, 128, 128, False),
                                                  (65, 3, 500, 128, True), (40, 4, 20, 24, True), (257, 7, 64, 32, True),
