@@ -32,8 +32,9 @@ constexpr int CHUNK_N = 64, CHUNK_K = 64;
 constexpr int CHUNK_PLANE = CHUNK_N * CHUNK_K * 2;  // 8 KB: one bf16 plane of a weight chunk
 constexpr int CHUNK_BYTES = 2 * CHUNK_PLANE;        // hi + lo
 constexpr int STAGES = 5;
-constexpr int NUM_WORKER_WARPS = 8;
-constexpr int THREADS = 32 * (2 + NUM_WORKER_WARPS);
+constexpr int NUM_WORKER_WARPS = 8, NUM_LOADER_WARPS = 4;
+constexpr int FIRST_LOADER_WARP = 4, FIRST_WORKER_WARP = 8;   // warp 0 producer, warp 1 MMA, warps 2-3 idle
+constexpr int THREADS = 32 * (FIRST_WORKER_WARP + NUM_WORKER_WARPS);
 constexpr uint32_t TMEM_COLS = 512;
 
 // ---- shared memory map (bytes)
@@ -67,25 +68,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+    // the suspend-time hint lets the hardware park the warp instead of spinning through issue slots
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
     return ok;
 }
 // Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) {
-            printf("ctgcn gru_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
-                   bar, parity);
-            __trap();
-        }
+        if (++spins > (1u << 24)) __trap();   // ≈ seconds: a protocol bug fails the launch instead of hanging
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -152,10 +149,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ------------------------------------------------------------------------------------------------ bf16 split
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-    const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-    hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+    // packed conversions (F2FP, ALU pipe) instead of scalar F2F (XU pipe, shared with the MUFU gate math)
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+    lo = *reinterpret_cast<const uint32_t*>(&l2);
 }
 __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
     split2(v[0], v[1], hi.x, lo.x);
@@ -177,14 +175,19 @@ __device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float (&
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
-// Chunk order = consumption order of one step: part ∈ {X half0, X half1, H half0, H half1}, gate ∈ {r, z, n},
-// k-chunk.  X parts read W_ih [3H, d_in], H parts W_hh [3H, H].  Chunk image: bf16 hi plane then lo plane, element
-// (n, k) at (k/8)·1024 + n·16 + (k%8)·2  (no-swizzle K-major core matrices, LBO = 1024, SBO = 128).
+// Chunk order = consumption order of one step: part ∈ {X half0, X half1, H half0, H half1}; inside a part first the
+// "RZ" chunks (128 rows = this half's 64 r rows then its 64 z rows, 32 k each: one N=128 MMA feeds both gate
+// accumulators), then the n-gate chunks (64 rows × 64 k).  X parts read W_ih [3H, d_in], H parts W_hh [3H, H].
+// Chunk image: bf16 hi plane (8 KB) then lo plane; element (row, k) at (k/8)·(rows·16) + row·16 + (k%8)·2
+// (no-swizzle K-major core matrices: LBO = rows·16, SBO = 128).  Rows are pre-scaled for the ex2-based gate math.
+__host__ __device__ constexpr int chunks_per_part(int k) { return k / 32 + k / 64; }
+
 __global__ void pack_weights_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                                     const float* __restrict__ b_ih, const float* __restrict__ b_hh, int d_in,
-                                    uint8_t* __restrict__ packed, float* __restrict__ bias4) {
-    const int kcx = d_in / CHUNK_K, kch = H / CHUNK_K;
-    const int nchunks = 2 * 3 * kcx + 2 * 3 * kch;
+                                    uint8_t* __restrict__ packed, float* __restrict__ bias4, int prescale) {
+    constexpr float kLog2e = 1.4426950408889634f;
+    const int cx = chunks_per_part(d_in), chh = chunks_per_part(H);
+    const int nchunks = 2 * cx + 2 * chh;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < 4 * H) {
         const int g = t / H, f = t % H;
@@ -195,36 +198,40 @@ __global__ void pack_weights_kernel(const float* __restrict__ w_ih, const float*
             if (g == 2) v = b_ih[2 * H + f];
             if (g == 3) v = b_hh[2 * H + f];
         }
-        bias4[t] = v;
+        bias4[t] = prescale ? v * (g < 2 ? -kLog2e : 2.f * kLog2e) : v;
     }
-    if (t >= nchunks * CHUNK_N * (CHUNK_K / 8)) return;
-    const int c = t / (CHUNK_N * 8), rem = t % (CHUNK_N * 8);
-    const int kb = rem / CHUNK_N, n = rem % CHUNK_N;
-    int part, g, kc;
-    const int nx = 2 * 3 * kcx;
-    const float* w;
-    int ld;
-    if (c < nx) {
-        part = c / (3 * kcx);
-        g = (c / kcx) % 3;
-        kc = c % kcx;
-        w = w_ih;
-        ld = d_in;
-    } else {
-        const int cc = c - nx;
-        part = cc / (3 * kch);
-        g = (cc / kch) % 3;
-        kc = cc % kch;
-        w = w_hh;
-        ld = H;
+    // one thread per 16-byte unit (8 k-elements of one row): 512 units per plane
+    if (t >= nchunks * 512) return;
+    const int c = t / 512, unit = t % 512;
+    const bool is_x = c < 2 * cx;
+    const int cc = is_x ? c : c - 2 * cx;
+    const int per = is_x ? cx : chh;
+    const int ktot = is_x ? d_in : H;
+    const int half = cc / per, ci = cc % per;
+    const float* w = is_x ? w_ih : w_hh;
+    int row_in_chunk, kb, rows, src_row, k0;
+    if (ci < ktot / 32) {            // RZ chunk: 128 rows × 32 k
+        rows = 128;
+        kb = unit / 128;
+        row_in_chunk = unit % 128;
+        const int g = row_in_chunk / 64;
+        src_row = g * H + half * 64 + (row_in_chunk % 64);
+        k0 = ci * 32 + kb * 8;
+    } else {                          // n-gate chunk: 64 rows × 64 k
+        rows = 64;
+        kb = unit / 64;
+        row_in_chunk = unit % 64;
+        src_row = 2 * H + half * 64 + row_in_chunk;
+        k0 = (ci - ktot / 32) * 64 + kb * 8;
     }
-    const float* src = w + (int64_t)(g * H + part * CHUNK_N + n) * ld + kc * CHUNK_K + kb * 8;
+    const float scale = prescale ? (src_row < 2 * H ? -kLog2e : 2.f * kLog2e) : 1.f;
+    const float* src = w + (int64_t)src_row * ktot + k0;
     float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = src[i];
+    for (int i = 0; i < 8; ++i) v[i] = src[i] * scale;
     uint4 hi, lo;
     split8(v, hi, lo);
-    uint8_t* dst = packed + (size_t)c * CHUNK_BYTES + kb * 1024 + n * 16;
+    uint8_t* dst = packed + (size_t)c * CHUNK_BYTES + kb * (rows * 16) + row_in_chunk * 16;
     *reinterpret_cast<uint4*>(dst) = hi;
     *reinterpret_cast<uint4*>(dst + CHUNK_PLANE) = lo;
 }
@@ -244,18 +251,49 @@ struct Params {
     int num_tiles;
 };
 
-__device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
-__device__ __forceinline__ float tanh_fast(float v) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * v)); }
+// Gate math on pre-scaled pre-activations: pack_weights_kernel multiplies the r/z rows (and biases) by -log2(e) and
+// the n rows by 2·log2(e), so that sigmoid and tanh need a bare ex2 each.  One reciprocal serves r and z:
+// 1/((1+e^-a)(1+e^-b)); the exponentials are clamped so that the product stays finite.
+__device__ __forceinline__ float ex2_approx(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ void sigmoid2_scaled(float a, float b, float& r, float& z) {
+    const float ea = 1.f + fminf(ex2_approx(a), 1e18f);
+    const float eb = 1.f + fminf(ex2_approx(b), 1e18f);
+    const float t = rcp_approx(ea * eb);
+    r = t * eb;
+    z = t * ea;
+}
+__device__ __forceinline__ float tanh_scaled(float v) { return fmaf(-2.f, rcp_approx(1.f + ex2_approx(v)), 1.f); }
 
-// One weight chunk = 4 K-steps × 3 split products, all into one 64-column accumulator.
-__device__ __forceinline__ void issue_chunk(uint32_t a_hi, uint32_t a_lo, uint32_t b_chunk, uint32_t d_tmem, bool fresh) {
-    constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, CHUNK_N);
+// Descriptor words: hi word is constant (SBO = 128 B, version 1); lo word = (address >> 4) | (LBO >> 4) << 16.
+constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo) { return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; }
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred;
+}
+
+// One 16 KB weight chunk: KSTEPS K=16 steps × 3 split products (hi·hi, lo·hi, hi·lo) into one accumulator block.
+// a_lo32 / b_lo32: descriptor low words of the A hi plane at this chunk's first k and of the chunk's hi plane.
+template <int N, int KSTEPS>
+__device__ __forceinline__ void issue_chunk(uint32_t a_lo32, uint32_t b_lo32, uint32_t d_tmem, bool fresh) {
+    constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, N);
+    constexpr uint32_t A_STEP = (2 * TILE_M * 16) >> 4, B_STEP = (2 * N * 16) >> 4;
+    constexpr uint32_t A_LO_PLANE = A_PLANE >> 4, B_LO_PLANE = CHUNK_PLANE >> 4;
 #pragma unroll
-    for (int ks = 0; ks < CHUNK_K / 16; ++ks) {
-        const uint64_t ah = umma_desc(a_hi + ks * 2 * (TILE_M * 16), TILE_M * 16, 128);
-        const uint64_t al = umma_desc(a_lo + ks * 2 * (TILE_M * 16), TILE_M * 16, 128);
-        const uint64_t bh = umma_desc(b_chunk + ks * 2 * (CHUNK_N * 16), CHUNK_N * 16, 128);
-        const uint64_t bl = umma_desc(b_chunk + CHUNK_PLANE + ks * 2 * (CHUNK_N * 16), CHUNK_N * 16, 128);
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+        const uint64_t ah = desc64(a_lo32 + ks * A_STEP), al = desc64(a_lo32 + A_LO_PLANE + ks * A_STEP);
+        const uint64_t bh = desc64(b_lo32 + ks * B_STEP), bl = desc64(b_lo32 + B_LO_PLANE + ks * B_STEP);
         umma_bf16(d_tmem, ah, bh, idesc, (fresh && ks == 0) ? 0u : 1u);
         umma_bf16(d_tmem, al, bh, idesc, 1u);
         umma_bf16(d_tmem, ah, bl, idesc, 1u);
@@ -269,8 +307,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = sbase + SM_BAR;
     auto bar = [&](int i) { return bar0 + 8u * i; };
-    const int kcx = p.d_in / CHUNK_K;          // k-chunks of the input part
-    constexpr int kch = H / CHUNK_K;           // k-chunks of the recurrent part
+    const int cpx = chunks_per_part(p.d_in);   // weight chunks of one half of the input part
+    constexpr int cph = chunks_per_part(H);    // … of the recurrent part
     const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (threadIdx.x == 0) {
@@ -278,7 +316,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
             mbar_init(bar(BAR_W_FULL + s), 1);
             mbar_init(bar(BAR_W_EMPTY + s), 1);
         }
-        mbar_init(bar(BAR_U_READY), NUM_WORKER_WARPS);
+        mbar_init(bar(BAR_U_READY), NUM_LOADER_WARPS);
         mbar_init(bar(BAR_U_FREE), 1);
         mbar_init(bar(BAR_H_READY), NUM_WORKER_WARPS);
         mbar_init(bar(BAR_ACC_FULL0), 1);
@@ -298,11 +336,14 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM_PTR);
 
+    // 512 threads start with 128 registers each; the gate-math warps need more, the others far fewer: every role
+    // branch starts with its warpgroup's setmaxnreg (warps 0-3: 56, loaders 4-7: 112, workers 8-15: 168)
     if (warp == 0) {
         // ===================================================== weight producer
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            const int nx = 2 * 3 * kcx, nh = 2 * 3 * kch;
+            const int nx = 2 * cpx, nh = 2 * cph;
             for (int t = 0; t < my_tiles; ++t) {
                 for (int i = 0; i < p.steps; ++i) {
                     const int nchunks = nx + (i > 0 ? nh : 0);
@@ -321,27 +362,47 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        if (lane == 0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        // All 32 lanes run the (warp-uniform) control flow and the barrier waits; one elected lane issues.
+        {
             uint32_t stage = 0, phase = 0, gs = 0;
-            const uint32_t u_hi = sbase + SM_U, u_lo = u_hi + A_PLANE, h_hi = sbase + SM_H, h_lo = h_hi + A_PLANE;
-            auto run_part = [&](uint32_t a_hi, uint32_t a_lo, int kchunks, int half, bool recurrent) {
-                for (int g = 0; g < 3; ++g) {
-                    // accumulator column block: r, z shared by both parts; the n gate keeps W_in·x and W_hn·h apart
-                    const int blk = (g < 2) ? g : (recurrent ? 3 : 2);
-                    const uint32_t d = tmem + half * 256 + blk * 64;
-                    for (int kc = 0; kc < kchunks; ++kc) {
-                        mbar_wait(bar(BAR_W_FULL + stage), phase);
-                        tc_fence_after();
-                        const bool fresh = (kc == 0) && (!recurrent || g == 2);
-                        issue_chunk(a_hi + kc * (CHUNK_K / 8) * (TILE_M * 16), a_lo + kc * (CHUNK_K / 8) * (TILE_M * 16),
-                                    sbase + SM_W + stage * CHUNK_BYTES, d, fresh);
+            const uint32_t u_desc = desc_lo(sbase + SM_U, TILE_M * 16), h_desc = desc_lo(sbase + SM_H, TILE_M * 16);
+            // one part = one half (64 hidden features) of the input (A = U) or recurrent (A = h) contribution
+            auto run_part = [&](uint32_t a_desc, int ktot, int half, bool recurrent) {
+                const uint32_t d_rz = tmem + half * 256;                               // r | z blocks (128 columns)
+                const uint32_t d_n = tmem + half * 256 + (recurrent ? 192 : 128);      // W_in·x and W_hn·h kept apart
+                for (int kc = 0; kc < ktot / 32; ++kc) {
+                    mbar_wait(bar(BAR_W_FULL + stage), phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        issue_chunk<128, 2>(a_desc + kc * 4 * ((TILE_M * 16) >> 4),
+                                            desc_lo(sbase + SM_W + stage * CHUNK_BYTES, 128 * 16), d_rz, !recurrent && kc == 0);
                         umma_commit(bar(BAR_W_EMPTY + stage));
-                        if (++stage == STAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
                     }
                 }
+                for (int kc = 0; kc < ktot / 64; ++kc) {
+                    mbar_wait(bar(BAR_W_FULL + stage), phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        issue_chunk<64, 4>(a_desc + kc * 8 * ((TILE_M * 16) >> 4),
+                                           desc_lo(sbase + SM_W + stage * CHUNK_BYTES, 64 * 16), d_n, kc == 0);
+                        umma_commit(bar(BAR_W_EMPTY + stage));
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            };
+            auto commit = [&](int b) {
+                if (elect_one()) umma_commit(bar(b));
+                __syncwarp();
             };
             for (int t = 0; t < my_tiles; ++t) {
                 for (int i = 0; i < p.steps; ++i, ++gs) {
@@ -349,28 +410,75 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
                     mbar_wait(bar(BAR_U_READY), par);
                     mbar_wait(bar(BAR_ACC_FREE0), par ^ 1);
                     tc_fence_after();
-                    run_part(u_hi, u_lo, kcx, 0, false);
-                    if (i == 0) umma_commit(bar(BAR_ACC_FULL0));
+                    run_part(u_desc, p.d_in, 0, false);
+                    if (i == 0) commit(BAR_ACC_FULL0);
                     mbar_wait(bar(BAR_ACC_FREE1), par ^ 1);
                     tc_fence_after();
-                    run_part(u_hi, u_lo, kcx, 1, false);
-                    umma_commit(bar(BAR_U_FREE));
+                    run_part(u_desc, p.d_in, 1, false);
+                    commit(BAR_U_FREE);
                     if (i == 0) {
-                        umma_commit(bar(BAR_ACC_FULL1));
+                        commit(BAR_ACC_FULL1);
                     } else {
                         mbar_wait(bar(BAR_H_READY), par ^ 1);
                         tc_fence_after();
-                        run_part(h_hi, h_lo, kch, 0, true);
-                        umma_commit(bar(BAR_ACC_FULL0));
-                        run_part(h_hi, h_lo, kch, 1, true);
-                        umma_commit(bar(BAR_ACC_FULL1));
+                        run_part(h_desc, H, 0, true);
+                        commit(BAR_ACC_FULL0);
+                        run_part(h_desc, H, 1, true);
+                        commit(BAR_ACC_FULL1);
                     }
                 }
             }
         }
+    } else if (warp < FIRST_WORKER_WARP) {
+        // ===================================================== input loaders (warps 4-7; warps 2-3 idle)
+        if (warp < FIRST_LOADER_WARP) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        } else {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+            const int m = 32 * (warp - FIRST_LOADER_WARP) + lane;   // one tile row per thread
+            uint8_t* u_hi = smem + SM_U;
+            const int nkb = p.d_in / 8;
+            uint32_t gs = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                const int64_t srow = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + m;
+                const bool ok = srow < p.n;
+                for (int i = 0; i < p.steps; ++i, ++gs) {
+                    // the input part of the previous step's MMAs must have released the single U buffer
+                    mbar_wait(bar(BAR_U_FREE), (gs & 1) ^ 1);
+                    const float* src = p.seq + srow * p.srs + (int64_t)i * p.sss;
+                    // fp32 → bf16 hi/lo planes, 8 k-elements (16 B) per store; 8 k-blocks (16 LDG.128) in flight
+                    for (int kb0 = 0; kb0 < nkb; kb0 += 8) {
+                        float4 v[16];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (ok) {
+                                v[2 * u] = __ldg(reinterpret_cast<const float4*>(src + (kb0 + u) * 8));
+                                v[2 * u + 1] = __ldg(reinterpret_cast<const float4*>(src + (kb0 + u) * 8 + 4));
+                            } else {
+                                v[2 * u] = v[2 * u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int kb = kb0 + u;
+                            const float f8[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w,
+                                                 v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
+                            uint4 hi, lo;
+                            split8(f8, hi, lo);
+                            *reinterpret_cast<uint4*>(u_hi + kb * (TILE_M * 16) + m * 16) = hi;
+                            *reinterpret_cast<uint4*>(u_hi + A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(BAR_U_READY));
+                }
+            }
+        }
     } else {
-        // ===================================================== workers
-        const int ww = warp - 2;
+        // ===================================================== workers (warps 8-15): gate math, h, Σh, LayerNorm
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+        const int ww = warp - FIRST_WORKER_WARP;
         const int q = warp & 3;          // TMEM lane quarter this warp may access
         const int ch = ww >> 2;          // which 32 of a half's 64 features this thread owns
         const int m = 32 * q + lane;     // row inside the tile
@@ -378,9 +486,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
         const float* bias = reinterpret_cast<const float*>(smem + SM_BIAS);
         const float* lnw = reinterpret_cast<const float*>(smem + SM_LN);
         float* red = reinterpret_cast<float*>(smem + SM_RED);
-        uint8_t* u_hi = smem + SM_U;
         uint8_t* h_hi = smem + SM_H;
-        const int kb_per_thread = (p.d_in / 8) / 2;
         uint32_t gs = 0;
 
         // LayerNorm over the row: this thread holds 64 of its 128 values, the partner warp (other ch) the rest
@@ -426,38 +532,6 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
 
             for (int i = 0; i < p.steps; ++i, ++gs) {
                 const uint32_t par = gs & 1;
-                // ---- (1) stage this step's input rows: fp32 → bf16 hi/lo planes, 8 k-elements (16 B) per store
-                mbar_wait(bar(BAR_U_FREE), par ^ 1);
-                {
-                    const float* src = p.seq + row * p.srs + (int64_t)i * p.sss;
-                    for (int kb0 = 0; kb0 < kb_per_thread; kb0 += 4) {
-                        float4 v[8];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int kb = ch * kb_per_thread + kb0 + u;
-                            if (valid) {
-                                v[2 * u] = __ldg(reinterpret_cast<const float4*>(src + kb * 8));
-                                v[2 * u + 1] = __ldg(reinterpret_cast<const float4*>(src + kb * 8 + 4));
-                            } else {
-                                v[2 * u] = v[2 * u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int kb = ch * kb_per_thread + kb0 + u;
-                            const float f8[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w,
-                                                 v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
-                            uint4 hi, lo;
-                            split8(f8, hi, lo);
-                            *reinterpret_cast<uint4*>(u_hi + kb * (TILE_M * 16) + m * 16) = hi;
-                            *reinterpret_cast<uint4*>(u_hi + A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
-                        }
-                    }
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(BAR_U_READY));
-
                 // ---- (2) gates, one half (64 hidden features) at a time; this thread owns 32 of them, 8 per pass
                 float h0[32];   // first half of h_i, published only when no MMA reads h_{i-1} any more
                 auto put_h8 = [&](const float (&f8)[8], int f) {
@@ -501,9 +575,9 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int f = f0 + j;
-                            const float r = sigmoid_fast(gr[j] + bias[f]);
-                            const float z = sigmoid_fast(gz[j] + bias[H + f]);
-                            const float nn = tanh_fast(gi[j] + bias[2 * H + f] + r * (gh[j] + bias[3 * H + f]));
+                            float r, z;
+                            sigmoid2_scaled(gr[j] + bias[f], gz[j] + bias[H + f], r, z);
+                            const float nn = tanh_scaled(fmaf(r, gh[j] + bias[3 * H + f], gi[j] + bias[2 * H + f]));
                             hn8[j] = nn + z * (hold[j] - nn);
                         }
                         if (hf == 0) {
@@ -538,58 +612,66 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
 }
 
 // ------------------------------------------------------------------------------------------------ self test
-// out[128×64] = A[128×64] · B[64×64]ᵀ through exactly the operand layouts, descriptors, bulk copy and TMEM loads
-// the GRU kernel uses (one weight chunk, 12 MMAs).  Exposed as ctgcn_selftest_umma for the GPU test-suite.
-__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __restrict__ a, const uint8_t* __restrict__ bchunk,
+// out[128×192] = A[128×64] · Wsel[192×64]ᵀ where Wsel = rows {0..63, 128..191, 256..319} of w[384×64] — i.e. half 0 of the
+// input part for d_in = 64 — through exactly the packer, chunk images, bulk copies, descriptors (N=128 and N=64),
+// split-bf16 MMAs and TMEM loads of the GRU kernel.  Exposed as ctgcn_selftest_umma for the GPU test-suite.
+__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __restrict__ a, const uint8_t* __restrict__ packed,
                                                                 float* __restrict__ out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
-    constexpr int A_PL = TILE_M * CHUNK_K * 2;  // 16 KB plane
-    const uint32_t sa = sbase, sb = sbase + 2 * A_PL, bar_w = sb + CHUNK_BYTES, bar_d = bar_w + 8, tptr = bar_d + 8;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, m = threadIdx.x;
+    const uint32_t sa = sbase, sb = sbase + 2 * A_PLANE, bar_w = sb + 3 * CHUNK_BYTES, bar_d = bar_w + 8, tptr = bar_d + 8;
+    const int warp = threadIdx.x >> 5, m = threadIdx.x;
     if (threadIdx.x == 0) {
         mbar_init(bar_w, 1);
         mbar_init(bar_d, 1);
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(tptr, 64);
-    for (int kb = 0; kb < CHUNK_K / 8; ++kb) {
+    if (warp == 0) tmem_alloc(tptr, 256);
+    for (int kb = 0; kb < 8; ++kb) {
         float f8[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f8[e] = a[m * CHUNK_K + kb * 8 + e];
+        for (int e = 0; e < 8; ++e) f8[e] = a[m * 64 + kb * 8 + e];
         uint4 hi, lo;
         split8(f8, hi, lo);
         *reinterpret_cast<uint4*>(smem + kb * (TILE_M * 16) + m * 16) = hi;
-        *reinterpret_cast<uint4*>(smem + A_PL + kb * (TILE_M * 16) + m * 16) = lo;
+        *reinterpret_cast<uint4*>(smem + A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
     }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + 2 * A_PL + CHUNK_BYTES + 16);
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(bar_w, CHUNK_BYTES);
-        bulk_g2s(sb, bchunk, CHUNK_BYTES, bar_w);
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + 2 * A_PLANE + 3 * CHUNK_BYTES + 16);
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(bar_w, 3 * CHUNK_BYTES);
+            bulk_g2s(sb, packed, 3 * CHUNK_BYTES, bar_w);
+        }
+        __syncwarp();
         mbar_wait(bar_w, 0);
         tc_fence_after();
-        issue_chunk(sa, sa + A_PL, sb, tmem, true);
-        umma_commit(bar_d);
+        if (elect_one()) {
+            const uint32_t a_desc = desc_lo(sa, TILE_M * 16);
+            issue_chunk<128, 2>(a_desc, desc_lo(sb, 128 * 16), tmem, true);
+            issue_chunk<128, 2>(a_desc + 4 * ((TILE_M * 16) >> 4), desc_lo(sb + CHUNK_BYTES, 128 * 16), tmem, false);
+            issue_chunk<64, 4>(a_desc, desc_lo(sb + 2 * CHUNK_BYTES, 64 * 16), tmem + 128, true);
+            umma_commit(bar_d);
+        }
+        __syncwarp();
     }
     mbar_wait(bar_d, 0);
     tc_fence_after();
     const uint32_t tl = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
 #pragma unroll
-    for (int c = 0; c < 64; c += 16) {
+    for (int c = 0; c < 192; c += 16) {
         float v[16];
         tmem_ld16(tl + c, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) out[m * 64 + c + j] = v[j];
+        for (int j = 0; j < 16; ++j) out[m * 192 + c + j] = v[j];
     }
-    (void)lane;
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 64);
+    if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
 }  // namespace
@@ -601,15 +683,15 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
     if (h != H || (d_in != 64 && d_in != 128)) return 1;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     if (!al16(seq) || !al16(y) || (srs & 3) || (sss & 3) || (yrs & 3) || (yss & 3)) return 1;
-    const int nchunks = 2 * 3 * (d_in / CHUNK_K) + 2 * 3 * (H / CHUNK_K);
+    const int nchunks = 2 * chunks_per_part(d_in) + 2 * chunks_per_part(H);
     const size_t packed_bytes = (size_t)nchunks * CHUNK_BYTES;
     CTGCN_REQUIRE(ws && ws_bytes >= packed_bytes + 4 * H * sizeof(float), "gru_tc: workspace too small");
     uint8_t* packed = (uint8_t*)ws;
     float* bias4 = (float*)(packed + packed_bytes);
     {
         ProfScope prof(PROF_PACK, st);
-        const int threads = nchunks * CHUNK_N * (CHUNK_K / 8);
-        pack_weights_kernel<<<(threads + 255) / 256, 256, 0, st>>>(w_ih, w_hh, b_ih, b_hh, d_in, packed, bias4);
+        const int threads = nchunks * 512;
+        pack_weights_kernel<<<(threads + 255) / 256, 256, 0, st>>>(w_ih, w_hh, b_ih, b_hh, d_in, packed, bias4, 1);
         CTGCN_LAUNCH_OK("pack_weights_kernel");
     }
     static int sm_count = 0;
@@ -650,20 +732,20 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
 
 using namespace ctgcn;
 
-// out[128,64] = a[128,64] · b[64,64]ᵀ on the tensor cores with the split-bf16 scheme (test hook).
-// workspace: 16 KB + 2 KB device scratch.
-extern "C" int ctgcn_selftest_umma(const float* a, const float* b, float* out, void* workspace, size_t workspace_bytes,
+// Test hook: out[128,192] = a[128,64] · w[{0..63,128..191,256..319}, :]ᵀ (w is [384,64]) on the tensor cores with the
+// split-bf16 scheme, through the GRU kernel's packer / chunk images / descriptors.  workspace ≥ 160 KB device memory.
+extern "C" int ctgcn_selftest_umma(const float* a, const float* w, float* out, void* workspace, size_t workspace_bytes,
                                    void* stream) {
-    CTGCN_REQUIRE(a && b && out && workspace && workspace_bytes >= CHUNK_BYTES + 4 * H * sizeof(float),
-                  "selftest_umma: bad arguments");
+    const int nchunks = 2 * chunks_per_part(64) + 2 * chunks_per_part(H);
+    CTGCN_REQUIRE(a && w && out && workspace && workspace_bytes >= (size_t)nchunks * CHUNK_BYTES + 4 * H * sizeof(float),
+                  "selftest_umma: bad arguments (workspace needs %zu bytes)", (size_t)nchunks * CHUNK_BYTES + 4 * H * sizeof(float));
     cudaStream_t st = (cudaStream_t)stream;
-    // reuse the weight packer: with d_in = 64 the first chunk (part 0, gate r, kc 0) is rows 0..63 × k 0..63 of w_ih.
-    // b is [64,64]; the packer reads w_ih as [3H, 64] but chunk 0 only touches its first 64 rows.
     uint8_t* packed = (uint8_t*)workspace;
-    float* bias4 = (float*)(packed + CHUNK_BYTES);
-    pack_weights_kernel<<<(CHUNK_N * 8 + 255) / 256, 256, 0, st>>>(b, b, nullptr, nullptr, 64, packed, bias4);
+    float* bias4 = (float*)(packed + (size_t)nchunks * CHUNK_BYTES);
+    // only the first 3 chunks (input part, half 0) are packed: 3 × 512 threads; w doubles as a dummy w_hh (never read)
+    pack_weights_kernel<<<(3 * 512 + 255) / 256, 256, 0, st>>>(w, w, nullptr, nullptr, 64, packed, bias4, 0);
     CTGCN_LAUNCH_OK("pack_weights_kernel(selftest)");
-    const int smem = 2 * TILE_M * CHUNK_K * 2 + CHUNK_BYTES + 64;
+    const int smem = 2 * A_PLANE + 3 * CHUNK_BYTES + 64;
     CTGCN_CUDA_OK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     umma_selftest_kernel<<<1, 128, smem, st>>>(a, packed, out);
     CTGCN_LAUNCH_OK("umma_selftest_kernel");

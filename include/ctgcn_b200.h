@@ -112,9 +112,10 @@ int ctgcn_gru_seq_fwd(const float* seq, int64_t seq_row_stride, int64_t seq_step
                       const float* ln_w, const float* ln_b, float eps, int mode, float* y, int64_t y_row_stride,
                       int64_t y_step_stride, void* workspace, size_t workspace_bytes, void* stream);
 int ctgcn_set_gru_impl(int impl);
-/* test hook: out[128,64] = a[128,64] b[64,64]^T through the tcgen05 operand layouts / descriptors / TMEM loads the GRU
- * kernel uses (split-bf16, three MMAs per product).  workspace >= 18432 bytes of device memory. */
-int ctgcn_selftest_umma(const float* a, const float* b, float* out, void* workspace, size_t workspace_bytes, void* stream);
+/* test hook: out[128,192] = a[128,64] w[{0..63,128..191,256..319},:]^T (w is [384,64]) through the tcgen05 weight packer,
+ * chunk images, descriptors and TMEM loads the GRU kernel uses (split-bf16, three MMAs per product).
+ * workspace >= 512 KB of device memory. */
+int ctgcn_selftest_umma(const float* a, const float* w, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- CoreDiffusion.forward (layers.py:38-63)
  * y[n_rows, h] (row stride ldy) = LayerNorm(sum_i GRU(relu(cumsum_i A_i x))).

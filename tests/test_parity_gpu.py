@@ -193,20 +193,22 @@ def test_model_golden(name, impl, lib, cuda_device):
 
 # ----------------------------------------------------------------------------- tcgen05 building block
 def test_umma_selftest(lib, cuda_device):
-    """One weight chunk through the exact operand layouts / descriptors / bulk copy / TMEM loads of the GRU kernel:
-    out = A·Bᵀ with the split-bf16 (hi·hi + lo·hi + hi·lo) scheme must match fp64 to ~2^-16."""
+    """Half 0 of the input part for d_in = 64 through the exact packer / chunk images / bulk copies / descriptors
+    (N=128 and N=64) / TMEM loads of the GRU kernel: the split-bf16 product (hi·hi + lo·hi + hi·lo) must match fp64
+    to ~2^-16."""
     import ctypes as C
     rng = np.random.default_rng(0)
     a = rng.standard_normal((128, 64)).astype(np.float32)
-    b = (rng.standard_normal((64, 64)) * 0.1).astype(np.float32)
-    ta, tb = torch.from_numpy(a).to(cuda_device), torch.from_numpy(b).to(cuda_device)
-    out = torch.zeros(128, 64, device=cuda_device)
-    ws = torch.zeros(32768, dtype=torch.uint8, device=cuda_device)
-    rc = lib.lib.ctgcn_selftest_umma(C.c_void_p(ta.data_ptr()), C.c_void_p(tb.data_ptr()), C.c_void_p(out.data_ptr()),
+    w = (rng.standard_normal((384, 64)) * 0.1).astype(np.float32)
+    ta, tw = torch.from_numpy(a).to(cuda_device), torch.from_numpy(w).to(cuda_device)
+    out = torch.zeros(128, 192, device=cuda_device)
+    ws = torch.zeros(512 * 1024, dtype=torch.uint8, device=cuda_device)
+    rc = lib.lib.ctgcn_selftest_umma(C.c_void_p(ta.data_ptr()), C.c_void_p(tw.data_ptr()), C.c_void_p(out.data_ptr()),
                                      C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     lib.check(rc, "ctgcn_selftest_umma")
     torch.cuda.synchronize()
-    ref = a.astype(np.float64) @ b.astype(np.float64).T
+    sel = np.concatenate([np.arange(0, 64), np.arange(128, 192), np.arange(256, 320)])
+    ref = a.astype(np.float64) @ w[sel].astype(np.float64).T
     err = cases.relerr(out.cpu().numpy(), ref)
     assert err < 3e-5, err
 
