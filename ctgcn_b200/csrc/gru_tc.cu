@@ -346,15 +346,23 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
             const int nx = 2 * cpx, nh = 2 * cph;
             for (int t = 0; t < my_tiles; ++t) {
                 for (int i = 0; i < p.steps; ++i) {
-                    const int nchunks = nx + (i > 0 ? nh : 0);
-                    for (int c = 0; c < nchunks; ++c) {
-                        mbar_wait(bar(BAR_W_EMPTY + stage), phase ^ 1);
-                        mbar_expect_tx(bar(BAR_W_FULL + stage), CHUNK_BYTES);
-                        bulk_g2s(sbase + SM_W + stage * CHUNK_BYTES, p.packed + (size_t)c * CHUNK_BYTES, CHUNK_BYTES,
-                                 bar(BAR_W_FULL + stage));
-                        if (++stage == STAGES) {
-                            stage = 0;
-                            phase ^= 1;
+                    // consumption order of the MMA issuer: X half0, [H half0], X half1, [H half1]
+                    // (packed order is X half0, X half1, H half0, H half1)
+                    for (int seg = 0; seg < 4; ++seg) {
+                        const bool rec = seg & 1;
+                        if (rec && i == 0) continue;
+                        const int half = seg >> 1;
+                        const int first = rec ? nx + half * cph : half * cpx;
+                        const int count = rec ? cph : cpx;
+                        for (int c = first; c < first + count; ++c) {
+                            mbar_wait(bar(BAR_W_EMPTY + stage), phase ^ 1);
+                            mbar_expect_tx(bar(BAR_W_FULL + stage), CHUNK_BYTES);
+                            bulk_g2s(sbase + SM_W + stage * CHUNK_BYTES, p.packed + (size_t)c * CHUNK_BYTES, CHUNK_BYTES,
+                                     bar(BAR_W_FULL + stage));
+                            if (++stage == STAGES) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
                         }
                     }
                 }
@@ -411,21 +419,22 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
                     mbar_wait(bar(BAR_ACC_FREE0), par ^ 1);
                     tc_fence_after();
                     run_part(u_desc, p.d_in, 0, false);
-                    if (i == 0) commit(BAR_ACC_FULL0);
-                    mbar_wait(bar(BAR_ACC_FREE1), par ^ 1);
-                    tc_fence_after();
-                    run_part(u_desc, p.d_in, 1, false);
-                    commit(BAR_U_FREE);
                     if (i == 0) {
-                        commit(BAR_ACC_FULL1);
+                        commit(BAR_ACC_FULL0);
                     } else {
+                        // the recurrence h_{i-1} → gates → h_i is the critical chain: the first half's recurrent part
+                        // goes ahead of the second half's input part (same chunk order in the producer)
                         mbar_wait(bar(BAR_H_READY), par ^ 1);
                         tc_fence_after();
                         run_part(h_desc, H, 0, true);
                         commit(BAR_ACC_FULL0);
-                        run_part(h_desc, H, 1, true);
-                        commit(BAR_ACC_FULL1);
                     }
+                    mbar_wait(bar(BAR_ACC_FREE1), par ^ 1);
+                    tc_fence_after();
+                    run_part(u_desc, p.d_in, 1, false);
+                    commit(BAR_U_FREE);
+                    if (i > 0) run_part(h_desc, H, 1, true);
+                    commit(BAR_ACC_FULL1);
                 }
             }
         }
