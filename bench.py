@@ -300,6 +300,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _, _ = timed(step_e2e, args.steps, 1)
     launches_total = int(tot(launches))
+    h2d = tot(len(owned) * n * d * 4)          # collectives stay above the rank-0-only reporting below
 
     # ---- correctness guard on the measured configuration: finite output of the right shape
     out = step_resident()
@@ -338,7 +339,6 @@ def main():
 
     ms_step = ms / args.steps
     value = e_agg / (ms_step * 1e-3)
-    h2d = tot(len(owned) * n * d * 4)
     d2h = T * n * d * 4
     line = {
         "metric": "edges-aggregated/s, CTGCN CoreDiffusion forward", "value": value, "unit": "edges-aggregated/s",
