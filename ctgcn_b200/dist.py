@@ -84,6 +84,7 @@ def ctgcn_forward_sharded(model, x_list, adj_list):
     ``model.gather_output`` else this rank's slice [T, rows, D]; model_type 'S' adds the list of MLP outputs
     (None for snapshots owned by other ranks)."""
     from .layers import _guard
+    from .models import _HostFeatureStager
 
     G, r = world_size(), rank()
     T = len(x_list)
@@ -92,8 +93,9 @@ def ctgcn_forward_sharded(model, x_list, adj_list):
     dev = model.norm.weight.device
     trans_list = [None] * T
     hx_local, n = None, None
+    stager = _HostFeatureStager(x_list, owned, dev)
     for j, t in enumerate(owned):
-        trans = model.mlp_list[t](x_list[t])
+        trans = model.mlp_list[t](stager.get(t))
         trans_list[t] = trans
         if hx_local is None:
             n = trans.shape[0]

@@ -17,6 +17,48 @@ from .layers import CoreDiffusion, MLP, _guard
 from . import dist as _dist
 
 
+_copy_streams = {}
+
+
+class _HostFeatureStager:
+    """Features handed over as (pinned) HOST tensors are uploaded on a side stream, `depth` snapshots ahead of the
+    compute stream, so that the H2D copy of snapshot t+1 overlaps the kernels of snapshot t.  Device tensors and
+    sparse inputs pass through untouched."""
+
+    def __init__(self, x_list, order, dev, depth=2):
+        self.x_list, self.order, self.dev, self.depth = x_list, list(order), dev, depth
+        self.stream = _copy_streams.setdefault(str(dev), torch.cuda.Stream(device=dev))
+        self.pending = {}
+        self.next = 0
+
+    def _is_host_dense(self, x):
+        return isinstance(x, torch.Tensor) and x.layout == torch.strided and not x.is_cuda
+
+    def _issue(self):
+        while self.next < len(self.order) and len(self.pending) < self.depth:
+            t = self.order[self.next]
+            self.next += 1
+            x = self.x_list[t]
+            if self._is_host_dense(x):
+                with torch.cuda.stream(self.stream):
+                    xd = x.to(self.dev, dtype=torch.float32, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self.stream)
+                self.pending[t] = (xd, ev)
+
+    def get(self, t):
+        self._issue()
+        x = self.x_list[t]
+        if not self._is_host_dense(x):
+            return x
+        xd, ev = self.pending.pop(t)
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(ev)
+        xd.record_stream(cur)
+        self._issue()
+        return xd
+
+
 class CDN(nn.Module):
     """Stack of ``diffusion_num`` CoreDiffusion layers sharing one adj_list — reference models.py:8-42."""
 
@@ -123,8 +165,9 @@ class CTGCN(nn.Module):
         T = len(x_list)
         dev = self.norm.weight.device
         hx, trans_list = None, []
+        stager = _HostFeatureStager(x_list, range(T), dev)
         for t in range(T):
-            trans = self.mlp_list[t](x_list[t])
+            trans = self.mlp_list[t](stager.get(t))
             trans_list.append(trans)
             if hx is None:
                 hx = torch.empty(trans.shape[0], T, self.output_dim, dtype=torch.float32, device=dev)
