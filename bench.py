@@ -339,9 +339,19 @@ def main():
                                 "unit": "TFLOP/s", "avg_ms": kern["gru"]["ms"] / kern["gru"]["launches"],
                                 "launches": kern["gru"]["launches"], "share_of_step": kern["gru"]["ms"] / ms,
                                 "algorithmic_flops_per_step": gru_core_flops + gru_temporal_flops}
-    for v in by_kernel.values():
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.config, {})
+    except (OSError, ValueError):
+        pass
+    for name, v in by_kernel.items():
         v["frac"] = v["achieved"] / v["peak"]
-        v["traffic"] = None
+        # DRAM bytes per launch from the committed ncu capture of this kernel at this configuration (core-GRU launch for gru_seq)
+        v["traffic"] = traffic.get({"cumspmm": "cumspmm", "gru_seq": "gru_seq"}[name])
+    if "gru_seq" in by_kernel:
+        g = by_kernel["gru_seq"]
+        g["issued_mma_tflops"] = 3.0 * g["achieved"] if args.gru_impl != "simt" else None
+        g["note"] = "achieved = algorithmic flops; the tcgen05 path issues 3 bf16 MMAs per product (split precision, 1e-4 parity bar)"
     other_ms = {k: v["ms"] for k, v in kern.items() if k not in ("spmm", "gru")}
     dominant = max(by_kernel, key=lambda k: by_kernel[k]["share_of_step"]) if by_kernel else None
     roofline = dict(by_kernel[dominant], kernel=dominant, peak_source=peaks["source"]) if dominant else None
