@@ -580,14 +580,42 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
                             for (int j = 0; j < 8; ++j) gh[j] = hold[j] = 0.f;
                         }
                         tmem_ld_wait();
-                        float hn8[8];
+                        // Gate math written stage by stage over the 8 features so that the 8 dependent chains
+                        // (ex2 → rcp → ex2 → rcp) are interleaved instead of being scheduled one element at a time.
+                        // Pre-activations are pre-scaled (see pack_weights_kernel): sigmoid(a) = 1/(1 + 2^a'), tanh(s) = 1 − 2/(1 + 2^s').
+                        float hn8[8], ea[8], eb[8], zz[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const int f = f0 + j;
-                            float r, z;
-                            sigmoid2_scaled(gr[j] + bias[f], gz[j] + bias[H + f], r, z);
-                            const float nn = tanh_scaled(fmaf(r, gh[j] + bias[3 * H + f], gi[j] + bias[2 * H + f]));
-                            hn8[j] = nn + z * (hold[j] - nn);
+                            ea[j] = gr[j] + bias[f0 + j];
+                            eb[j] = gz[j] + bias[H + f0 + j];
+                            gi[j] += bias[2 * H + f0 + j];
+                            gh[j] += bias[3 * H + f0 + j];
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            ea[j] = ex2_approx(ea[j]);
+                            eb[j] = ex2_approx(eb[j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            ea[j] = 1.f + fminf(ea[j], 1e18f);     // clamped so that the product below stays finite
+                            eb[j] = 1.f + fminf(eb[j], 1e18f);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) hn8[j] = rcp_approx(ea[j] * eb[j]);   // one reciprocal for r and z
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            zz[j] = hn8[j] * ea[j];                                          // z
+                            gi[j] = fmaf(hn8[j] * eb[j], gh[j], gi[j]);                      // W_in x + b_in + r ⊙ (W_hn h + b_hn)
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) gi[j] = ex2_approx(gi[j]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) gi[j] = rcp_approx(1.f + gi[j]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float nn = fmaf(-2.f, gi[j], 1.f);                         // tanh
+                            hn8[j] = fmaf(zz[j], hold[j] - nn, nn);                          // (1 − z) n + z h
                         }
                         if (hf == 0) {
 #pragma unroll
