@@ -102,6 +102,14 @@ extern "C" int ctgcn_prof_collect(double* ms, int64_t* counts, int reset) {
     return CTGCN_OK;
 }
 
+namespace ctgcn {
+void set_gru_trace(long long* buf);
+}
+extern "C" int ctgcn_debug_gru_trace(int64_t* device_buf) {
+    set_gru_trace(reinterpret_cast<long long*>(device_buf));
+    return CTGCN_OK;
+}
+
 extern "C" int ctgcn_set_gru_impl(int impl) {
     CTGCN_REQUIRE(impl >= CTGCN_IMPL_AUTO && impl <= CTGCN_IMPL_TCGEN05, "set_gru_impl: unknown implementation %d", impl);
     g_gru_impl.store(impl);

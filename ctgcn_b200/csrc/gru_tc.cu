@@ -249,7 +249,14 @@ struct Params {
     float* y;
     int64_t yrs, yss;
     int num_tiles;
+    long long* trace;   // optional [16 events][64 steps] clock64 stamps of block 0 (ctgcn_debug_gru_trace), else NULL
 };
+
+// debug timeline: event e of global step gs of block 0
+#define GRU_TRACE(e, gs)                                                                   \
+    do {                                                                                   \
+        if (p.trace && blockIdx.x == 0 && (gs) < 64u) p.trace[(e) * 64 + (gs)] = clock64(); \
+    } while (0)
 
 // Gate math on pre-scaled pre-activations: pack_weights_kernel multiplies the r/z rows (and biases) by -log2(e) and
 // the n rows by 2·log2(e), so that sigmoid and tanh need a bare ex2 each.  One reciprocal serves r and z:
@@ -415,10 +422,13 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
             for (int t = 0; t < my_tiles; ++t) {
                 for (int i = 0; i < p.steps; ++i, ++gs) {
                     const uint32_t par = gs & 1;
+                    if (lane == 0) GRU_TRACE(0, gs);
                     mbar_wait(bar(BAR_U_READY), par);
                     mbar_wait(bar(BAR_ACC_FREE0), par ^ 1);
                     tc_fence_after();
+                    if (lane == 0) GRU_TRACE(1, gs);
                     run_part(u_desc, p.d_in, 0, false);
+                    if (lane == 0) GRU_TRACE(2, gs);
                     if (i == 0) {
                         commit(BAR_ACC_FULL0);
                     } else {
@@ -426,15 +436,20 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
                         // goes ahead of the second half's input part (same chunk order in the producer)
                         mbar_wait(bar(BAR_H_READY), par ^ 1);
                         tc_fence_after();
+                        if (lane == 0) GRU_TRACE(3, gs);
                         run_part(h_desc, H, 0, true);
                         commit(BAR_ACC_FULL0);
+                        if (lane == 0) GRU_TRACE(4, gs);
                     }
                     mbar_wait(bar(BAR_ACC_FREE1), par ^ 1);
                     tc_fence_after();
+                    if (lane == 0) GRU_TRACE(5, gs);
                     run_part(u_desc, p.d_in, 1, false);
                     commit(BAR_U_FREE);
+                    if (lane == 0) GRU_TRACE(6, gs);
                     if (i > 0) run_part(h_desc, H, 1, true);
                     commit(BAR_ACC_FULL1);
+                    if (lane == 0) GRU_TRACE(7, gs);
                 }
             }
         }
@@ -454,6 +469,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
                 for (int i = 0; i < p.steps; ++i, ++gs) {
                     // the input part of the previous step's MMAs must have released the single U buffer
                     mbar_wait(bar(BAR_U_FREE), (gs & 1) ^ 1);
+                    if (threadIdx.x == FIRST_LOADER_WARP * 32) GRU_TRACE(13, gs);
                     const float* src = p.seq + srow * p.srs + (int64_t)i * p.sss;
                     // fp32 → bf16 hi/lo planes, 8 k-elements (16 B) per store; 8 k-blocks (16 LDG.128) in flight
                     for (int kb0 = 0; kb0 < nkb; kb0 += 8) {
@@ -481,6 +497,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar(BAR_U_READY));
+                    if (threadIdx.x == FIRST_LOADER_WARP * 32) GRU_TRACE(14, gs);
                 }
             }
         }
@@ -552,8 +569,10 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
                 };
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
+                    if (threadIdx.x == FIRST_WORKER_WARP * 32) GRU_TRACE(8 + 2 * hf, gs);
                     mbar_wait(bar(BAR_ACC_FULL0 + hf), par);
                     tc_fence_after();
+                    if (threadIdx.x == FIRST_WORKER_WARP * 32) GRU_TRACE(9 + 2 * hf, gs);
                     if (hf == 1) {
 #pragma unroll
                         for (int j8 = 0; j8 < 32; j8 += 8) {
@@ -637,6 +656,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(BAR_H_READY));
+                if (threadIdx.x == FIRST_WORKER_WARP * 32) GRU_TRACE(12, gs);
                 if (MODE == CTGCN_GRU_EACH_LN) layer_norm_store(acc_out, p.y + row * p.yrs + (int64_t)i * p.yss, valid);
             }
             if (MODE == CTGCN_GRU_SUM_LN) layer_norm_store(acc_out, p.y + row * p.yrs, valid);
@@ -713,6 +733,9 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
 
 }  // namespace
 
+static long long* g_gru_trace = nullptr;
+void set_gru_trace(long long* buf) { g_gru_trace = buf; }
+
 // returns 0 = done, <0 = error, 1 = shape not supported by this path
 int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* w_ih,
                   const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
@@ -755,6 +778,7 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
     p.yrs = yrs;
     p.yss = yss;
     p.num_tiles = (int)((n + TILE_M - 1) / TILE_M);
+    p.trace = g_gru_trace;
     const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
     ProfScope prof(PROF_GRU, st);
     if (mode == CTGCN_GRU_SUM_LN)

@@ -112,6 +112,9 @@ int ctgcn_gru_seq_fwd(const float* seq, int64_t seq_row_stride, int64_t seq_step
                       const float* ln_w, const float* ln_b, float eps, int mode, float* y, int64_t y_row_stride,
                       int64_t y_step_stride, void* workspace, size_t workspace_bytes, void* stream);
 int ctgcn_set_gru_impl(int impl);
+/* debug: when non-NULL, block 0 of every following tcgen05 GRU launch writes clock64() stamps of its pipeline events
+ * into device_buf[16 events][64 steps] (int64); NULL switches it off. */
+int ctgcn_debug_gru_trace(int64_t* device_buf);
 /* test hook: out[128,192] = a[128,64] w[{0..63,128..191,256..319},:]^T (w is [384,64]) through the tcgen05 weight packer,
  * chunk images, descriptors and TMEM loads the GRU kernel uses (split-bf16, three MMAs per product).
  * workspace >= 512 KB of device memory. */
