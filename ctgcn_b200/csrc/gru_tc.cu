@@ -459,33 +459,39 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
             asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         } else {
             asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
-            const int m = 32 * (warp - FIRST_LOADER_WARP) + lane;   // one tile row per thread
+            // A warp owns 32 tile rows.  Per load instruction its lanes cover 8 rows × 4 k-blocks (r = lane%8, c = lane/8):
+            // 128 contiguous bytes per row (8 L1 wavefronts instead of 32 for a row-per-lane mapping) and the 16-byte
+            // shared-memory stores of one 8-lane phase hit 8 consecutive rows of one k-block (conflict-free).
+            const int r8 = lane & 7, c4 = lane >> 3;
+            const int row_base = 32 * (warp - FIRST_LOADER_WARP);
             uint8_t* u_hi = smem + SM_U;
-            const int nkb = p.d_in / 8;
+            const int nkg = p.d_in / 32;             // k-groups of 4 k-blocks
+            const int nit = 4 * nkg;                 // (row-group, k-group) iterations per step: 16 for d_in = 128
             uint32_t gs = 0;
             for (int t = 0; t < my_tiles; ++t) {
-                const int64_t srow = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + m;
-                const bool ok = srow < p.n;
+                const int64_t tile_row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M;
                 for (int i = 0; i < p.steps; ++i, ++gs) {
-                    // the input part of the previous step's MMAs must have released the single U buffer
-                    mbar_wait(bar(BAR_U_FREE), (gs & 1) ^ 1);
-                    if (threadIdx.x == FIRST_LOADER_WARP * 32) GRU_TRACE(13, gs);
-                    const float* src = p.seq + srow * p.srs + (int64_t)i * p.sss;
-                    // fp32 → bf16 hi/lo planes, 8 k-elements (16 B) per store; 8 k-blocks (16 LDG.128) in flight
-                    for (int kb0 = 0; kb0 < nkb; kb0 += 8) {
-                        float4 v[16];
+                    const float* base = p.seq + (int64_t)i * p.sss;
+                    float4 v[16];
+                    auto load_batch = [&](int it0) {   // 8 iterations = 16 LDG.128 in flight per lane
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            if (ok) {
-                                v[2 * u] = __ldg(reinterpret_cast<const float4*>(src + (kb0 + u) * 8));
-                                v[2 * u + 1] = __ldg(reinterpret_cast<const float4*>(src + (kb0 + u) * 8 + 4));
+                            const int it = it0 + u, rg = it & 3, kg = it >> 2;
+                            const int64_t srow = tile_row0 + row_base + 8 * rg + r8;
+                            if (srow < p.n) {
+                                const float* src = base + srow * p.srs + (4 * kg + c4) * 8;
+                                v[2 * u] = __ldg(reinterpret_cast<const float4*>(src));
+                                v[2 * u + 1] = __ldg(reinterpret_cast<const float4*>(src + 4));
                             } else {
                                 v[2 * u] = v[2 * u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
                             }
                         }
+                    };
+                    auto store_batch = [&](int it0) {  // fp32 → bf16 hi/lo planes, 8 k-elements (16 B) per store
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            const int kb = kb0 + u;
+                            const int it = it0 + u, rg = it & 3, kg = it >> 2;
+                            const int m = row_base + 8 * rg + r8, kb = 4 * kg + c4;
                             const float f8[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w,
                                                  v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
                             uint4 hi, lo;
@@ -493,6 +499,15 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
                             *reinterpret_cast<uint4*>(u_hi + kb * (TILE_M * 16) + m * 16) = hi;
                             *reinterpret_cast<uint4*>(u_hi + A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
                         }
+                    };
+                    load_batch(0);   // global loads are issued BEFORE the buffer is free: their latency is off the loop
+                    // the input part of the previous step's MMAs must have released the single U buffer
+                    mbar_wait(bar(BAR_U_FREE), (gs & 1) ^ 1);
+                    if (threadIdx.x == FIRST_LOADER_WARP * 32) GRU_TRACE(13, gs);
+                    store_batch(0);
+                    for (int it0 = 8; it0 < nit; it0 += 8) {
+                        load_batch(it0);
+                        store_batch(it0);
                     }
                     fence_proxy_async();
                     __syncwarp();
