@@ -6,17 +6,20 @@
 // significant bits) and each product is issued as three MMAs  hi·hi + lo·hi + hi·lo  accumulated in fp32 in
 // TMEM (error ≈ 2^-17 per product, ~1e-5 on the layer output).
 //
-// One persistent CTA per SM owns 128-node tiles for the WHOLE sequence (h and Σh never leave the SM):
-//   warp 0     weight producer: the packed [64 gate-rows × 64 k] hi/lo chunks (16 KB, exact shared-memory images,
-//              built once per call by pack_weights_kernel) stream from L2 through a 5-stage ring with
-//              cp.async.bulk + mbarrier complete_tx
-//   warp 1     MMA issuer (one elected lane): tcgen05.mma cta_group::1 kind::f16, M=128 N=64 K=16, operands
-//              described by no-swizzle K-major shared-memory descriptors, accumulators in TMEM
-//   warps 2-9  workers: stage the step's input rows (fp32 → bf16 hi/lo planes in UMMA core-matrix layout),
-//              read accumulators with tcgen05.ld, apply the gates, write h back as the next step's A operand,
-//              keep Σh (or emit LayerNorm(h_s)) and finally LayerNorm.
-// A step is processed in two halves of 64 hidden features so that the 512 TMEM columns hold two accumulator
-// sets (r,z,in,hn × 64 columns each): the gate math of one half overlaps the MMAs of the other.
+// One persistent CTA (512 threads) per SM owns 128-node tiles for the WHOLE sequence (h and Σh never leave the SM):
+//   warp 0      weight producer: packed 24 KB chunks (192 gate rows × 32 k, bf16 hi|lo planes, exact shared-memory
+//               images built once per call by pack_weights_kernel) stream from L2 through a 3-stage ring with
+//               cp.async.bulk + mbarrier complete_tx
+//   warp 1      MMA issuer (one elected lane): tcgen05.mma cta_group::1 kind::f16, M=128 N=192 K=16, operands described
+//               by no-swizzle K-major shared-memory descriptors, accumulators in TMEM.  N = 192 keeps the operand
+//               fetch (A 4 KB + B 6 KB per 96-cycle MMA) under the 128 B/cycle shared-memory bandwidth of the SM.
+//   warps 4-7   input loaders: fp32 rows → bf16 hi/lo planes in UMMA core-matrix order, one step ahead of the MMAs
+//   warps 8-15  gate math: tcgen05.ld the accumulators, ex2/rcp sigmoid & tanh, write h back as the next step's A operand,
+//               keep Σh (or emit LayerNorm(h_s)), final LayerNorm.  setmaxnreg moves registers to them.
+// A step is processed in two halves of 64 hidden features.  Each half owns one accumulator set of 256 TMEM columns
+//   [ W_in·x | r | z | W_hn·h ]   (64 columns each)
+// so the input part (A = U) is ONE N=192 MMA stream into columns [0,192) and the recurrent part (A = h) ONE N=192
+// stream into columns [64,256); the gate math of one half overlaps the MMAs of the other.
 //
 // Shapes: H = 128, d_in ∈ {64, 128} (everything the 128-d configurations need); other shapes use gru_simt.cu.
 #include <cuda_bf16.h>
@@ -28,23 +31,25 @@ namespace {
 
 constexpr int H = 128;
 constexpr int TILE_M = 128;
-constexpr int CHUNK_N = 64, CHUNK_K = 64;
-constexpr int CHUNK_PLANE = CHUNK_N * CHUNK_K * 2;  // 8 KB: one bf16 plane of a weight chunk
-constexpr int CHUNK_BYTES = 2 * CHUNK_PLANE;        // hi + lo
-constexpr int STAGES = 5;
+constexpr int CHUNK_ROWS = 192, CHUNK_K = 32;
+constexpr int CHUNK_PLANE = CHUNK_ROWS * CHUNK_K * 2;  // 12 KB: one bf16 plane of a weight chunk
+constexpr int CHUNK_BYTES = 2 * CHUNK_PLANE;           // hi + lo = 24 KB
+constexpr int STAGES = 3;
 constexpr int NUM_WORKER_WARPS = 8, NUM_LOADER_WARPS = 4;
 constexpr int FIRST_LOADER_WARP = 4, FIRST_WORKER_WARP = 8;   // warp 0 producer, warp 1 MMA, warps 2-3 idle
 constexpr int THREADS = 32 * (FIRST_WORKER_WARP + NUM_WORKER_WARPS);
 constexpr uint32_t TMEM_COLS = 512;
+// accumulator set layout (columns inside a 256-column set)
+constexpr uint32_t COL_IN = 0, COL_R = 64, COL_Z = 128, COL_HN = 192;
 
 // ---- shared memory map (bytes)
-constexpr int A_PLANE = TILE_M * H * 2;             // 32 KB: one bf16 plane of a 128×128 operand tile
-constexpr int SM_U = 0;                             // U hi | U lo
-constexpr int SM_H = SM_U + 2 * A_PLANE;            // h hi | h lo
-constexpr int SM_W = SM_H + 2 * A_PLANE;            // weight ring
-constexpr int SM_BIAS = SM_W + STAGES * CHUNK_BYTES;  // [4][H] fp32: b_r(+), b_z(+), b_in, b_hn
-constexpr int SM_LN = SM_BIAS + 4 * H * 4;          // ln_w | ln_b
-constexpr int SM_RED = SM_LN + 2 * H * 4;           // [2 buffers][2 column halves][128 rows] fp32
+constexpr int A_PLANE = TILE_M * H * 2;               // 32 KB: one bf16 plane of a 128×128 operand tile
+constexpr int SM_U = 0;                               // U hi | U lo
+constexpr int SM_H = SM_U + 2 * A_PLANE;              // h hi | h lo
+constexpr int SM_W = SM_H + 2 * A_PLANE;              // weight ring
+constexpr int SM_BIAS = SM_W + STAGES * CHUNK_BYTES;  // [4][H] fp32 (pre-scaled): b_r(+), b_z(+), b_in, b_hn
+constexpr int SM_LN = SM_BIAS + 4 * H * 4;            // ln_w | ln_b
+constexpr int SM_RED = SM_LN + 2 * H * 4;             // [2 buffers][2 column halves][128 rows] fp32
 constexpr int SM_BAR = SM_RED + 2 * 2 * TILE_M * 4;
 constexpr int NUM_BARS = 2 * STAGES + 7;
 constexpr int SM_TMEM_PTR = SM_BAR + NUM_BARS * 8;
@@ -82,7 +87,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) __trap();   // ≈ seconds: a protocol bug fails the launch instead of hanging
+        if (++spins > (1u << 24)) __trap();
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -104,13 +109,13 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 
-// K-major, no-swizzle ("interleaved") operand: 8-row × 16-byte core matrices; LBO = byte distance between the two
-// 8-element K halves of one K=16 MMA, SBO = byte distance between consecutive 8-row groups.  Descriptor version 1.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n
+// K-major, no-swizzle ("interleaved") operands: 8-row × 16-byte core matrices; LBO = byte distance between the two
+// 8-element K halves of one K=16 MMA (= rows·16 in the layouts used here), SBO = 128 B between consecutive 8-row
+// groups.  The 64-bit descriptor's high word is constant (SBO, version 1); the low word = (address >> 4) | (LBO >> 4) << 16.
+constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo) { return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; }
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
@@ -125,23 +130,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred;
 }
+// No "memory" clobber on the loads on purpose: TMEM is not memory the compiler knows about, and without the clobber the
+// loads of the next 8-feature pass can be hoisted above the shared-memory stores of the current one (tmem_ld_wait keeps
+// its clobber and orders the consumers).
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
+                 : "r"(taddr));
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
@@ -175,12 +176,13 @@ __device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float (&
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
-// Chunk order = consumption order of one step: part ∈ {X half0, X half1, H half0, H half1}; inside a part first the
-// "RZ" chunks (128 rows = this half's 64 r rows then its 64 z rows, 32 k each: one N=128 MMA feeds both gate
-// accumulators), then the n-gate chunks (64 rows × 64 k).  X parts read W_ih [3H, d_in], H parts W_hh [3H, H].
-// Chunk image: bf16 hi plane (8 KB) then lo plane; element (row, k) at (k/8)·(rows·16) + row·16 + (k%8)·2
-// (no-swizzle K-major core matrices: LBO = rows·16, SBO = 128).  Rows are pre-scaled for the ex2-based gate math.
-__host__ __device__ constexpr int chunks_per_part(int k) { return k / 32 + k / 64; }
+// Packed order: part ∈ {X half0, X half1, H half0, H half1}, then k-chunk.  An X chunk holds the rows
+// [n-gate | r | z] of W_ih for the half's 64 hidden features, an H chunk the rows [r | z | n-gate] of W_hh
+// (192 rows × 32 k).  Image: bf16 hi plane (12 KB) then lo plane; element (row, k) at (k/8)·3072 + row·16 + (k%8)·2
+// (no-swizzle K-major core matrices: LBO = 3072, SBO = 128).  With `prescale`, the r/z rows and biases are multiplied
+// by −log2(e) and the n rows by 2·log2(e) so that sigmoid/tanh need a bare ex2 (gate math below).
+__host__ __device__ constexpr int chunks_per_part(int k) { return k / CHUNK_K; }
+constexpr int UNITS_PER_PLANE = CHUNK_ROWS * (CHUNK_K / 8);  // 16-byte units
 
 __global__ void pack_weights_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                                     const float* __restrict__ b_ih, const float* __restrict__ b_hh, int d_in,
@@ -200,43 +202,30 @@ __global__ void pack_weights_kernel(const float* __restrict__ w_ih, const float*
         }
         bias4[t] = prescale ? v * (g < 2 ? -kLog2e : 2.f * kLog2e) : v;
     }
-    // one thread per 16-byte unit (8 k-elements of one row): 512 units per plane
-    if (t >= nchunks * 512) return;
-    const int c = t / 512, unit = t % 512;
+    if (t >= nchunks * UNITS_PER_PLANE) return;
+    const int c = t / UNITS_PER_PLANE, unit = t % UNITS_PER_PLANE;
     const bool is_x = c < 2 * cx;
     const int cc = is_x ? c : c - 2 * cx;
     const int per = is_x ? cx : chh;
     const int ktot = is_x ? d_in : H;
-    const int half = cc / per, ci = cc % per;
+    const int half = cc / per, kc = cc % per;
+    const int kb = unit / CHUNK_ROWS, row = unit % CHUNK_ROWS;
+    const int blk = row / 64, f = row % 64;
+    const int gate = is_x ? (blk == 0 ? 2 : blk - 1) : blk;    // X: [n, r, z]   H: [r, z, n]
     const float* w = is_x ? w_ih : w_hh;
-    int row_in_chunk, kb, rows, src_row, k0;
-    if (ci < ktot / 32) {            // RZ chunk: 128 rows × 32 k
-        rows = 128;
-        kb = unit / 128;
-        row_in_chunk = unit % 128;
-        const int g = row_in_chunk / 64;
-        src_row = g * H + half * 64 + (row_in_chunk % 64);
-        k0 = ci * 32 + kb * 8;
-    } else {                          // n-gate chunk: 64 rows × 64 k
-        rows = 64;
-        kb = unit / 64;
-        row_in_chunk = unit % 64;
-        src_row = 2 * H + half * 64 + row_in_chunk;
-        k0 = (ci - ktot / 32) * 64 + kb * 8;
-    }
-    const float scale = prescale ? (src_row < 2 * H ? -kLog2e : 2.f * kLog2e) : 1.f;
-    const float* src = w + (int64_t)src_row * ktot + k0;
+    const float* src = w + (int64_t)(gate * H + half * 64 + f) * ktot + kc * CHUNK_K + kb * 8;
+    const float scale = prescale ? (gate < 2 ? -kLog2e : 2.f * kLog2e) : 1.f;
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = src[i] * scale;
     uint4 hi, lo;
     split8(v, hi, lo);
-    uint8_t* dst = packed + (size_t)c * CHUNK_BYTES + kb * (rows * 16) + row_in_chunk * 16;
+    uint8_t* dst = packed + (size_t)c * CHUNK_BYTES + kb * (CHUNK_ROWS * 16) + row * 16;
     *reinterpret_cast<uint4*>(dst) = hi;
     *reinterpret_cast<uint4*>(dst + CHUNK_PLANE) = lo;
 }
 
-// ------------------------------------------------------------------------------------------------ roles
+// ------------------------------------------------------------------------------------------------ kernel pieces
 struct Params {
     const float* seq;
     int64_t srs, sss, n;
@@ -249,18 +238,15 @@ struct Params {
     float* y;
     int64_t yrs, yss;
     int num_tiles;
-    long long* trace;   // optional [16 events][64 steps] clock64 stamps of block 0 (ctgcn_debug_gru_trace), else NULL
+    long long* trace;   // optional [24 events][64 steps] clock64 stamps of block 0 (ctgcn_debug_gru_trace), else NULL
 };
 
 // debug timeline: event e of global step gs of block 0
-#define GRU_TRACE(e, gs)                                                                   \
-    do {                                                                                   \
+#define GRU_TRACE(e, gs)                                                                    \
+    do {                                                                                    \
         if (p.trace && blockIdx.x == 0 && (gs) < 64u) p.trace[(e) * 64 + (gs)] = clock64(); \
     } while (0)
 
-// Gate math on pre-scaled pre-activations: pack_weights_kernel multiplies the r/z rows (and biases) by -log2(e) and
-// the n rows by 2·log2(e), so that sigmoid and tanh need a bare ex2 each.  One reciprocal serves r and z:
-// 1/((1+e^-a)(1+e^-b)); the exponentials are clamped so that the product stays finite.
 __device__ __forceinline__ float ex2_approx(float v) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -271,39 +257,30 @@ __device__ __forceinline__ float rcp_approx(float v) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
 }
-__device__ __forceinline__ void sigmoid2_scaled(float a, float b, float& r, float& z) {
-    const float ea = 1.f + fminf(ex2_approx(a), 1e18f);
-    const float eb = 1.f + fminf(ex2_approx(b), 1e18f);
-    const float t = rcp_approx(ea * eb);
-    r = t * eb;
-    z = t * ea;
-}
-__device__ __forceinline__ float tanh_scaled(float v) { return fmaf(-2.f, rcp_approx(1.f + ex2_approx(v)), 1.f); }
 
-// Descriptor words: hi word is constant (SBO = 128 B, version 1); lo word = (address >> 4) | (LBO >> 4) << 16.
-constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
-__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo) { return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16); }
-__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; }
-__device__ __forceinline__ uint32_t elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred;
-}
-
-// One 16 KB weight chunk: KSTEPS K=16 steps × 3 split products (hi·hi, lo·hi, hi·lo) into one accumulator block.
-// a_lo32 / b_lo32: descriptor low words of the A hi plane at this chunk's first k and of the chunk's hi plane.
-template <int N, int KSTEPS>
-__device__ __forceinline__ void issue_chunk(uint32_t a_lo32, uint32_t b_lo32, uint32_t d_tmem, bool fresh) {
-    constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, N);
-    constexpr uint32_t A_STEP = (2 * TILE_M * 16) >> 4, B_STEP = (2 * N * 16) >> 4;
+// One 24 KB weight chunk (192 rows × 32 k): 2 K-steps × 3 split products (hi·hi, lo·hi, hi·lo) of N = 192 into 192
+// consecutive accumulator columns starting at d_tmem.  a_lo32 / b_lo32: descriptor low words of the A hi plane at this
+// chunk's first k and of the chunk's hi plane.
+//   fresh       : the very first MMA overwrites all 192 columns (input part, first chunk)
+//   split_first : recurrent part, first chunk — columns [0,128) (r|z) accumulate on the input part's result while
+//                 columns [128,192) (W_hn·h) start fresh: that one MMA is issued as an N=128 and an N=64 instruction.
+__device__ __forceinline__ void issue_chunk(uint32_t a_lo32, uint32_t b_lo32, uint32_t d_tmem, bool fresh, bool split_first) {
+    constexpr uint32_t idesc192 = umma_idesc_bf16(TILE_M, 192), idesc128 = umma_idesc_bf16(TILE_M, 128),
+                       idesc64 = umma_idesc_bf16(TILE_M, 64);
+    constexpr uint32_t A_STEP = (2 * TILE_M * 16) >> 4, B_STEP = (2 * CHUNK_ROWS * 16) >> 4;
     constexpr uint32_t A_LO_PLANE = A_PLANE >> 4, B_LO_PLANE = CHUNK_PLANE >> 4;
 #pragma unroll
-    for (int ks = 0; ks < KSTEPS; ++ks) {
+    for (int ks = 0; ks < CHUNK_K / 16; ++ks) {
         const uint64_t ah = desc64(a_lo32 + ks * A_STEP), al = desc64(a_lo32 + A_LO_PLANE + ks * A_STEP);
         const uint64_t bh = desc64(b_lo32 + ks * B_STEP), bl = desc64(b_lo32 + B_LO_PLANE + ks * B_STEP);
-        umma_bf16(d_tmem, ah, bh, idesc, (fresh && ks == 0) ? 0u : 1u);
-        umma_bf16(d_tmem, al, bh, idesc, 1u);
-        umma_bf16(d_tmem, ah, bl, idesc, 1u);
+        if (split_first && ks == 0) {
+            umma_bf16(d_tmem, ah, bh, idesc128, 1u);
+            umma_bf16(d_tmem + 128, ah, desc64(b_lo32 + ((128 * 16) >> 4)), idesc64, 0u);
+        } else {
+            umma_bf16(d_tmem, ah, bh, idesc192, (fresh && ks == 0) ? 0u : 1u);
+        }
+        umma_bf16(d_tmem, al, bh, idesc192, 1u);
+        umma_bf16(d_tmem, ah, bl, idesc192, 1u);
     }
 }
 
@@ -350,7 +327,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            const int nx = 2 * cpx, nh = 2 * cph;
+            const int nx = 2 * cpx;
             for (int t = 0; t < my_tiles; ++t) {
                 for (int i = 0; i < p.steps; ++i) {
                     // consumption order of the MMA issuer: X half0, [H half0], X half1, [H half1]
@@ -384,28 +361,14 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
             const uint32_t u_desc = desc_lo(sbase + SM_U, TILE_M * 16), h_desc = desc_lo(sbase + SM_H, TILE_M * 16);
             // one part = one half (64 hidden features) of the input (A = U) or recurrent (A = h) contribution
             auto run_part = [&](uint32_t a_desc, int ktot, int half, bool recurrent) {
-                const uint32_t d_rz = tmem + half * 256;                               // r | z blocks (128 columns)
-                const uint32_t d_n = tmem + half * 256 + (recurrent ? 192 : 128);      // W_in·x and W_hn·h kept apart
-                for (int kc = 0; kc < ktot / 32; ++kc) {
+                const uint32_t d = tmem + half * 256 + (recurrent ? COL_R : COL_IN);
+                for (int kc = 0; kc < ktot / CHUNK_K; ++kc) {
                     mbar_wait(bar(BAR_W_FULL + stage), phase);
                     tc_fence_after();
                     if (elect_one()) {
-                        issue_chunk<128, 2>(a_desc + kc * 4 * ((TILE_M * 16) >> 4),
-                                            desc_lo(sbase + SM_W + stage * CHUNK_BYTES, 128 * 16), d_rz, !recurrent && kc == 0);
-                        umma_commit(bar(BAR_W_EMPTY + stage));
-                    }
-                    __syncwarp();
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-                for (int kc = 0; kc < ktot / 64; ++kc) {
-                    mbar_wait(bar(BAR_W_FULL + stage), phase);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        issue_chunk<64, 4>(a_desc + kc * 8 * ((TILE_M * 16) >> 4),
-                                           desc_lo(sbase + SM_W + stage * CHUNK_BYTES, 64 * 16), d_n, kc == 0);
+                        issue_chunk(a_desc + kc * (CHUNK_K / 8) * ((TILE_M * 16) >> 4),
+                                    desc_lo(sbase + SM_W + stage * CHUNK_BYTES, CHUNK_ROWS * 16), d, !recurrent && kc == 0,
+                                    recurrent && kc == 0);
                         umma_commit(bar(BAR_W_EMPTY + stage));
                     }
                     __syncwarp();
@@ -573,7 +536,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
 
             for (int i = 0; i < p.steps; ++i, ++gs) {
                 const uint32_t par = gs & 1;
-                // ---- (2) gates, one half (64 hidden features) at a time; this thread owns 32 of them, 8 per pass
+                // gates, one half (64 hidden features) at a time; this thread owns 32 of them, 8 per pass
                 float h0[32];   // first half of h_i, published only when no MMA reads h_{i-1} any more
                 auto put_h8 = [&](const float (&f8)[8], int f) {
                     uint4 hi, lo;
@@ -588,23 +551,16 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
                     mbar_wait(bar(BAR_ACC_FULL0 + hf), par);
                     tc_fence_after();
                     if (threadIdx.x == FIRST_WORKER_WARP * 32) GRU_TRACE(9 + 2 * hf, gs);
-                    if (hf == 1) {
-#pragma unroll
-                        for (int j8 = 0; j8 < 32; j8 += 8) {
-                            const float f8[8] = {h0[j8], h0[j8 + 1], h0[j8 + 2], h0[j8 + 3], h0[j8 + 4], h0[j8 + 5], h0[j8 + 6], h0[j8 + 7]};
-                            put_h8(f8, ch * 32 + j8);
-                        }
-                    }
 #pragma unroll
                     for (int sub = 0; sub < 4; ++sub) {
                         const int f0 = hf * 64 + ch * 32 + sub * 8;             // first of 8 features
-                        const uint32_t col = hf * 256 + ch * 32 + sub * 8;      // + blk*64
+                        const uint32_t col = hf * 256 + ch * 32 + sub * 8;      // + gate block
                         float gr[8], gz[8], gi[8], gh[8], hold[8];
-                        tmem_ld8(tmem_lane + col, gr);
-                        tmem_ld8(tmem_lane + col + 64, gz);
-                        tmem_ld8(tmem_lane + col + 128, gi);
+                        tmem_ld8(tmem_lane + col + COL_R, gr);
+                        tmem_ld8(tmem_lane + col + COL_Z, gz);
+                        tmem_ld8(tmem_lane + col + COL_IN, gi);
                         if (i > 0) {
-                            tmem_ld8(tmem_lane + col + 192, gh);
+                            tmem_ld8(tmem_lane + col + COL_HN, gh);
                             const int kb = f0 >> 3;
                             const uint4 hi = *reinterpret_cast<const uint4*>(h_hi + kb * (TILE_M * 16) + m * 16);
                             const uint4 lo = *reinterpret_cast<const uint4*>(h_hi + A_PLANE + kb * (TILE_M * 16) + m * 16);
@@ -615,8 +571,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
                         }
                         tmem_ld_wait();
                         // Gate math written stage by stage over the 8 features so that the 8 dependent chains
-                        // (ex2 → rcp → ex2 → rcp) are interleaved instead of being scheduled one element at a time.
-                        // Pre-activations are pre-scaled (see pack_weights_kernel): sigmoid(a) = 1/(1 + 2^a'), tanh(s) = 1 − 2/(1 + 2^s').
+                        // (ex2 → rcp → ex2 → rcp) are interleaved.  Pre-activations are pre-scaled (pack_weights_kernel):
+                        // sigmoid(a) = 1/(1 + 2^a'), tanh(s) = 1 − 2/(1 + 2^s'); one reciprocal serves r and z.
                         float hn8[8], ea[8], eb[8], zz[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -636,7 +592,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
                             eb[j] = 1.f + fminf(eb[j], 1e18f);
                         }
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) hn8[j] = rcp_approx(ea[j] * eb[j]);   // one reciprocal for r and z
+                        for (int j = 0; j < 8; ++j) hn8[j] = rcp_approx(ea[j] * eb[j]);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             zz[j] = hn8[j] * ea[j];                                          // z
@@ -655,7 +611,13 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) h0[sub * 8 + j] = hn8[j];
                         } else {
-                            put_h8(hn8, f0);   // all MMAs of this step are complete: h may be overwritten in place
+                            // every MMA that reads h_{i-1} has completed (acc1 full): h may be overwritten in place.
+                            // The held-back first half is published piecewise here so that its ALU work hides
+                            // under the MUFU latency of this pass.
+                            const float f8[8] = {h0[sub * 8], h0[sub * 8 + 1], h0[sub * 8 + 2], h0[sub * 8 + 3],
+                                                 h0[sub * 8 + 4], h0[sub * 8 + 5], h0[sub * 8 + 6], h0[sub * 8 + 7]};
+                            put_h8(f8, ch * 32 + sub * 8);
+                            put_h8(hn8, f0);
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -663,11 +625,12 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
                             else acc_out[hf * 32 + sub * 8 + j] = hn8[j];
                         }
                     }
+                    if (threadIdx.x == FIRST_WORKER_WARP * 32 && hf == 1) GRU_TRACE(16, gs);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar(BAR_ACC_FREE0 + hf));
                 }
-                // ---- (3) h_i is complete in shared memory: the next step's recurrent MMAs may read it
+                // h_i is complete in shared memory: the next step's recurrent MMAs may read it
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(BAR_H_READY));
@@ -684,14 +647,16 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
 }
 
 // ------------------------------------------------------------------------------------------------ self test
-// out[128×192] = A[128×64] · Wsel[192×64]ᵀ where Wsel = rows {0..63, 128..191, 256..319} of w[384×64] — i.e. half 0 of the
-// input part for d_in = 64 — through exactly the packer, chunk images, bulk copies, descriptors (N=128 and N=64),
-// split-bf16 MMAs and TMEM loads of the GRU kernel.  Exposed as ctgcn_selftest_umma for the GPU test-suite.
-__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __restrict__ a, const uint8_t* __restrict__ packed,
-                                                                float* __restrict__ out) {
+// One half-step of a GRU cell's pre-activations for d_in = 64 through exactly the packer, chunk images, bulk copies,
+// descriptors, split-bf16 MMAs (incl. the split-first recurrent MMA) and TMEM loads of the GRU kernel:
+//   out[128×256] = [ x·W_inᵀ | x·W_irᵀ + h·W_hrᵀ | x·W_izᵀ + h·W_hzᵀ | h·W_hnᵀ ]   for hidden features 0..63
+// with x [128,64], h [128,128], w_ih [384,64], w_hh [384,128], no pre-scaling.  Exposed as ctgcn_selftest_umma.
+__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __restrict__ x, const float* __restrict__ h,
+                                                                const uint8_t* __restrict__ packed, float* __restrict__ out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t sa = sbase, sb = sbase + 2 * A_PLANE, bar_w = sb + 3 * CHUNK_BYTES, bar_d = bar_w + 8, tptr = bar_d + 8;
+    const uint32_t su = sbase, sh = sbase + 2 * A_PLANE, sw = sbase + 4 * A_PLANE;
+    const uint32_t bar_w = sw + CHUNK_BYTES, bar_d = bar_w + 8, tptr = bar_d + 8;
     const int warp = threadIdx.x >> 5, m = threadIdx.x;
     if (threadIdx.x == 0) {
         mbar_init(bar_w, 1);
@@ -699,47 +664,61 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tptr, 256);
-    for (int kb = 0; kb < 8; ++kb) {
+    for (int kb = 0; kb < 16; ++kb) {
         float f8[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f8[e] = a[m * 64 + kb * 8 + e];
         uint4 hi, lo;
+        if (kb < 8) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f8[e] = x[m * 64 + kb * 8 + e];
+            split8(f8, hi, lo);
+            *reinterpret_cast<uint4*>(smem + kb * (TILE_M * 16) + m * 16) = hi;
+            *reinterpret_cast<uint4*>(smem + A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f8[e] = h[m * 128 + kb * 8 + e];
         split8(f8, hi, lo);
-        *reinterpret_cast<uint4*>(smem + kb * (TILE_M * 16) + m * 16) = hi;
-        *reinterpret_cast<uint4*>(smem + A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
+        *reinterpret_cast<uint4*>(smem + 2 * A_PLANE + kb * (TILE_M * 16) + m * 16) = hi;
+        *reinterpret_cast<uint4*>(smem + 3 * A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
     }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + 2 * A_PLANE + 3 * CHUNK_BYTES + 16);
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + 4 * A_PLANE + CHUNK_BYTES + 16);
     if (warp == 0) {
-        if (elect_one()) {
-            mbar_expect_tx(bar_w, 3 * CHUNK_BYTES);
-            bulk_g2s(sb, packed, 3 * CHUNK_BYTES, bar_w);
+        // packed order for d_in = 64: X half0 = chunks 0,1; X half1 = 2,3; H half0 = 4..7
+        const int order[6] = {0, 1, 4, 5, 6, 7};
+        uint32_t par = 0;
+        for (int j = 0; j < 6; ++j) {
+            if (elect_one()) {
+                mbar_expect_tx(bar_w, CHUNK_BYTES);
+                bulk_g2s(sw, packed + (size_t)order[j] * CHUNK_BYTES, CHUNK_BYTES, bar_w);
+            }
+            __syncwarp();
+            mbar_wait(bar_w, par);
+            tc_fence_after();
+            if (elect_one()) {
+                const bool rec = j >= 2;
+                const int kc = rec ? j - 2 : j;
+                issue_chunk(desc_lo(rec ? sh : su, TILE_M * 16) + kc * (CHUNK_K / 8) * ((TILE_M * 16) >> 4),
+                            desc_lo(sw, CHUNK_ROWS * 16), tmem + (rec ? COL_R : COL_IN), !rec && kc == 0, rec && kc == 0);
+                umma_commit(bar_d);
+            }
+            __syncwarp();
+            mbar_wait(bar_d, par);     // the single weight buffer is reused: wait for the MMAs that read it
+            tc_fence_after();
+            par ^= 1;
         }
-        __syncwarp();
-        mbar_wait(bar_w, 0);
-        tc_fence_after();
-        if (elect_one()) {
-            const uint32_t a_desc = desc_lo(sa, TILE_M * 16);
-            issue_chunk<128, 2>(a_desc, desc_lo(sb, 128 * 16), tmem, true);
-            issue_chunk<128, 2>(a_desc + 4 * ((TILE_M * 16) >> 4), desc_lo(sb + CHUNK_BYTES, 128 * 16), tmem, false);
-            issue_chunk<64, 4>(a_desc, desc_lo(sb + 2 * CHUNK_BYTES, 64 * 16), tmem + 128, true);
-            umma_commit(bar_d);
-        }
-        __syncwarp();
     }
-    mbar_wait(bar_d, 0);
+    __syncthreads();
     tc_fence_after();
     const uint32_t tl = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-#pragma unroll
-    for (int c = 0; c < 192; c += 16) {
-        float v[16];
-        tmem_ld16(tl + c, v);
+    for (int c = 0; c < 256; c += 8) {
+        float v[8];
+        tmem_ld8(tl + c, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) out[m * 192 + c + j] = v[j];
+        for (int j = 0; j < 8; ++j) out[m * 256 + c + j] = v[j];
     }
     tc_fence_before();
     __syncthreads();
@@ -765,7 +744,7 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
     float* bias4 = (float*)(packed + packed_bytes);
     {
         ProfScope prof(PROF_PACK, st);
-        const int threads = nchunks * 512;
+        const int threads = nchunks * UNITS_PER_PLANE;
         pack_weights_kernel<<<(threads + 255) / 256, 256, 0, st>>>(w_ih, w_hh, b_ih, b_hh, d_in, packed, bias4, 1);
         CTGCN_LAUNCH_OK("pack_weights_kernel");
     }
@@ -808,22 +787,22 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
 
 using namespace ctgcn;
 
-// Test hook: out[128,192] = a[128,64] · w[{0..63,128..191,256..319}, :]ᵀ (w is [384,64]) on the tensor cores with the
-// split-bf16 scheme, through the GRU kernel's packer / chunk images / descriptors.  workspace ≥ 160 KB device memory.
-extern "C" int ctgcn_selftest_umma(const float* a, const float* w, float* out, void* workspace, size_t workspace_bytes,
-                                   void* stream) {
+// Test hook (see umma_selftest_kernel): out[128,256] from x[128,64], h[128,128], w_ih[384,64], w_hh[384,128].
+// workspace ≥ 512 KB of device memory.
+extern "C" int ctgcn_selftest_umma(const float* x, const float* h, const float* w_ih, const float* w_hh, float* out,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
     const int nchunks = 2 * chunks_per_part(64) + 2 * chunks_per_part(H);
-    CTGCN_REQUIRE(a && w && out && workspace && workspace_bytes >= (size_t)nchunks * CHUNK_BYTES + 4 * H * sizeof(float),
-                  "selftest_umma: bad arguments (workspace needs %zu bytes)", (size_t)nchunks * CHUNK_BYTES + 4 * H * sizeof(float));
+    const size_t need = (size_t)nchunks * CHUNK_BYTES + 4 * H * sizeof(float);
+    CTGCN_REQUIRE(x && h && w_ih && w_hh && out && workspace && workspace_bytes >= need,
+                  "selftest_umma: bad arguments (workspace needs %zu bytes)", need);
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t* packed = (uint8_t*)workspace;
     float* bias4 = (float*)(packed + (size_t)nchunks * CHUNK_BYTES);
-    // only the first 3 chunks (input part, half 0) are packed: 3 × 512 threads; w doubles as a dummy w_hh (never read)
-    pack_weights_kernel<<<(3 * 512 + 255) / 256, 256, 0, st>>>(w, w, nullptr, nullptr, 64, packed, bias4, 0);
+    pack_weights_kernel<<<(nchunks * UNITS_PER_PLANE + 255) / 256, 256, 0, st>>>(w_ih, w_hh, nullptr, nullptr, 64, packed, bias4, 0);
     CTGCN_LAUNCH_OK("pack_weights_kernel(selftest)");
-    const int smem = 2 * A_PLANE + 3 * CHUNK_BYTES + 64;
+    const int smem = 4 * A_PLANE + CHUNK_BYTES + 64;
     CTGCN_CUDA_OK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    umma_selftest_kernel<<<1, 128, smem, st>>>(a, packed, out);
+    umma_selftest_kernel<<<1, 128, smem, st>>>(x, h, packed, out);
     CTGCN_LAUNCH_OK("umma_selftest_kernel");
     return CTGCN_OK;
 }

@@ -113,7 +113,16 @@ int ctgcn_gru_seq_fwd(const float* seq, int64_t seq_row_stride, int64_t seq_step
                       int64_t y_step_stride, void* workspace, size_t workspace_bytes, void* stream);
 int ctgcn_set_gru_impl(int impl);
 /* debug: when non-NULL, block 0 of every following tcgen05 GRU launch writes clock64() stamps of its pipeline events
- * into device_buf[16 events][64 steps] (int64); NULL switches it off. */
+ * into device_buf[24 events][64 steps] (int64); NULL switches it off. */
+int ctgcn_debug_gru_trace(int64_t* device_buf);
+/* test hook: one half-step of a GRU cell's pre-activations for d_in = 64 through the tcgen05 weight packer, chunk images,
+ * descriptors, split-bf16 MMAs and TMEM loads of the GRU kernel:
+ *   out[128,256] = [ x W_in^T | x W_ir^T + h W_hr^T | x W_iz^T + h W_hz^T | h W_hn^T ]  for hidden features 0..63,
+ * x [128,64], h [128,128], w_ih [384,64], w_hh [384,128] (no bias, no pre-scaling).  workspace >= 512 KB device memory. */
+int ctgcn_selftest_umma(const float* x, const float* h, const float* w_ih, const float* w_hh, float* out, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* debug: when non-NULL, block 0 of every following tcgen05 GRU launch writes clock64() stamps of its pipeline events
+ * into device_buf[24 events][64 steps] (int64); NULL switches it off. */
 int ctgcn_debug_gru_trace(int64_t* device_buf);
 /* test hook: out[128,192] = a[128,64] w[{0..63,128..191,256..319},:]^T (w is [384,64]) through the tcgen05 weight packer,
  * chunk images, descriptors and TMEM loads the GRU kernel uses (split-bf16, three MMAs per product).

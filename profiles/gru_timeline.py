@@ -14,7 +14,7 @@ import torch  # noqa: E402
 NAMES = {0: "mma: step begin", 1: "mma: U ready & acc0 free", 2: "mma: X half0 issued", 3: "mma: h ready", 4: "mma: H half0 issued",
          5: "mma: acc1 free", 6: "mma: X half1 issued", 7: "mma: H half1 issued", 8: "wrk: wait acc0", 9: "wrk: acc0 full",
          10: "wrk: half0 math done / wait acc1", 11: "wrk: acc1 full", 12: "wrk: h published", 13: "ldr: U buffer free",
-         14: "ldr: U staged"}
+         14: "ldr: U staged", 15: "wrk: h half0 published", 16: "wrk: half1 passes done", 17: "wrk: before proxy fence"}
 
 
 def main():
@@ -33,7 +33,7 @@ def main():
     sd.update(cases.norm_params(rng, "norm.", d))
     sd = {k: torch.from_numpy(v).to(dev) for k, v in sd.items()}
     seq = torch.randn(n, args.steps, d, device=dev).abs()
-    buf = torch.zeros(16, 64, dtype=torch.int64, device=dev)
+    buf = torch.zeros(24, 64, dtype=torch.int64, device=dev)
     run = lambda: ops.gru_seq(seq, sd["rnn.weight_ih_l0"], sd["rnn.weight_hh_l0"], sd["rnn.bias_ih_l0"], sd["rnn.bias_hh_l0"],
                               sd["norm.weight"], sd["norm.bias"], 1e-5, args.mode)
     run()

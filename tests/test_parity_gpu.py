@@ -193,24 +193,32 @@ def test_model_golden(name, impl, lib, cuda_device):
 
 # ----------------------------------------------------------------------------- tcgen05 building block
 def test_umma_selftest(lib, cuda_device):
-    """Half 0 of the input part for d_in = 64 through the exact packer / chunk images / bulk copies / descriptors
-    (N=128 and N=64) / TMEM loads of the GRU kernel: the split-bf16 product (hi·hi + lo·hi + hi·lo) must match fp64
-    to ~2^-16."""
+    """One half-step of GRU pre-activations (d_in = 64, hidden features 0..63) through the exact packer / chunk images /
+    bulk copies / descriptors (N = 192 and the split first recurrent MMA) / TMEM loads of the GRU kernel: the split-bf16
+    product (hi·hi + lo·hi + hi·lo) must match fp64 to ~2^-16."""
     import ctypes as C
     rng = np.random.default_rng(0)
-    a = rng.standard_normal((128, 64)).astype(np.float32)
-    w = (rng.standard_normal((384, 64)) * 0.1).astype(np.float32)
-    ta, tw = torch.from_numpy(a).to(cuda_device), torch.from_numpy(w).to(cuda_device)
-    out = torch.zeros(128, 192, device=cuda_device)
+    x = rng.standard_normal((128, 64)).astype(np.float32)
+    h = rng.standard_normal((128, 128)).astype(np.float32)
+    w_ih = (rng.standard_normal((384, 64)) * 0.1).astype(np.float32)
+    w_hh = (rng.standard_normal((384, 128)) * 0.1).astype(np.float32)
+    t = [torch.from_numpy(a).to(cuda_device) for a in (x, h, w_ih, w_hh)]
+    out = torch.zeros(128, 256, device=cuda_device)
     ws = torch.zeros(512 * 1024, dtype=torch.uint8, device=cuda_device)
-    rc = lib.lib.ctgcn_selftest_umma(C.c_void_p(ta.data_ptr()), C.c_void_p(tw.data_ptr()), C.c_void_p(out.data_ptr()),
+    rc = lib.lib.ctgcn_selftest_umma(*[C.c_void_p(a.data_ptr()) for a in t], C.c_void_p(out.data_ptr()),
                                      C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     lib.check(rc, "ctgcn_selftest_umma")
     torch.cuda.synchronize()
-    sel = np.concatenate([np.arange(0, 64), np.arange(128, 192), np.arange(256, 320)])
-    ref = a.astype(np.float64) @ w[sel].astype(np.float64).T
-    err = cases.relerr(out.cpu().numpy(), ref)
-    assert err < 3e-5, err
+    x64, h64, wi, wh = (a.astype(np.float64) for a in (x, h, w_ih, w_hh))
+    f = slice(0, 64)
+    ref = np.concatenate([x64 @ wi[256:320].T,
+                          x64 @ wi[0:64].T + h64 @ wh[0:64].T,
+                          x64 @ wi[128:192].T + h64 @ wh[128:192].T,
+                          h64 @ wh[256:320].T], axis=1)
+    got = out.cpu().numpy()
+    for blk, name in enumerate(("W_in x", "r", "z", "W_hn h")):
+        err = cases.relerr(got[:, 64 * blk:64 * blk + 64], ref[:, 64 * blk:64 * blk + 64])
+        assert err < 3e-5, (name, err)
 
 
 # ----------------------------------------------------------------------------- GRU kernel alone
