@@ -121,13 +121,6 @@ int ctgcn_debug_gru_trace(int64_t* device_buf);
  * x [128,64], h [128,128], w_ih [384,64], w_hh [384,128] (no bias, no pre-scaling).  workspace >= 512 KB device memory. */
 int ctgcn_selftest_umma(const float* x, const float* h, const float* w_ih, const float* w_hh, float* out, void* workspace,
                         size_t workspace_bytes, void* stream);
-/* debug: when non-NULL, block 0 of every following tcgen05 GRU launch writes clock64() stamps of its pipeline events
- * into device_buf[24 events][64 steps] (int64); NULL switches it off. */
-int ctgcn_debug_gru_trace(int64_t* device_buf);
-/* test hook: out[128,192] = a[128,64] w[{0..63,128..191,256..319},:]^T (w is [384,64]) through the tcgen05 weight packer,
- * chunk images, descriptors and TMEM loads the GRU kernel uses (split-bf16, three MMAs per product).
- * workspace >= 512 KB of device memory. */
-int ctgcn_selftest_umma(const float* a, const float* w, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- CoreDiffusion.forward (layers.py:38-63)
  * y[n_rows, h] (row stride ldy) = LayerNorm(sum_i GRU(relu(cumsum_i A_i x))).
