@@ -20,7 +20,7 @@ OBJ_DIR = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
-          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+          "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("CTGCN_NVCC_FLAGS", "").split()
 
 
 def sources():

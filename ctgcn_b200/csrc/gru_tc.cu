@@ -247,6 +247,10 @@ struct Params {
         if (p.trace && blockIdx.x == 0 && (gs) < 64u) p.trace[(e) * 64 + (gs)] = clock64(); \
     } while (0)
 
+#ifdef GRU_EXP_NO_MUFU   // timing experiment: no special-function unit work at all (results are wrong)
+__device__ __forceinline__ float ex2_approx(float v) { return v * 0.5f + 1.f; }
+__device__ __forceinline__ float rcp_approx(float v) { return v * 0.25f + 0.5f; }
+#else
 __device__ __forceinline__ float ex2_approx(float v) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -257,6 +261,7 @@ __device__ __forceinline__ float rcp_approx(float v) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
 }
+#endif
 
 // One 24 KB weight chunk (192 rows × 32 k): 2 K-steps × 3 split products (hi·hi, lo·hi, hi·lo) of N = 192 into 192
 // consecutive accumulator columns starting at d_tmem.  a_lo32 / b_lo32: descriptor low words of the A hi plane at this
@@ -459,6 +464,9 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
                                                  v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
                             uint4 hi, lo;
                             split8(f8, hi, lo);
+#ifdef GRU_EXP_NO_U_STORE
+                            if (f8[0] != 12345.678f) continue;   // timing experiment
+#endif
                             *reinterpret_cast<uint4*>(u_hi + kb * (TILE_M * 16) + m * 16) = hi;
                             *reinterpret_cast<uint4*>(u_hi + A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
                         }
@@ -539,6 +547,9 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
                 // gates, one half (64 hidden features) at a time; this thread owns 32 of them, 8 per pass
                 float h0[32];   // first half of h_i, published only when no MMA reads h_{i-1} any more
                 auto put_h8 = [&](const float (&f8)[8], int f) {
+#ifdef GRU_EXP_NO_H_STORE
+                    if (f8[0] != 12345.678f) return;   // timing experiment: never true in practice
+#endif
                     uint4 hi, lo;
                     split8(f8, hi, lo);
                     const int kb = f >> 3;
