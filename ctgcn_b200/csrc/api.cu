@@ -47,8 +47,10 @@ void set_error(const char* fmt, ...) {
 // tcgen05 path (gru_tc.cu); returns 1 when the shape is not supported by it
 int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* w_ih,
                   const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
-                  int mode, float* y, int64_t yrs, int64_t yss, void* ws, size_t ws_bytes, cudaStream_t st)
-;
+                  int mode, float* y, int64_t yrs, int64_t yss, void* ws, size_t ws_bytes, cudaStream_t st);
+// tcgen05 dense layer (linear_tc.cu); returns 1 when the shape is not supported by it
+int launch_linear_tc(const float* x, int64_t ldx, int64_t n, int64_t d_in, const float* w, const float* b, int64_t d_out,
+                     int act, float* y, int64_t ldy, void* ws, cudaStream_t st);
 
 }  // namespace ctgcn
 
@@ -208,6 +210,10 @@ extern "C" int ctgcn_linear_fwd(const float* x, int64_t ldx, int64_t n, int64_t 
     }
     if (n == 0) return CTGCN_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_gru_impl.load() != CTGCN_IMPL_SIMT) {   // the implementation selector covers every tensor-core kernel
+        int rc = launch_linear_tc(x, ldx, n, d_in, w, b, d_out, act, y, ldy, workspace, st);
+        if (rc <= 0) return rc;                   // done or failed; 1 = shape not supported → SIMT kernel
+    }
     float* wt = (float*)workspace;
     int rc = launch_transpose(w, d_out, d_in, wt, st);
     if (rc) return rc;

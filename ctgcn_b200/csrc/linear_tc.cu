@@ -1,0 +1,255 @@
+// tcgen05 dense layer  y = act(x·Wᵀ + b)  for the 128-wide MLP layers (layers.py:95-106) — same split-bf16 scheme as
+// gru_tc.cu (hi·hi + lo·hi + hi·lo, fp32 accumulation in TMEM) so that the 1e-4 parity bar holds.
+//
+// The layer is HBM-bound (4·(d_in + d_out) bytes per row against 6·d_in·d_out issued flops): one persistent CTA per SM
+// keeps the packed weights (≤ 64 KB) resident in shared memory and streams 128-row tiles through a double-buffered
+// A operand and two TMEM accumulator buffers:
+//   warp 0       MMA issuer (elected lane): M=128, N=d_out, K=16, no-swizzle K-major descriptors
+//   warps 4-11   loaders: fp32 rows → bf16 hi/lo planes in core-matrix order; a whole tile (64 KB) is in flight at once
+//   warps 12-15  epilogue: tcgen05.ld → + bias → selu? → 128-bit stores
+// Shapes: d_in, d_out ∈ {64, 128}; everything else goes to the SIMT kernel in gru_simt.cu.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace ctgcn {
+namespace {
+using namespace tc;
+
+constexpr int TILE_M = 128;
+constexpr int MAX_D = 128;
+constexpr int A_PLANE = TILE_M * MAX_D * 2;   // 32 KB
+constexpr int SM_A = 0;                       // 2 buffers × (hi | lo)
+constexpr int SM_B = SM_A + 4 * A_PLANE;      // weights hi | lo (plane = d_out·d_in·2 ≤ 32 KB)
+constexpr int SM_BIAS = SM_B + 2 * A_PLANE;
+constexpr int SM_BAR = SM_BIAS + MAX_D * 4;
+constexpr int NUM_BARS = 9;                   // a_ready[2] a_free[2] acc_full[2] acc_free[2] w_full
+constexpr int SM_TMEM_PTR = SM_BAR + NUM_BARS * 8;
+constexpr int SMEM_BYTES = SM_TMEM_PTR + 16;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+constexpr int NUM_LOADER_WARPS = 8, NUM_EPI_WARPS = 4;
+constexpr int FIRST_LOADER_WARP = 4, FIRST_EPI_WARP = 12;
+constexpr int THREADS = 32 * 16;
+enum { BAR_A_READY = 0, BAR_A_FREE = 2, BAR_ACC_FULL = 4, BAR_ACC_FREE = 6, BAR_W_FULL = 8 };
+
+// Weight image: element (n, k) of W [d_out, d_in] at (k/8)·(d_out·16) + n·16 + (k%8)·2, hi plane then lo plane.
+__global__ void pack_linear_weights_kernel(const float* __restrict__ w, int d_in, int d_out, uint8_t* __restrict__ packed) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int units = d_out * (d_in / 8);
+    if (t >= units) return;
+    const int kb = t / d_out, n = t % d_out;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = w[(int64_t)n * d_in + kb * 8 + i];
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    uint8_t* dst = packed + kb * (d_out * 16) + n * 16;
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + d_out * d_in * 2) = lo;
+}
+
+struct Params {
+    const float* x;
+    int64_t ldx, n;
+    int d_in, d_out;
+    const uint8_t* packed;
+    const float* bias;
+    int act;
+    float* y;
+    int64_t ldy;
+    int num_tiles;
+};
+
+template <int N>
+__device__ __forceinline__ void issue_tile(uint32_t a_lo32, uint32_t b_lo32, uint32_t b_plane16, uint32_t d_tmem, int ksteps) {
+    constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, N);
+    constexpr uint32_t A_STEP = (2 * TILE_M * 16) >> 4, B_STEP = (2 * N * 16) >> 4, A_LO_PLANE = A_PLANE >> 4;
+    for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t ah = desc64(a_lo32 + ks * A_STEP), al = desc64(a_lo32 + A_LO_PLANE + ks * A_STEP);
+        const uint64_t bh = desc64(b_lo32 + ks * B_STEP), bl = desc64(b_lo32 + b_plane16 + ks * B_STEP);
+        umma_bf16(d_tmem, ah, bh, idesc, ks == 0 ? 0u : 1u);
+        umma_bf16(d_tmem, al, bh, idesc, 1u);
+        umma_bf16(d_tmem, ah, bl, idesc, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto bar = [&](int i) { return sbase + SM_BAR + 8u * i; };
+    const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t w_plane = (uint32_t)p.d_out * p.d_in * 2;
+
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar(BAR_A_READY + b), NUM_LOADER_WARPS);
+            mbar_init(bar(BAR_A_FREE + b), 1);
+            mbar_init(bar(BAR_ACC_FULL + b), 1);
+            mbar_init(bar(BAR_ACC_FREE + b), NUM_EPI_WARPS);
+        }
+        mbar_init(bar(BAR_W_FULL), 1);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < p.d_out; i += THREADS) reinterpret_cast<float*>(smem + SM_BIAS)[i] = p.bias ? p.bias[i] : 0.f;
+    if (warp == 0) tmem_alloc(sbase + SM_TMEM_PTR, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM_PTR);
+
+    if (warp == 0) {
+        // ===================================================== weights (once) + MMA issuer
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (elect_one()) {
+            mbar_expect_tx(bar(BAR_W_FULL), 2 * w_plane);
+            bulk_g2s(sbase + SM_B, p.packed, 2 * w_plane, bar(BAR_W_FULL));
+        }
+        __syncwarp();
+        mbar_wait(bar(BAR_W_FULL), 0);
+        const uint32_t b_desc = desc_lo(sbase + SM_B, p.d_out * 16);
+        for (int t = 0; t < my_tiles; ++t) {
+            const int b = t & 1;
+            const uint32_t par = (t >> 1) & 1;
+            mbar_wait(bar(BAR_A_READY + b), par);
+            mbar_wait(bar(BAR_ACC_FREE + b), par ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_desc = desc_lo(sbase + SM_A + b * 2 * A_PLANE, TILE_M * 16);
+                if (p.d_out == 128) issue_tile<128>(a_desc, b_desc, w_plane >> 4, tmem + b * 128, p.d_in / 16);
+                else issue_tile<64>(a_desc, b_desc, w_plane >> 4, tmem + b * 128, p.d_in / 16);
+                umma_commit(bar(BAR_A_FREE + b));
+                umma_commit(bar(BAR_ACC_FULL + b));
+            }
+            __syncwarp();
+        }
+    } else if (warp < FIRST_LOADER_WARP) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    } else if (warp < FIRST_EPI_WARP) {
+        // ===================================================== loaders: 16 tile rows per warp, the whole tile in flight
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+        const int r8 = lane & 7, c4 = lane >> 3;
+        const int row_base = 16 * (warp - FIRST_LOADER_WARP);
+        const int nkg = p.d_in / 32;          // k-groups of 4 k-blocks
+        const int nit = 2 * nkg;              // (row-group of 8, k-group) iterations: 8 for d_in = 128
+        for (int t = 0; t < my_tiles; ++t) {
+            const int b = t & 1;
+            const int64_t tile_row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M;
+            uint8_t* a_hi = smem + SM_A + b * 2 * A_PLANE;
+            float4 v[16];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int rg = u & 1, kg = u >> 1;
+                const int64_t srow = tile_row0 + row_base + 8 * rg + r8;
+                if (u < nit && srow < p.n) {
+                    const float* src = p.x + srow * p.ldx + (4 * kg + c4) * 8;
+                    v[2 * u] = __ldg(reinterpret_cast<const float4*>(src));
+                    v[2 * u + 1] = __ldg(reinterpret_cast<const float4*>(src + 4));
+                } else {
+                    v[2 * u] = v[2 * u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            mbar_wait(bar(BAR_A_FREE + b), ((t >> 1) & 1) ^ 1);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (u < nit) {
+                    const int rg = u & 1, kg = u >> 1;
+                    const int m = row_base + 8 * rg + r8, kb = 4 * kg + c4;
+                    const float f8[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w,
+                                         v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
+                    uint4 hi, lo;
+                    split8(f8, hi, lo);
+                    *reinterpret_cast<uint4*>(a_hi + kb * (TILE_M * 16) + m * 16) = hi;
+                    *reinterpret_cast<uint4*>(a_hi + A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(BAR_A_READY + b));
+        }
+    } else {
+        // ===================================================== epilogue: thread = tile row
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+        const int q = warp & 3;
+        const int m = 32 * q + lane;
+        const float* bias = reinterpret_cast<const float*>(smem + SM_BIAS);
+        const uint32_t tmem_lane = tmem + ((uint32_t)(32 * q) << 16);
+        for (int t = 0; t < my_tiles; ++t) {
+            const int b = t & 1;
+            const int64_t row = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + m;
+            mbar_wait(bar(BAR_ACC_FULL + b), (t >> 1) & 1);
+            tc_fence_after();
+            float* dst = p.y + row * p.ldy;
+            for (int c = 0; c < p.d_out; c += 16) {
+                float v0[8], v1[8];
+                tmem_ld8(tmem_lane + b * 128 + c, v0);
+                tmem_ld8(tmem_lane + b * 128 + c + 8, v1);
+                tmem_ld_wait();
+                float o[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    o[j] = v0[j] + bias[c + j];
+                    o[8 + j] = v1[j] + bias[c + 8 + j];
+                }
+                if (p.act == CTGCN_ACT_SELU) {
+                    const float alpha = 1.6732632423543772848170429916717f, scale = 1.0507009873554804934193349852946f;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] = scale * (o[j] > 0.f ? o[j] : alpha * expm1f(o[j]));
+                }
+                if (row < p.n) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(dst + c + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(BAR_ACC_FREE + b));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace
+
+// returns 0 = done, <0 = error, 1 = shape not supported by this path.  workspace ≥ 4·d_in·d_out bytes (packed weights).
+int launch_linear_tc(const float* x, int64_t ldx, int64_t n, int64_t d_in, const float* w, const float* b, int64_t d_out,
+                     int act, float* y, int64_t ldy, void* ws, cudaStream_t st) {
+    if ((d_in != 64 && d_in != 128) || (d_out != 64 && d_out != 128)) return 1;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (!al16(x) || !al16(y) || (ldx & 3) || (ldy & 3)) return 1;
+    uint8_t* packed = (uint8_t*)ws;
+    {
+        ProfScope prof(PROF_PACK, st);
+        const int units = (int)(d_out * (d_in / 8));
+        pack_linear_weights_kernel<<<(units + 255) / 256, 256, 0, st>>>(w, (int)d_in, (int)d_out, packed);
+        CTGCN_LAUNCH_OK("pack_linear_weights_kernel");
+    }
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        CTGCN_CUDA_OK(cudaGetDevice(&dev));
+        CTGCN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        CTGCN_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    }
+    Params p;
+    p.x = x;
+    p.ldx = ldx;
+    p.n = n;
+    p.d_in = (int)d_in;
+    p.d_out = (int)d_out;
+    p.packed = packed;
+    p.bias = b;
+    p.act = act;
+    p.y = y;
+    p.ldy = ldy;
+    p.num_tiles = (int)((n + TILE_M - 1) / TILE_M);
+    const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
+    ProfScope prof(PROF_LINEAR, st);
+    linear_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p);
+    CTGCN_LAUNCH_OK("linear_tc_kernel");
+    return CTGCN_OK;
+}
+
+}  // namespace ctgcn

@@ -1,0 +1,128 @@
+// tcgen05 / TMEM / mbarrier / bulk-copy PTX wrappers and the split-bf16 helpers shared by the tensor-core kernels
+// (gru_tc.cu, linear_tc.cu).  sm_100a only.
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace ctgcn {
+namespace tc {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    // the suspend-time hint lets the hardware park the warp instead of spinning through issue slots
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(20000u)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// K-major, no-swizzle ("interleaved") operands: 8-row × 16-byte core matrices; LBO = byte distance between the two
+// 8-element K halves of one K=16 MMA (= rows·16 in the layouts used here), SBO = 128 B between consecutive 8-row
+// groups.  The 64-bit descriptor's high word is constant (SBO, version 1); the low word = (address >> 4) | (LBO >> 4) << 16.
+constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo) { return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; }
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred;
+}
+// No "memory" clobber on the loads on purpose: TMEM is not memory the compiler knows about, and without the clobber the
+// loads of the next 8-feature pass can be hoisted above the shared-memory stores of the current one (tmem_ld_wait keeps
+// its clobber and orders the consumers).
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ bf16 split
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    // packed conversions (F2FP, ALU pipe) instead of scalar F2F (XU pipe, shared with the MUFU gate math)
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+    lo = *reinterpret_cast<const uint32_t*>(&l2);
+}
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+    split2(v[0], v[1], hi.x, lo.x);
+    split2(v[2], v[3], hi.y, lo.y);
+    split2(v[4], v[5], hi.z, lo.z);
+    split2(v[6], v[7], hi.w, lo.w);
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float (&v)[8]) {
+    v[0] = bf_lo(hi.x) + bf_lo(lo.x);
+    v[1] = bf_hi(hi.x) + bf_hi(lo.x);
+    v[2] = bf_lo(hi.y) + bf_lo(lo.y);
+    v[3] = bf_hi(hi.y) + bf_hi(lo.y);
+    v[4] = bf_lo(hi.z) + bf_lo(lo.z);
+    v[5] = bf_hi(hi.z) + bf_hi(lo.z);
+    v[6] = bf_lo(hi.w) + bf_lo(lo.w);
+    v[7] = bf_hi(hi.w) + bf_hi(lo.w);
+}
+
+
+}  // namespace tc
+}  // namespace ctgcn

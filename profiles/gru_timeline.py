@@ -14,7 +14,8 @@ import torch  # noqa: E402
 NAMES = {0: "mma: step begin", 1: "mma: U ready & acc0 free", 2: "mma: X half0 issued", 3: "mma: h ready", 4: "mma: H half0 issued",
          5: "mma: acc1 free", 6: "mma: X half1 issued", 7: "mma: H half1 issued", 8: "wrk: wait acc0", 9: "wrk: acc0 full",
          10: "wrk: half0 math done / wait acc1", 11: "wrk: acc1 full", 12: "wrk: h published", 13: "ldr: U buffer free",
-         14: "ldr: U staged", 15: "wrk: h half0 published", 16: "wrk: half1 passes done", 17: "wrk: before proxy fence"}
+         14: "ldr: U staged", 16: "wrk: half0 pass0 done", 17: "wrk: half0 pass1 done", 18: "wrk: half0 pass2 done", 19: "wrk: half0 pass3 done",
+         20: "wrk: half1 pass0 done", 21: "wrk: half1 pass1 done", 22: "wrk: half1 pass2 done", 23: "wrk: half1 pass3 done"}
 
 
 def main():

@@ -250,6 +250,24 @@ def test_gru_seq_kernel(n, steps, d_in, h, bias, mode, impl, lib, cuda_device):
     assert (out[:, 0] == 7.0).all() if mode else (out[:, h:] == 7.0).all()   # nothing written outside the view
 
 
+# ----------------------------------------------------------------------------- dense layer kernels
+@pytest.mark.parametrize("n,d_in,d_out,act,bias", [(1000, 128, 128, "L", True), (77, 64, 128, "N", True), (300, 128, 64, "N", False),
+                                                   (5, 64, 64, "L", True), (40000, 128, 128, "N", True), (129, 100, 128, "L", True)])
+def test_linear_kernel(n, d_in, d_out, act, bias, impl, lib, cuda_device):
+    """layers.py:97-105 through ctgcn_linear_fwd: tcgen05 path for 64/128-wide layers (impl=auto), SIMT otherwise."""
+    from ctgcn_b200 import ops
+    rng = np.random.default_rng(n + d_in)
+    sd = cases.linear_params(rng, "", d_in, d_out, bias)
+    x = (rng.standard_normal((n, d_in)) * 2).astype(np.float32)
+    ref = oracle_np.mlp(x, {("linear." + k): v for k, v in sd.items()}, "", 1, act)
+    d = tsd(sd, cuda_device)
+    # strided input rows (a view into a wider buffer) exercise ldx
+    buf = torch.zeros(n, d_in + 4, device=cuda_device)
+    buf[:, :d_in] = torch.from_numpy(x).to(cuda_device)
+    y = ops.linear(buf[:, :d_in], d["weight"], d.get("bias"), lib.ACT_SELU if act == "N" else lib.ACT_NONE)
+    close(y.cpu().numpy(), ref, f"linear {n}x{d_in}->{d_out} {act} [{impl}]")
+
+
 # ----------------------------------------------------------------------------- edge cases
 def test_empty_and_isolated(lib, cuda_device, impl):
     import ctgcn_b200 as pkg
