@@ -52,6 +52,8 @@ SIGNATURES = {
     "ctgcn_selftest_umma": (C.c_int, [_p, _p, _p, _p, _p, _p, _sz, _p]),
     "ctgcn_core_diffusion_workspace_bytes": (_sz, [_p, _i32, _i32]),
     "ctgcn_core_diffusion_fwd": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _f32, _p, _i64, _p, _sz, _p]),
+    "ctgcn_core_diffusion_fwd_scatter": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _f32, _p, _i32, _i64, _i64,
+                                                   _p, _sz, _p]),
     "ctgcn_linear_workspace_bytes": (_sz, [_i64, _i64]),
     "ctgcn_linear_fwd": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _i32, _p, _i64, _p, _sz, _p]),
     "ctgcn_spmm_linear_fwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _i64, _p, _sz, _p]),

@@ -47,7 +47,7 @@ void set_error(const char* fmt, ...) {
 // tcgen05 path (gru_tc.cu); returns 1 when the shape is not supported by it
 int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* w_ih,
                   const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
-                  int mode, float* y, int64_t yrs, int64_t yss, void* ws, size_t ws_bytes, cudaStream_t st);
+                  int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* sc, void* ws, size_t ws_bytes, cudaStream_t st);
 // tcgen05 dense layer (linear_tc.cu); returns 1 when the shape is not supported by it
 int launch_linear_tc(const float* x, int64_t ldx, int64_t n, int64_t d_in, const float* w, const float* b, int64_t d_out,
                      int act, float* y, int64_t ldy, void* ws, cudaStream_t st);
@@ -133,11 +133,11 @@ extern "C" size_t ctgcn_gru_workspace_bytes(int d_in, int h) {
     return gru_ws_simt(d_in, h) + gru_ws_tc(d_in, h);
 }
 
-extern "C" int ctgcn_gru_seq_fwd(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h,
-                                 const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
-                                 const float* ln_w, const float* ln_b, float eps, int mode, float* y, int64_t yrs,
-                                 int64_t yss, void* workspace, size_t workspace_bytes, void* stream) {
-    CTGCN_REQUIRE(seq && w_ih && w_hh && ln_w && ln_b && y, "gru_seq_fwd: NULL argument");
+static int gru_seq_impl(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* w_ih,
+                        const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b,
+                        float eps, int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* sc, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    CTGCN_REQUIRE(seq && w_ih && w_hh && ln_w && ln_b && (y || sc), "gru_seq_fwd: NULL argument");
     CTGCN_REQUIRE((b_ih == nullptr) == (b_hh == nullptr), "gru_seq_fwd: b_ih and b_hh must both be given or both NULL");
     CTGCN_REQUIRE(n >= 0 && steps >= 1 && d_in >= 1 && h >= 1, "gru_seq_fwd: bad sizes n=%lld steps=%d d_in=%d h=%d",
                   (long long)n, steps, d_in, h);
@@ -151,7 +151,7 @@ extern "C" int ctgcn_gru_seq_fwd(const float* seq, int64_t srs, int64_t sss, int
     const int impl = g_gru_impl.load();
     if (impl != CTGCN_IMPL_SIMT) {
         char* tc_ws = (char*)workspace + gru_ws_simt(d_in, h);
-        int rc = launch_gru_tc(seq, srs, sss, n, steps, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss,
+        int rc = launch_gru_tc(seq, srs, sss, n, steps, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, sc,
                                tc_ws, gru_ws_tc(d_in, h), st);
         if (rc <= 0) return rc;  // done or failed
         CTGCN_REQUIRE(impl == CTGCN_IMPL_AUTO, "gru_seq_fwd: tcgen05 path does not support d_in=%d h=%d", d_in, h);
@@ -162,7 +162,15 @@ extern "C" int ctgcn_gru_seq_fwd(const float* seq, int64_t srs, int64_t sss, int
     if (rc) return rc;
     rc = launch_transpose(w_hh, 3 * h, h, wt_hh, st);
     if (rc) return rc;
-    return launch_gru_simt(seq, srs, sss, n, steps, d_in, h, wt_ih, wt_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, st);
+    return launch_gru_simt(seq, srs, sss, n, steps, d_in, h, wt_ih, wt_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, sc, st);
+}
+
+extern "C" int ctgcn_gru_seq_fwd(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h,
+                                 const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                 const float* ln_w, const float* ln_b, float eps, int mode, float* y, int64_t yrs,
+                                 int64_t yss, void* workspace, size_t workspace_bytes, void* stream) {
+    return gru_seq_impl(seq, srs, sss, n, steps, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, nullptr,
+                        workspace, workspace_bytes, stream);
 }
 
 // ---- CoreDiffusion.forward: cumulative SpMM → U [n, K, d_in] (workspace) → GRU over cores + Σ + LayerNorm
@@ -171,13 +179,13 @@ extern "C" size_t ctgcn_core_diffusion_workspace_bytes(const ctgcn_plan* plan, i
     return align_up((size_t)plan->n_rows * plan->k * d_in * sizeof(float), 256) + ctgcn_gru_workspace_bytes(d_in, h);
 }
 
-extern "C" int ctgcn_core_diffusion_fwd(const ctgcn_plan* plan, const float* x, int64_t ldx, int d_in, int h,
-                                        const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
-                                        const float* ln_w, const float* ln_b, float eps, float* y, int64_t ldy,
-                                        void* workspace, size_t workspace_bytes, void* stream) {
-    CTGCN_REQUIRE(plan && x && y, "core_diffusion_fwd: NULL argument");
+static int core_diffusion_impl(const ctgcn_plan* plan, const float* x, int64_t ldx, int d_in, int h, const float* w_ih,
+                               const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b,
+                               float eps, float* y, int64_t ldy, const RowScatter* sc, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+    CTGCN_REQUIRE(plan && x && (y || sc), "core_diffusion_fwd: NULL argument");
     CTGCN_REQUIRE(plan->n_rows == plan->n_cols, "core_diffusion_fwd: adjacency plan must be square");
-    CTGCN_REQUIRE(ldx >= d_in && ldy >= h, "core_diffusion_fwd: leading dimension too small");
+    CTGCN_REQUIRE(ldx >= d_in && (sc || ldy >= h), "core_diffusion_fwd: leading dimension too small");
     const size_t need = ctgcn_core_diffusion_workspace_bytes(plan, d_in, h);
     if (!workspace || workspace_bytes < need) {
         set_error("core_diffusion_fwd: workspace of %zu bytes, need %zu", workspace_bytes, need);
@@ -187,9 +195,34 @@ extern "C" int ctgcn_core_diffusion_fwd(const ctgcn_plan* plan, const float* x, 
     const size_t u_bytes = align_up((size_t)plan->n_rows * plan->k * d_in * sizeof(float), 256);
     int rc = launch_cumspmm(plan, x, ldx, d_in, u, true, (cudaStream_t)stream);
     if (rc) return rc;
-    return ctgcn_gru_seq_fwd(u, (int64_t)plan->k * d_in, d_in, plan->n_rows, plan->k, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w,
-                             ln_b, eps, CTGCN_GRU_SUM_LN, y, ldy, 0, (char*)workspace + u_bytes, workspace_bytes - u_bytes,
-                             stream);
+    return gru_seq_impl(u, (int64_t)plan->k * d_in, d_in, plan->n_rows, plan->k, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b,
+                        eps, CTGCN_GRU_SUM_LN, y, ldy, 0, sc, (char*)workspace + u_bytes, workspace_bytes - u_bytes, stream);
+}
+
+extern "C" int ctgcn_core_diffusion_fwd(const ctgcn_plan* plan, const float* x, int64_t ldx, int d_in, int h,
+                                        const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                        const float* ln_w, const float* ln_b, float eps, float* y, int64_t ldy,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+    return core_diffusion_impl(plan, x, ldx, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, y, ldy, nullptr, workspace,
+                               workspace_bytes, stream);
+}
+
+extern "C" int ctgcn_core_diffusion_fwd_scatter(const ctgcn_plan* plan, const float* x, int64_t ldx, int d_in, int h,
+                                                const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                                const float* ln_w, const float* ln_b, float eps, float* const* slice_ptrs,
+                                                int n_slices, int64_t slice_row_stride, int64_t slice_col_offset,
+                                                void* workspace, size_t workspace_bytes, void* stream) {
+    CTGCN_REQUIRE(plan && slice_ptrs && n_slices >= 1 && n_slices <= plan->n_rows, "core_diffusion_fwd_scatter: bad slice arguments");
+    CTGCN_REQUIRE(slice_row_stride >= slice_col_offset + h && slice_col_offset >= 0, "core_diffusion_fwd_scatter: bad slice strides");
+    RowScatter sc;
+    sc.slices = slice_ptrs;
+    sc.n_slices = n_slices;
+    sc.base = plan->n_rows / n_slices;
+    sc.rem = plan->n_rows % n_slices;
+    sc.row_stride = slice_row_stride;
+    sc.col_offset = slice_col_offset;
+    return core_diffusion_impl(plan, x, ldx, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, nullptr, 0, &sc, workspace,
+                               workspace_bytes, stream);
 }
 
 // ---- MLP layers

@@ -74,6 +74,34 @@ struct ctgcn_plan {
     size_t bytes = 0;
 };
 
+namespace ctgcn {
+// Optional per-row redirection of a [N, H] output: row r is written into the buffer of the node slice that owns it
+// (balanced contiguous slices: the first `rem` slices hold base+1 rows).  With peer-mapped slice pointers this is the
+// snapshot exchange of CTGCN.forward (models.py:248) fused into the producing kernel's epilogue: every GPU stores its
+// snapshot's rows straight into the [rows, T, D] sequence buffer of the rank that runs the temporal GRU on them.
+struct RowScatter {
+    float* const* slices = nullptr;  // DEVICE array of n_slices base pointers; nullptr = disabled
+    int n_slices = 0;
+    long long base = 0, rem = 0;
+    long long row_stride = 0;        // elements between consecutive rows of a slice buffer (T·D)
+    long long col_offset = 0;        // element offset of this output inside a slice row (t·D)
+#ifdef __CUDACC__
+    __device__ __forceinline__ float* row_ptr(long long row) const {
+        const long long big = rem * (base + 1);
+        long long g, local;
+        if (row < big) {
+            g = row / (base + 1);
+            local = row - g * (base + 1);
+        } else {
+            g = rem + (row - big) / base;
+            local = (row - big) - (g - rem) * base;
+        }
+        return slices[g] + local * row_stride + col_offset;
+    }
+#endif
+};
+}  // namespace ctgcn
+
 // kernels' host launchers (defined in the respective .cu files)
 namespace ctgcn {
 int launch_cumspmm(const ctgcn_plan* p, const float* x, int64_t ldx, int d, float* u, bool relu, cudaStream_t st);
@@ -84,5 +112,6 @@ int launch_linear_simt(const float* x, int64_t ldx, int64_t n, int64_t d_in, con
                        int64_t d_out, int act, float* y, int64_t ldy, cudaStream_t st);
 int launch_gru_simt(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h,
                     const float* wt_ih, const float* wt_hh, const float* b_ih, const float* b_hh, const float* ln_w,
-                    const float* ln_b, float eps, int mode, float* y, int64_t yrs, int64_t yss, cudaStream_t st);
+                    const float* ln_b, float eps, int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* sc,
+                    cudaStream_t st);
 }  // namespace ctgcn

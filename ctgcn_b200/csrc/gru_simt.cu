@@ -94,7 +94,7 @@ __device__ __forceinline__ void gemm_part(float (&acc)[4][RM][4], const float* _
 template <int RM>
 __device__ __forceinline__ void layer_norm_rows(const float* __restrict__ buf, int h, const float* __restrict__ ln_w,
                                                 const float* __restrict__ ln_b, float eps, int64_t row0, int64_t n,
-                                                float* __restrict__ y, int64_t yrs) {
+                                                float* __restrict__ y, int64_t yrs, const RowScatter& sc) {
     constexpr int RP = Tile<RM>::RP;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int r = 0; r < RM; ++r) {
@@ -113,7 +113,7 @@ __device__ __forceinline__ void layer_norm_rows(const float* __restrict__ buf, i
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
         const float rstd = rsqrtf(q / (float)h + eps);
-        float* yr = y + (row0 + row) * yrs;
+        float* yr = sc.slices ? sc.row_ptr(row0 + row) : y + (row0 + row) * yrs;
         for (int f = tx; f < h; f += 32) yr[f] = (buf[f * RP + row] - mean) * rstd * __ldg(ln_w + f) + __ldg(ln_b + f);
     }
 }
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(THREADS)
     gru_seq_kernel(const float* __restrict__ seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h,
                    const float* __restrict__ wt_ih, const float* __restrict__ wt_hh, const float* __restrict__ b_ih,
                    const float* __restrict__ b_hh, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                   float eps, int mode, float* __restrict__ y, int64_t yrs, int64_t yss) {
+                   float eps, int mode, float* __restrict__ y, int64_t yrs, int64_t yss, const RowScatter sc) {
     constexpr int R = Tile<RM>::R, RP = Tile<RM>::RP;
     extern __shared__ __align__(16) float smem[];
     const int d_pad = (d_in + KC - 1) / KC * KC, h_pad = (h + KC - 1) / KC * KC;
@@ -183,11 +183,11 @@ __global__ void __launch_bounds__(THREADS)
         }
         __syncthreads();
         if (mode == CTGCN_GRU_EACH_LN) {
-            layer_norm_rows<RM>(hnxt, h, ln_w, ln_b, eps, row0, n, y + (int64_t)s * yss, yrs);
+            layer_norm_rows<RM>(hnxt, h, ln_w, ln_b, eps, row0, n, y + (int64_t)s * yss, yrs, RowScatter());
         }
         cur ^= 1;
     }
-    if (mode == CTGCN_GRU_SUM_LN) layer_norm_rows<RM>(os, h, ln_w, ln_b, eps, row0, n, y, yrs);
+    if (mode == CTGCN_GRU_SUM_LN) layer_norm_rows<RM>(os, h, ln_w, ln_b, eps, row0, n, y, yrs, sc);
 }
 
 // y[n, d_out] = act(x · Wᵀ + b);  wt is k-major [d_in][d_out].  CTA: 64 rows × 128 features, k chunks of 16.
@@ -282,12 +282,12 @@ size_t gru_smem_bytes(int d_in, int h) {
 template <int RM>
 int launch_gru_t(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* wt_ih,
                  const float* wt_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
-                 int mode, float* y, int64_t yrs, int64_t yss, cudaStream_t st) {
+                 int mode, float* y, int64_t yrs, int64_t yss, const RowScatter& sc, cudaStream_t st) {
     const size_t smem = gru_smem_bytes<RM>(d_in, h);
     CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_seq_kernel<RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned blocks = (unsigned)((n + Tile<RM>::R - 1) / Tile<RM>::R);
     gru_seq_kernel<RM><<<blocks, THREADS, smem, st>>>(seq, srs, sss, n, steps, d_in, h, wt_ih, wt_hh, b_ih, b_hh, ln_w, ln_b,
-                                                      eps, mode, y, yrs, yss);
+                                                      eps, mode, y, yrs, yss, sc);
     CTGCN_LAUNCH_OK("gru_seq_kernel");
     return CTGCN_OK;
 }
@@ -296,13 +296,14 @@ int launch_gru_t(const float* seq, int64_t srs, int64_t sss, int64_t n, int step
 
 int launch_gru_simt(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* wt_ih,
                     const float* wt_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
-                    int mode, float* y, int64_t yrs, int64_t yss, cudaStream_t st) {
+                    int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* scp, cudaStream_t st) {
     constexpr size_t kMaxSmem = 227 * 1024;
+    const RowScatter sc = scp ? *scp : RowScatter();
     ProfScope prof(PROF_GRU, st);
     if (gru_smem_bytes<8>(d_in, h) <= kMaxSmem)
-        return launch_gru_t<8>(seq, srs, sss, n, steps, d_in, h, wt_ih, wt_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, st);
+        return launch_gru_t<8>(seq, srs, sss, n, steps, d_in, h, wt_ih, wt_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, sc, st);
     CTGCN_REQUIRE(gru_smem_bytes<4>(d_in, h) <= kMaxSmem, "gru: d_in=%d, h=%d needs more than 227 KB of shared memory", d_in, h);
-    return launch_gru_t<4>(seq, srs, sss, n, steps, d_in, h, wt_ih, wt_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, st);
+    return launch_gru_t<4>(seq, srs, sss, n, steps, d_in, h, wt_ih, wt_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, sc, st);
 }
 
 int launch_linear_simt(const float* x, int64_t ldx, int64_t n, int64_t d_in, const float* wt, const float* b, int64_t d_out,

@@ -122,6 +122,7 @@ struct Params {
     float eps;
     float* y;
     int64_t yrs, yss;
+    RowScatter sc;      // SUM_LN only: rows go to their node slice's buffer (fused snapshot exchange)
     int num_tiles;
     long long* trace;   // optional [24 events][64 steps] clock64 stamps of block 0 (ctgcn_debug_gru_trace), else NULL
 };
@@ -533,7 +534,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
                 if (threadIdx.x == FIRST_WORKER_WARP * 32) GRU_TRACE(12, gs);
                 if (MODE == CTGCN_GRU_EACH_LN) layer_norm_store(acc_out, p.y + row * p.yrs + (int64_t)i * p.yss, valid);
             }
-            if (MODE == CTGCN_GRU_SUM_LN) layer_norm_store(acc_out, p.y + row * p.yrs, valid);
+            if (MODE == CTGCN_GRU_SUM_LN)
+                layer_norm_store(acc_out, (p.sc.slices && valid) ? p.sc.row_ptr(row) : p.y + row * p.yrs, valid);
         }
     }
 
@@ -629,10 +631,11 @@ void set_gru_trace(long long* buf) { g_gru_trace = buf; }
 // returns 0 = done, <0 = error, 1 = shape not supported by this path
 int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* w_ih,
                   const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
-                  int mode, float* y, int64_t yrs, int64_t yss, void* ws, size_t ws_bytes, cudaStream_t st) {
+                  int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* sc, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (h != H || (d_in != 64 && d_in != 128)) return 1;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    if (!al16(seq) || !al16(y) || (srs & 3) || (sss & 3) || (yrs & 3) || (yss & 3)) return 1;
+    if (!al16(seq) || (srs & 3) || (sss & 3)) return 1;
+    if (sc ? ((sc->row_stride & 3) || (sc->col_offset & 3)) : (!al16(y) || (yrs & 3) || (yss & 3))) return 1;
     const int nchunks = 2 * chunks_per_part(d_in) + 2 * chunks_per_part(H);
     const size_t packed_bytes = (size_t)nchunks * CHUNK_BYTES;
     CTGCN_REQUIRE(ws && ws_bytes >= packed_bytes + 4 * H * sizeof(float), "gru_tc: workspace too small");
@@ -667,6 +670,7 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
     p.y = y;
     p.yrs = yrs;
     p.yss = yss;
+    p.sc = sc ? *sc : RowScatter();
     p.num_tiles = (int)((n + TILE_M - 1) / TILE_M);
     p.trace = g_gru_trace;
     const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;

@@ -5,7 +5,8 @@ of adj_list[t] are disjoint per snapshot (reference models.py:225-231, 243-247),
 collective until the stack at models.py:248.  There, ONE exchange moves the per-snapshot embeddings so that
 every rank holds all T snapshots of ITS node slice ([N/G, T, D]); the temporal GRU + LayerNorm
 (models.py:249-250) is node-wise independent and runs on that slice.  ``exchange='all_to_all'`` (default)
-sends each rank only its slice; ``exchange='all_gather'`` is the literal all-gather of whole snapshots.
+sends each rank only its slice; ``exchange='all_gather'`` is the literal all-gather of whole snapshots;
+``exchange='p2p'`` fuses the exchange into the producing kernel's epilogue over NVLink peer memory (PeerExchange).
 A second collective gathers the output only if ``model.gather_output`` is set.
 
 The tensor-shuffling helpers below are device-agnostic so that the host logic is testable with gloo on CPU.
@@ -78,6 +79,67 @@ def gather_node_slices(out_slice: torch.Tensor, n: int, group=None) -> torch.Ten
     return torch.cat([full[g, : e - s] for g, (s, e) in enumerate(slices)], dim=0)
 
 
+class PeerExchange:
+    """Snapshot exchange fused into the CoreDiffusion epilogue over NVLink peer memory.
+
+    Every rank owns a symmetric buffer seq[rows_max, T, D] (torch symmetric memory: the same allocation is mapped into
+    every peer's address space).  The last CoreDiffusion layer of snapshot t stores row r directly into the buffer of the
+    rank that owns r's node slice (ctgcn_core_diffusion_fwd_scatter) — no staging copy, no NCCL call, no permute; the
+    transfer overlaps the GRU math tile by tile.  Two device-side barriers on the stream bracket the writes."""
+
+    _cache = {}
+
+    def __init__(self, n, T, d, dev, group):
+        import torch.distributed._symmetric_memory as symm
+        self.n, self.T, self.d = n, T, d
+        G = td.get_world_size(group)
+        self.slices = node_slices(n, G)
+        rows_max = max(e - s for s, e in self.slices)
+        self.buf = symm.empty((rows_max, T, d), dtype=torch.float32, device=dev)
+        self.handle = symm.rendezvous(self.buf, group if group is not None else td.group.WORLD)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+        s, e = self.slices[td.get_rank(group)]
+        self.rows = e - s
+
+    @classmethod
+    def get(cls, n, T, d, dev, group=None):
+        key = (n, T, d, str(dev), id(group))
+        if key not in cls._cache:
+            cls._cache[key] = cls(n, T, d, dev, group)
+        return cls._cache[key]
+
+    def scatter_args(self, t):
+        return (self.ptrs, self.T * self.d, t * self.d)
+
+    def barrier(self):
+        self.handle.barrier()
+
+    def local_seq(self):
+        return self.buf[: self.rows]
+
+
+def _forward_p2p(model, x_list, adj_list, owned, T, dev):
+    from .models import _HostFeatureStager
+    stager = _HostFeatureStager(x_list, owned, dev)
+    trans_list = [None] * T
+    ex, n = None, None
+    for t in owned:
+        trans = model.mlp_list[t](stager.get(t))
+        trans_list[t] = trans
+        if ex is None:
+            n = trans.shape[0]
+            ex = PeerExchange.get(n, T, model.output_dim, dev)
+            ex.barrier()                      # every peer has finished reading the previous call's sequence buffer
+        model.duffision_list[t].forward_into(trans, adj_list[t], scatter=ex.scatter_args(t))
+    if ex is None:                            # this rank owns no snapshot but still takes part in the barriers
+        n = int(getattr(model, "node_num", 0)) or _infer_rows(x_list, adj_list)
+        ex = PeerExchange.get(n, T, model.output_dim, dev)
+        ex.barrier()
+    ex.barrier()                              # all peers' rows have landed
+    return ex.local_seq(), n, trans_list
+
+
 def ctgcn_forward_sharded(model, x_list, adj_list):
     """CTGCN.forward under snapshot parallelism.  x_list[t] / adj_list[t] are only touched for owned t
     (entries for other snapshots may be None).  Returns the reference's [T, N, D] view when
@@ -91,6 +153,13 @@ def ctgcn_forward_sharded(model, x_list, adj_list):
     owned = owned_snapshots(T, G, r)
     tl = (T + G - 1) // G
     dev = model.norm.weight.device
+    if getattr(model, "exchange", "all_to_all") == "p2p":
+        seq, n, trans_list = _forward_p2p(model, x_list, adj_list, owned, T, dev)
+        out = model._temporal(seq)
+        if getattr(model, "gather_output", True):
+            out = gather_node_slices(out, n)
+        out = _guard(out, model).transpose(0, 1)
+        return out if model.model_type == 'C' else (out, trans_list)
     trans_list = [None] * T
     hx_local, n = None, None
     stager = _HostFeatureStager(x_list, owned, dev)

@@ -61,9 +61,15 @@ class CoreDiffusion(nn.Module):
         return (r.weight_ih_l0, r.weight_hh_l0, getattr(r, "bias_ih_l0", None) if self.bias else None,
                 getattr(r, "bias_hh_l0", None) if self.bias else None)
 
-    def forward_into(self, x, adj_list, out=None):
+    def forward_into(self, x, adj_list, out=None, scatter=None):
+        """forward() writing into `out` ([N, H] view, any row stride) or — `scatter` = (slice_ptrs, row_stride,
+        col_offset) — straight into the node slices' (peer) buffers; then nothing is returned."""
         plan = plan_for(adj_list, x.device)
         w_ih, w_hh, b_ih, b_hh = self._gru_params()
+        if scatter is not None:
+            ops.core_diffusion_scatter(plan, x.detach(), w_ih, w_hh, b_ih, b_hh, self.norm.weight, self.norm.bias, self.norm.eps,
+                                       *scatter)
+            return None
         y = ops.core_diffusion(plan, x.detach(), w_ih, w_hh, b_ih, b_hh, self.norm.weight, self.norm.bias, self.norm.eps,
                                out=out)
         return _guard(y, self, x)

@@ -73,10 +73,10 @@ class CDN(nn.Module):
         self.diffusion_list = nn.ModuleList(
             CoreDiffusion(widths[l], widths[l + 1], bias=bias, rnn_type=rnn_type) for l in range(diffusion_num))
 
-    def forward_into(self, x, adj_list, out=None):
+    def forward_into(self, x, adj_list, out=None, scatter=None):
         last = self.diffusion_num - 1
         for l, layer in enumerate(self.diffusion_list):
-            x = layer.forward_into(x, adj_list, out if l == last else None)
+            x = layer.forward_into(x, adj_list, out if l == last else None, scatter if l == last else None)
         return x
 
     def forward(self, x, adj_list):

@@ -111,6 +111,29 @@ def core_diffusion(plan: GraphPlan, x, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps: 
     return out
 
 
+def core_diffusion_scatter(plan: GraphPlan, x, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps: float, slice_ptrs: torch.Tensor,
+                           slice_row_stride: int, slice_col_offset: int):
+    """CoreDiffusion.forward whose [N, H] result is scattered row-wise into the node slices' buffers
+    (ctgcn_core_diffusion_fwd_scatter).  slice_ptrs: int64 CUDA tensor of (peer-mapped) base pointers."""
+    x = _f32_rows(x, "x")
+    d_in = x.shape[1]
+    h = w_hh.shape[1]
+    if x.shape[0] != plan.n_cols:
+        raise _lib.CtgcnError(f"x has {x.shape[0]} rows, the plan expects {plan.n_cols}")
+    if slice_ptrs.dtype != torch.int64 or not slice_ptrs.is_cuda:
+        raise _lib.CtgcnError("slice_ptrs must be an int64 CUDA tensor of device pointers")
+    w_ih, w_hh, b_ih, b_hh, ln_w, ln_b = (_vec(t, nm) for t, nm in
+                                           ((w_ih, "w_ih"), (w_hh, "w_hh"), (b_ih, "b_ih"), (b_hh, "b_hh"),
+                                            (ln_w, "ln_w"), (ln_b, "ln_b")))
+    ws_bytes = _lib.lib.ctgcn_core_diffusion_workspace_bytes(plan.handle, d_in, h)
+    ws = _workspace(ws_bytes, x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib.ctgcn_core_diffusion_fwd_scatter(
+            plan.handle, _ptr(x), x.stride(0), d_in, h, _ptr(w_ih), _ptr(w_hh), _ptr(b_ih), _ptr(b_hh), _ptr(ln_w), _ptr(ln_b),
+            float(eps), _ptr(slice_ptrs), slice_ptrs.numel(), int(slice_row_stride), int(slice_col_offset), _ptr(ws), ws_bytes,
+            _stream()), "ctgcn_core_diffusion_fwd_scatter")
+
+
 def linear(x, w, b, act: int):
     """act(x wᵀ + b) for dense x [N, d_in]."""
     x = _f32_rows(x, "x")

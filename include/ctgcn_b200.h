@@ -131,6 +131,19 @@ int ctgcn_core_diffusion_fwd(const ctgcn_plan* plan, const float* x, int64_t ldx
                              const float* ln_w, const float* ln_b, float eps, float* y, int64_t ldy,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same layer with the snapshot exchange of CTGCN.forward (models.py:248) fused into the epilogue: output row r is stored
+ * into the buffer of the node slice that owns it (n_slices balanced contiguous slices of the n_rows nodes, the first
+ * n_rows % n_slices of them one row longer) at
+ *     slice_ptrs[g][(r - start_g) * slice_row_stride + slice_col_offset + j],   j < h.
+ * slice_ptrs is a DEVICE array of n_slices pointers; with peer-mapped (NVLink) pointers every GPU writes its snapshot's rows
+ * straight into the [rows, T, D] sequence buffer of the rank that runs the temporal GRU on them.  The caller provides the
+ * cross-GPU barrier before those buffers are read. */
+int ctgcn_core_diffusion_fwd_scatter(const ctgcn_plan* plan, const float* x, int64_t ldx, int d_in, int h,
+                                     const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                     const float* ln_w, const float* ln_b, float eps, float* const* slice_ptrs, int n_slices,
+                                     int64_t slice_row_stride, int64_t slice_col_offset, void* workspace,
+                                     size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- MLP layers (layers.py:95-106)
  * dense:  y[n, d_out] = act(x[n, d_in] w^T + b),  w [d_out, d_in] (nn.Linear layout), b may be NULL.
  * workspace: ctgcn_linear_workspace_bytes(d_in, d_out). */

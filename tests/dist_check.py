@@ -39,7 +39,7 @@ def main():
     snaps = [synth.make_snapshot("er", n, 30000, K, seed=t) for t in range(T)]
     sd = cases.ctgcn_params(np.random.default_rng(0), d, d, d, 1, 1, T, "S")
     ok = True
-    for exchange in ("all_to_all", "all_gather"):
+    for exchange in ("all_to_all", "all_gather", "p2p"):
         model = pkg.CTGCN(d, d, d, 1, 1, T, model_type="S").to(dev)
         model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
         model.exchange = exchange

@@ -250,6 +250,31 @@ def test_gru_seq_kernel(n, steps, d_in, h, bias, mode, impl, lib, cuda_device):
     assert (out[:, 0] == 7.0).all() if mode else (out[:, h:] == 7.0).all()   # nothing written outside the view
 
 
+# ----------------------------------------------------------------------------- fused exchange epilogue
+@pytest.mark.parametrize("name,n_slices", [("cd_nested_k5", 3), ("cd_nested_k5", 8), ("cd_general", 4), ("cd_uci_0404_500_128", 5)])
+def test_core_diffusion_scatter(name, n_slices, impl, lib, cuda_device):
+    """ctgcn_core_diffusion_fwd_scatter: rows land in their node slice's [rows, T, D] buffer at snapshot slot t —
+    here all slices are local buffers; with peer-mapped pointers this is the NVLink snapshot exchange."""
+    import ctgcn_b200 as pkg
+    from ctgcn_b200 import dist, ops, plan as P
+    c = cases.load_case(name)
+    m = c["meta"]
+    mod = pkg.CoreDiffusion(m["d_in"], m["d_out"], bias=m["bias"]).to(cuda_device)
+    mod.load_state_dict(tsd(c["sd"], cuda_device), strict=True)
+    plan = P.build_plan_coo(coo(c["adj"], cuda_device), cuda_device)
+    x = torch.from_numpy(c["x"]).to(cuda_device)
+    n, h, T, t = plan.n_rows, m["d_out"], 3, 1
+    slices = dist.node_slices(n, n_slices)
+    bufs = [torch.full((e - s + 2, T, h), -5.0, device=cuda_device) for s, e in slices]   # 2 guard rows each
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=cuda_device)
+    with torch.no_grad():
+        ref = mod(x, plan)
+        assert mod.forward_into(x, plan, scatter=(ptrs, T * h, t * h)) is None
+    for (s, e), b in zip(slices, bufs):
+        assert torch.equal(b[: e - s, t], ref[s:e]), name
+        assert (b[: e - s, 0] == -5.0).all() and (b[: e - s, 2] == -5.0).all() and (b[e - s:] == -5.0).all()
+
+
 # ----------------------------------------------------------------------------- dense layer kernels
 @pytest.mark.parametrize("n,d_in,d_out,act,bias", [(1000, 128, 128, "L", True), (77, 64, 128, "N", True), (300, 128, 64, "N", False),
                                                    (5, 64, 64, "L", True), (40000, 128, 128, "N", True), (129, 100, 128, "L", True)])
