@@ -174,7 +174,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--gru-impl", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="all_to_all", choices=["all_to_all", "all_gather", "p2p"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "all_to_all", "all_gather", "p2p"])
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -4,9 +4,10 @@ Sharding: snapshot t is owned by rank t mod G — MLP_t / CDN_t
 of adj_list[t] are disjoint per snapshot (reference models.py:225-231, 243-247), so there is no data-path
 collective until the stack at models.py:248.  There, ONE exchange moves the per-snapshot embeddings so that
 every rank holds all T snapshots of ITS node slice ([N/G, T, D]); the temporal GRU + LayerNorm
-(models.py:249-250) is node-wise independent and runs on that slice.  ``exchange='all_to_all'`` (default)
+(models.py:249-250) is node-wise independent and runs on that slice.  ``exchange='all_to_all'``
 sends each rank only its slice; ``exchange='all_gather'`` is the literal all-gather of whole snapshots;
-``exchange='p2p'`` fuses the exchange into the producing kernel's epilogue over NVLink peer memory (PeerExchange).
+``exchange='p2p'`` fuses the exchange into the producing kernel's epilogue over NVLink peer memory (PeerExchange);
+``'auto'`` (default) = p2p when symmetric memory is available, else all_to_all.
 A second collective gathers the output only if ``model.gather_output`` is set.
 
 The tensor-shuffling helpers below are device-agnostic so that the host logic is testable with gloo on CPU.
@@ -119,6 +120,29 @@ class PeerExchange:
         return self.buf[: self.rows]
 
 
+_p2p_state = {}
+
+
+def _p2p_available(dev) -> bool:
+    """Symmetric (peer-mapped) memory works for this process group?  Probed once, collectively (every rank takes the same
+    branch: the outcome is all-reduced), with a tiny allocation; any failure selects the NCCL all_to_all exchange."""
+    key = str(dev)
+    if key not in _p2p_state:
+        ok = 1
+        try:
+            import torch.distributed._symmetric_memory as symm
+            t = symm.empty((16,), dtype=torch.float32, device=dev)
+            symm.rendezvous(t, td.group.WORLD).barrier()
+        except Exception as exc:  # noqa: BLE001 - any failure means "use NCCL"
+            import sys
+            print(f"ctgcn_b200: peer-memory exchange unavailable ({exc!r}); using NCCL all_to_all", file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        td.all_reduce(flag, op=td.ReduceOp.MIN)
+        _p2p_state[key] = bool(flag.item())
+    return _p2p_state[key]
+
+
 def _forward_p2p(model, x_list, adj_list, owned, T, dev):
     from .models import _HostFeatureStager
     stager = _HostFeatureStager(x_list, owned, dev)
@@ -153,7 +177,10 @@ def ctgcn_forward_sharded(model, x_list, adj_list):
     owned = owned_snapshots(T, G, r)
     tl = (T + G - 1) // G
     dev = model.norm.weight.device
-    if getattr(model, "exchange", "all_to_all") == "p2p":
+    mode = getattr(model, "exchange", "auto")
+    if mode == "auto":
+        mode = "p2p" if _p2p_available(dev) else "all_to_all"
+    if mode == "p2p":
         seq, n, trans_list = _forward_p2p(model, x_list, adj_list, owned, T, dev)
         out = model._temporal(seq)
         if getattr(model, "gather_output", True):
@@ -173,7 +200,7 @@ def ctgcn_forward_sharded(model, x_list, adj_list):
     if hx_local is None:  # more ranks than snapshots: this rank owns nothing but still takes part
         n = int(getattr(model, "node_num", 0)) or _infer_rows(x_list, adj_list)
         hx_local = torch.zeros(n, tl, model.output_dim, dtype=torch.float32, device=dev)
-    seq = exchange_to_node_slices(hx_local, T, mode=getattr(model, "exchange", "all_to_all"))
+    seq = exchange_to_node_slices(hx_local, T, mode=mode)
     out = model._temporal(seq)
     if getattr(model, "gather_output", True):
         out = gather_node_slices(out, n)
