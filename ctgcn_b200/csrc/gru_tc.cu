@@ -421,6 +421,51 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
             }
         };
 
+        // SUM_LN result of a tile: normalised rows are staged in the (now idle) h buffer with a 16-byte XOR swizzle and
+        // written out one whole 512-byte row per warp instruction — to y, or straight into the owning node slice's
+        // (peer) buffer: NVLink wants full-line stores, not 32 scattered 16-byte pieces per instruction.
+        auto layer_norm_store_rows = [&](const float (&v)[64], int64_t tile_row0) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) s += v[j];
+            red[ch * TILE_M + m] = s;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float mean = (s + red[(ch ^ 1) * TILE_M + m]) * (1.f / H);
+            float sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const float dlt = v[j] - mean;
+                sq = fmaf(dlt, dlt, sq);
+            }
+            red[2 * TILE_M + ch * TILE_M + m] = sq;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float rstd = rsqrtf((sq + red[2 * TILE_M + (ch ^ 1) * TILE_M + m]) * (1.f / H) + p.eps);
+            float* stage = reinterpret_cast<float*>(smem + SM_H);     // [128 rows][32 chunks of 4 floats], chunk c of row r at c ^ (r & 31)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                for (int j4 = 0; j4 < 32; j4 += 4) {
+                    const int f = hf * 64 + ch * 32 + j4;
+                    float4 o;
+                    o.x = (v[hf * 32 + j4 + 0] - mean) * rstd * lnw[f + 0] + lnw[H + f + 0];
+                    o.y = (v[hf * 32 + j4 + 1] - mean) * rstd * lnw[f + 1] + lnw[H + f + 1];
+                    o.z = (v[hf * 32 + j4 + 2] - mean) * rstd * lnw[f + 2] + lnw[H + f + 2];
+                    o.w = (v[hf * 32 + j4 + 3] - mean) * rstd * lnw[f + 3] + lnw[H + f + 3];
+                    *reinterpret_cast<float4*>(stage + m * H + (((f >> 2) ^ (m & 31)) << 2)) = o;
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int rr = 0; rr < TILE_M / NUM_WORKER_WARPS; ++rr) {
+                const int r = ww * (TILE_M / NUM_WORKER_WARPS) + rr;
+                const int64_t grow = tile_row0 + r;
+                if (grow >= p.n) break;   // warp-uniform
+                const float4 o = *reinterpret_cast<const float4*>(stage + r * H + ((lane ^ (r & 31)) << 2));
+                float* dst = p.sc.slices ? p.sc.row_ptr(grow) : p.y + grow * p.yrs;
+                *reinterpret_cast<float4*>(dst + 4 * lane) = o;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // the staging area is h again from the next tile's first step on
+        };
+
         for (int t = 0; t < my_tiles; ++t) {
             const int64_t row = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + m;
             const bool valid = row < p.n;
@@ -534,8 +579,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
                 if (threadIdx.x == FIRST_WORKER_WARP * 32) GRU_TRACE(12, gs);
                 if (MODE == CTGCN_GRU_EACH_LN) layer_norm_store(acc_out, p.y + row * p.yrs + (int64_t)i * p.yss, valid);
             }
-            if (MODE == CTGCN_GRU_SUM_LN)
-                layer_norm_store(acc_out, (p.sc.slices && valid) ? p.sc.row_ptr(row) : p.y + row * p.yrs, valid);
+            if (MODE == CTGCN_GRU_SUM_LN) layer_norm_store_rows(acc_out, row - m);
         }
     }
 

@@ -102,6 +102,8 @@ class PeerExchange:
         self.ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
         s, e = self.slices[td.get_rank(group)]
         self.rows = e - s
+        self.group = group
+        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
 
     @classmethod
     def get(cls, n, T, d, dev, group=None):
@@ -114,7 +116,9 @@ class PeerExchange:
         return (self.ptrs, self.T * self.d, t * self.d)
 
     def barrier(self):
-        self.handle.barrier()
+        # A 4-byte NCCL all-reduce on the compute stream: it starts after this rank's producing kernel has completed
+        # (peer stores are visible system-wide at kernel completion) and completes only when every rank got there.
+        td.all_reduce(self._flag, group=self.group)
 
     def local_seq(self):
         return self.buf[: self.rows]
