@@ -15,6 +15,8 @@ OK, EINVAL, ECUDA, ENOMEM, ENODEV = 0, -1, -2, -3, -4
 ACT_NONE, ACT_SELU = 0, 1
 GRU_SUM_LN, GRU_EACH_LN = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+CELL_GRU, CELL_LSTM = 0, 1
+CELLS = {"GRU": CELL_GRU, "LSTM": CELL_LSTM}
 MAX_CORES = 64
 
 
@@ -44,8 +46,14 @@ SIGNATURES = {
     "ctgcn_plan_stats": (C.c_int, [_p, _p]),
     "ctgcn_plan_arrays": (C.c_int, [_p, _p, _p, _p, _p, _p]),
     "ctgcn_cumspmm_fwd": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),
+    "ctgcn_cumspmm_fwd_ex": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p]),
+    "ctgcn_cumspmm_bwd_workspace_bytes": (_sz, [_p, _i32]),
+    "ctgcn_cumspmm_bwd": (C.c_int, [_p, _p, _i32, _p, _i64, _p, _sz, _p]),
     "ctgcn_gru_workspace_bytes": (_sz, [_i32, _i32]),
     "ctgcn_gru_seq_fwd": (C.c_int, [_p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _f32, _i32, _p, _i64,
+                                    _i64, _p, _sz, _p]),
+    "ctgcn_rnn_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "ctgcn_rnn_seq_fwd": (C.c_int, [_i32, _p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _f32, _i32, _p, _i64,
                                     _i64, _p, _sz, _p]),
     "ctgcn_set_gru_impl": (C.c_int, [_i32]),
     "ctgcn_debug_gru_trace": (C.c_int, [_p]),
@@ -54,6 +62,9 @@ SIGNATURES = {
     "ctgcn_core_diffusion_fwd": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _f32, _p, _i64, _p, _sz, _p]),
     "ctgcn_core_diffusion_fwd_scatter": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _f32, _p, _i32, _i64, _i64,
                                                    _p, _sz, _p]),
+    "ctgcn_core_diffusion_rnn_workspace_bytes": (_sz, [_p, _i32, _i32, _i32]),
+    "ctgcn_core_diffusion_rnn_fwd": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _f32, _p, _i64, _p, _i32,
+                                               _i64, _i64, _p, _sz, _p]),
     "ctgcn_linear_workspace_bytes": (_sz, [_i64, _i64]),
     "ctgcn_linear_fwd": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _i32, _p, _i64, _p, _sz, _p]),
     "ctgcn_spmm_linear_fwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _i64, _p, _sz, _p]),

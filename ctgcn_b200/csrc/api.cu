@@ -124,69 +124,121 @@ extern "C" int ctgcn_cumspmm_fwd(const ctgcn_plan* plan, const float* x, int64_t
     return launch_cumspmm(plan, x, ldx, d, u, true, (cudaStream_t)stream);
 }
 
-// ---- GRU: workspace = k-major copies of the two weight matrices (SIMT path) | tcgen05 packed weights
-static size_t gru_ws_simt(int d_in, int h) { return align_up((size_t)3 * h * (d_in + h) * sizeof(float), 256); }
-static size_t gru_ws_tc(int d_in, int h) { return align_up((size_t)3 * h * (d_in + h) * 2 * sizeof(uint16_t), 256) + 4096; }
-
-extern "C" size_t ctgcn_gru_workspace_bytes(int d_in, int h) {
-    if (d_in <= 0 || h <= 0) return 0;
-    return gru_ws_simt(d_in, h) + gru_ws_tc(d_in, h);
+// plain / cumulative SpMM with the relu switchable (relu = 0: S_i itself; with a K = 1 plan a plain SpMM A·x)
+extern "C" int ctgcn_cumspmm_fwd_ex(const ctgcn_plan* plan, const float* x, int64_t ldx, int d, int relu, float* u,
+                                    void* stream) {
+    CTGCN_REQUIRE(plan && x && u, "cumspmm_fwd_ex: NULL argument");
+    CTGCN_REQUIRE(ldx >= d, "cumspmm_fwd_ex: ldx < d");
+    return launch_cumspmm(plan, x, ldx, d, u, relu != 0, (cudaStream_t)stream);
 }
 
-static int gru_seq_impl(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* w_ih,
-                        const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b,
-                        float eps, int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* sc, void* workspace,
-                        size_t workspace_bytes, void* stream) {
-    CTGCN_REQUIRE(seq && w_ih && w_hh && ln_w && ln_b && (y || sc), "gru_seq_fwd: NULL argument");
-    CTGCN_REQUIRE((b_ih == nullptr) == (b_hh == nullptr), "gru_seq_fwd: b_ih and b_hh must both be given or both NULL");
-    CTGCN_REQUIRE(n >= 0 && steps >= 1 && d_in >= 1 && h >= 1, "gru_seq_fwd: bad sizes n=%lld steps=%d d_in=%d h=%d",
+// ---- backward of the cumulative SpMM w.r.t. x: workspace = Zo | Zn, each [n_cols(plan_t), K, d]
+extern "C" size_t ctgcn_cumspmm_bwd_workspace_bytes(const ctgcn_plan* plan_t, int d) {
+    if (!plan_t || d <= 0) return 0;
+    return 2 * align_up((size_t)plan_t->n_cols * plan_t->k * d * sizeof(float), 256);
+}
+
+extern "C" int ctgcn_cumspmm_bwd(const ctgcn_plan* plan_t, const float* g, int d, float* dx, int64_t lddx, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+    CTGCN_REQUIRE(plan_t && g && dx, "cumspmm_bwd: NULL argument");
+    CTGCN_REQUIRE(lddx >= d, "cumspmm_bwd: lddx < d");
+    const size_t need = ctgcn_cumspmm_bwd_workspace_bytes(plan_t, d);
+    if (!workspace || workspace_bytes < need) {
+        set_error("cumspmm_bwd: workspace of %zu bytes, need %zu", workspace_bytes, need);
+        return CTGCN_ENOMEM;
+    }
+    float* zo = (float*)workspace;
+    float* zn = (float*)((char*)workspace + need / 2);
+    return launch_cumspmm_bwd(plan_t, g, d, zo, zn, dx, lddx, (cudaStream_t)stream);
+}
+
+// ---- GRU / LSTM: workspace = k-major copies of the two weight matrices (SIMT path) | tcgen05 packed weights (GRU only)
+static int cell_gates(int cell) { return cell == CTGCN_CELL_LSTM ? 4 : 3; }
+static size_t rnn_ws_simt(int cell, int d_in, int h) {
+    return align_up((size_t)cell_gates(cell) * h * (d_in + h) * sizeof(float), 256);
+}
+static size_t gru_ws_tc(int d_in, int h) { return align_up((size_t)3 * h * (d_in + h) * 2 * sizeof(uint16_t), 256) + 4096; }
+
+extern "C" size_t ctgcn_rnn_workspace_bytes(int cell, int d_in, int h) {
+    if (d_in <= 0 || h <= 0 || (cell != CTGCN_CELL_GRU && cell != CTGCN_CELL_LSTM)) return 0;
+    return rnn_ws_simt(cell, d_in, h) + (cell == CTGCN_CELL_GRU ? gru_ws_tc(d_in, h) : 0);
+}
+
+extern "C" size_t ctgcn_gru_workspace_bytes(int d_in, int h) { return ctgcn_rnn_workspace_bytes(CTGCN_CELL_GRU, d_in, h); }
+
+static int rnn_seq_impl(int cell, const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h,
+                        const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w,
+                        const float* ln_b, float eps, int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* sc,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    CTGCN_REQUIRE(cell == CTGCN_CELL_GRU || cell == CTGCN_CELL_LSTM, "rnn_seq_fwd: unknown cell %d", cell);
+    CTGCN_REQUIRE(seq && w_ih && w_hh && ln_w && ln_b && (y || sc), "rnn_seq_fwd: NULL argument");
+    CTGCN_REQUIRE((b_ih == nullptr) == (b_hh == nullptr), "rnn_seq_fwd: b_ih and b_hh must both be given or both NULL");
+    CTGCN_REQUIRE(n >= 0 && steps >= 1 && d_in >= 1 && h >= 1, "rnn_seq_fwd: bad sizes n=%lld steps=%d d_in=%d h=%d",
                   (long long)n, steps, d_in, h);
-    CTGCN_REQUIRE(mode == CTGCN_GRU_SUM_LN || mode == CTGCN_GRU_EACH_LN, "gru_seq_fwd: unknown mode %d", mode);
-    if (workspace_bytes < ctgcn_gru_workspace_bytes(d_in, h) || !workspace) {
-        set_error("gru_seq_fwd: workspace of %zu bytes, need %zu", workspace_bytes, ctgcn_gru_workspace_bytes(d_in, h));
+    CTGCN_REQUIRE(mode == CTGCN_GRU_SUM_LN || mode == CTGCN_GRU_EACH_LN, "rnn_seq_fwd: unknown mode %d", mode);
+    if (workspace_bytes < ctgcn_rnn_workspace_bytes(cell, d_in, h) || !workspace) {
+        set_error("rnn_seq_fwd: workspace of %zu bytes, need %zu", workspace_bytes, ctgcn_rnn_workspace_bytes(cell, d_in, h));
         return CTGCN_ENOMEM;
     }
     if (n == 0) return CTGCN_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int impl = g_gru_impl.load();
-    if (impl != CTGCN_IMPL_SIMT) {
-        char* tc_ws = (char*)workspace + gru_ws_simt(d_in, h);
+    if (cell == CTGCN_CELL_GRU && impl != CTGCN_IMPL_SIMT) {
+        char* tc_ws = (char*)workspace + rnn_ws_simt(cell, d_in, h);
         int rc = launch_gru_tc(seq, srs, sss, n, steps, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, sc,
                                tc_ws, gru_ws_tc(d_in, h), st);
         if (rc <= 0) return rc;  // done or failed
         CTGCN_REQUIRE(impl == CTGCN_IMPL_AUTO, "gru_seq_fwd: tcgen05 path does not support d_in=%d h=%d", d_in, h);
     }
+    const int g = cell_gates(cell);
     float* wt_ih = (float*)workspace;
-    float* wt_hh = wt_ih + (size_t)3 * h * d_in;
-    int rc = launch_transpose(w_ih, 3 * h, d_in, wt_ih, st);
+    float* wt_hh = wt_ih + (size_t)g * h * d_in;
+    int rc = launch_transpose(w_ih, (int64_t)g * h, d_in, wt_ih, st);
     if (rc) return rc;
-    rc = launch_transpose(w_hh, 3 * h, h, wt_hh, st);
+    rc = launch_transpose(w_hh, (int64_t)g * h, h, wt_hh, st);
     if (rc) return rc;
+    if (cell == CTGCN_CELL_LSTM)
+        return launch_lstm_simt(seq, srs, sss, n, steps, d_in, h, wt_ih, wt_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, sc, st);
     return launch_gru_simt(seq, srs, sss, n, steps, d_in, h, wt_ih, wt_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, sc, st);
+}
+
+extern "C" int ctgcn_rnn_seq_fwd(int cell, const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h,
+                                 const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                 const float* ln_w, const float* ln_b, float eps, int mode, float* y, int64_t yrs,
+                                 int64_t yss, void* workspace, size_t workspace_bytes, void* stream) {
+    return rnn_seq_impl(cell, seq, srs, sss, n, steps, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss,
+                        nullptr, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ctgcn_gru_seq_fwd(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h,
                                  const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                                  const float* ln_w, const float* ln_b, float eps, int mode, float* y, int64_t yrs,
                                  int64_t yss, void* workspace, size_t workspace_bytes, void* stream) {
-    return gru_seq_impl(seq, srs, sss, n, steps, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, nullptr,
-                        workspace, workspace_bytes, stream);
+    return rnn_seq_impl(CTGCN_CELL_GRU, seq, srs, sss, n, steps, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y,
+                        yrs, yss, nullptr, workspace, workspace_bytes, stream);
 }
 
-// ---- CoreDiffusion.forward: cumulative SpMM → U [n, K, d_in] (workspace) → GRU over cores + Σ + LayerNorm
-extern "C" size_t ctgcn_core_diffusion_workspace_bytes(const ctgcn_plan* plan, int d_in, int h) {
+// ---- CoreDiffusion.forward: cumulative SpMM → U [n, K, d_in] (workspace) → GRU/LSTM over cores + Σ + LayerNorm
+extern "C" size_t ctgcn_core_diffusion_rnn_workspace_bytes(const ctgcn_plan* plan, int cell, int d_in, int h) {
     if (!plan || d_in <= 0 || h <= 0) return 0;
-    return align_up((size_t)plan->n_rows * plan->k * d_in * sizeof(float), 256) + ctgcn_gru_workspace_bytes(d_in, h);
+    const size_t r = ctgcn_rnn_workspace_bytes(cell, d_in, h);
+    if (!r) return 0;
+    return align_up((size_t)plan->n_rows * plan->k * d_in * sizeof(float), 256) + r;
 }
 
-static int core_diffusion_impl(const ctgcn_plan* plan, const float* x, int64_t ldx, int d_in, int h, const float* w_ih,
-                               const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b,
-                               float eps, float* y, int64_t ldy, const RowScatter* sc, void* workspace, size_t workspace_bytes,
-                               void* stream) {
+extern "C" size_t ctgcn_core_diffusion_workspace_bytes(const ctgcn_plan* plan, int d_in, int h) {
+    return ctgcn_core_diffusion_rnn_workspace_bytes(plan, CTGCN_CELL_GRU, d_in, h);
+}
+
+static int core_diffusion_impl(const ctgcn_plan* plan, int cell, const float* x, int64_t ldx, int d_in, int h,
+                               const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w,
+                               const float* ln_b, float eps, float* y, int64_t ldy, const RowScatter* sc, void* workspace,
+                               size_t workspace_bytes, void* stream) {
     CTGCN_REQUIRE(plan && x && (y || sc), "core_diffusion_fwd: NULL argument");
+    CTGCN_REQUIRE(cell == CTGCN_CELL_GRU || cell == CTGCN_CELL_LSTM, "core_diffusion_fwd: unknown cell %d", cell);
     CTGCN_REQUIRE(plan->n_rows == plan->n_cols, "core_diffusion_fwd: adjacency plan must be square");
     CTGCN_REQUIRE(ldx >= d_in && (sc || ldy >= h), "core_diffusion_fwd: leading dimension too small");
-    const size_t need = ctgcn_core_diffusion_workspace_bytes(plan, d_in, h);
+    const size_t need = ctgcn_core_diffusion_rnn_workspace_bytes(plan, cell, d_in, h);
     if (!workspace || workspace_bytes < need) {
         set_error("core_diffusion_fwd: workspace of %zu bytes, need %zu", workspace_bytes, need);
         return CTGCN_ENOMEM;
@@ -195,16 +247,30 @@ static int core_diffusion_impl(const ctgcn_plan* plan, const float* x, int64_t l
     const size_t u_bytes = align_up((size_t)plan->n_rows * plan->k * d_in * sizeof(float), 256);
     int rc = launch_cumspmm(plan, x, ldx, d_in, u, true, (cudaStream_t)stream);
     if (rc) return rc;
-    return gru_seq_impl(u, (int64_t)plan->k * d_in, d_in, plan->n_rows, plan->k, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b,
-                        eps, CTGCN_GRU_SUM_LN, y, ldy, 0, sc, (char*)workspace + u_bytes, workspace_bytes - u_bytes, stream);
+    return rnn_seq_impl(cell, u, (int64_t)plan->k * d_in, d_in, plan->n_rows, plan->k, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w,
+                        ln_b, eps, CTGCN_GRU_SUM_LN, y, ldy, 0, sc, (char*)workspace + u_bytes, workspace_bytes - u_bytes,
+                        stream);
+}
+
+static int make_scatter(const ctgcn_plan* plan, int h, float* const* slice_ptrs, int n_slices, int64_t slice_row_stride,
+                        int64_t slice_col_offset, RowScatter* sc) {
+    CTGCN_REQUIRE(plan && slice_ptrs && n_slices >= 1 && n_slices <= plan->n_rows, "core_diffusion_fwd_scatter: bad slice arguments");
+    CTGCN_REQUIRE(slice_row_stride >= slice_col_offset + h && slice_col_offset >= 0, "core_diffusion_fwd_scatter: bad slice strides");
+    sc->slices = slice_ptrs;
+    sc->n_slices = n_slices;
+    sc->base = plan->n_rows / n_slices;
+    sc->rem = plan->n_rows % n_slices;
+    sc->row_stride = slice_row_stride;
+    sc->col_offset = slice_col_offset;
+    return CTGCN_OK;
 }
 
 extern "C" int ctgcn_core_diffusion_fwd(const ctgcn_plan* plan, const float* x, int64_t ldx, int d_in, int h,
                                         const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                                         const float* ln_w, const float* ln_b, float eps, float* y, int64_t ldy,
                                         void* workspace, size_t workspace_bytes, void* stream) {
-    return core_diffusion_impl(plan, x, ldx, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, y, ldy, nullptr, workspace,
-                               workspace_bytes, stream);
+    return core_diffusion_impl(plan, CTGCN_CELL_GRU, x, ldx, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, y, ldy, nullptr,
+                               workspace, workspace_bytes, stream);
 }
 
 extern "C" int ctgcn_core_diffusion_fwd_scatter(const ctgcn_plan* plan, const float* x, int64_t ldx, int d_in, int h,
@@ -212,16 +278,25 @@ extern "C" int ctgcn_core_diffusion_fwd_scatter(const ctgcn_plan* plan, const fl
                                                 const float* ln_w, const float* ln_b, float eps, float* const* slice_ptrs,
                                                 int n_slices, int64_t slice_row_stride, int64_t slice_col_offset,
                                                 void* workspace, size_t workspace_bytes, void* stream) {
-    CTGCN_REQUIRE(plan && slice_ptrs && n_slices >= 1 && n_slices <= plan->n_rows, "core_diffusion_fwd_scatter: bad slice arguments");
-    CTGCN_REQUIRE(slice_row_stride >= slice_col_offset + h && slice_col_offset >= 0, "core_diffusion_fwd_scatter: bad slice strides");
     RowScatter sc;
-    sc.slices = slice_ptrs;
-    sc.n_slices = n_slices;
-    sc.base = plan->n_rows / n_slices;
-    sc.rem = plan->n_rows % n_slices;
-    sc.row_stride = slice_row_stride;
-    sc.col_offset = slice_col_offset;
-    return core_diffusion_impl(plan, x, ldx, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, nullptr, 0, &sc, workspace,
+    int rc = make_scatter(plan, h, slice_ptrs, n_slices, slice_row_stride, slice_col_offset, &sc);
+    if (rc) return rc;
+    return core_diffusion_impl(plan, CTGCN_CELL_GRU, x, ldx, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, nullptr, 0, &sc,
+                               workspace, workspace_bytes, stream);
+}
+
+extern "C" int ctgcn_core_diffusion_rnn_fwd(const ctgcn_plan* plan, int cell, const float* x, int64_t ldx, int d_in, int h,
+                                            const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                            const float* ln_w, const float* ln_b, float eps, float* y, int64_t ldy,
+                                            float* const* slice_ptrs, int n_slices, int64_t slice_row_stride,
+                                            int64_t slice_col_offset, void* workspace, size_t workspace_bytes, void* stream) {
+    if (y)
+        return core_diffusion_impl(plan, cell, x, ldx, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, y, ldy, nullptr,
+                                   workspace, workspace_bytes, stream);
+    RowScatter sc;
+    int rc = make_scatter(plan, h, slice_ptrs, n_slices, slice_row_stride, slice_col_offset, &sc);
+    if (rc) return rc;
+    return core_diffusion_impl(plan, cell, x, ldx, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, nullptr, 0, &sc, workspace,
                                workspace_bytes, stream);
 }
 

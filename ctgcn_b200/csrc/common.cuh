@@ -105,6 +105,8 @@ struct RowScatter {
 // kernels' host launchers (defined in the respective .cu files)
 namespace ctgcn {
 int launch_cumspmm(const ctgcn_plan* p, const float* x, int64_t ldx, int d, float* u, bool relu, cudaStream_t st);
+int launch_cumspmm_bwd(const ctgcn_plan* pt, const float* g, int d, float* zo, float* zn, float* dx, int64_t lddx,
+                       cudaStream_t st);
 int launch_spmm_linear(const ctgcn_plan* p, const float* wt, const float* b, int64_t d_out, int act, float* y,
                        int64_t ldy, cudaStream_t st);
 int launch_transpose(const float* src, int64_t rows, int64_t cols, float* dst, cudaStream_t st);
@@ -114,4 +116,8 @@ int launch_gru_simt(const float* seq, int64_t srs, int64_t sss, int64_t n, int s
                     const float* wt_ih, const float* wt_hh, const float* b_ih, const float* b_hh, const float* ln_w,
                     const float* ln_b, float eps, int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* sc,
                     cudaStream_t st);
+int launch_lstm_simt(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h,
+                     const float* wt_ih, const float* wt_hh, const float* b_ih, const float* b_hh, const float* ln_w,
+                     const float* ln_b, float eps, int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* sc,
+                     cudaStream_t st);
 }  // namespace ctgcn

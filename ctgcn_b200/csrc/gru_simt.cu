@@ -33,11 +33,11 @@ struct Tile {
 // acc[g][r][j] += Σ_k A[k][row r] · Wt[k][gate g][feature j]   for one K-range, weights streamed in chunks.
 // A: transposed tile in shared memory (As[k*RP + row]).  Wt: global, k-major [ktot][ng*hout].
 // gate g of this part is accumulated into acc[gmap[g]].
-template <int RM, int NG, int GA, int GB, int GC>
+template <int RM, int NG, int GA, int GB, int GC, int GD = 3>
 __device__ __forceinline__ void gemm_part(float (&acc)[4][RM][4], const float* __restrict__ As, int ktot,
                                           const float* __restrict__ Wt, int hout, int fb, float* __restrict__ ws) {
     constexpr int RP = Tile<RM>::RP;
-    constexpr int gmap[3] = {GA, GB, GC};
+    constexpr int gmap[4] = {GA, GB, GC, GD};
     constexpr int CHUNK = KC * NG * FBW;
     constexpr int PER_THREAD = CHUNK / THREADS;
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
@@ -190,6 +190,85 @@ __global__ void __launch_bounds__(THREADS)
     if (mode == CTGCN_GRU_SUM_LN) layer_norm_rows<RM>(os, h, ln_w, ln_b, eps, row0, n, y, yrs, sc);
 }
 
+// LSTM flavour of the same sequence kernel (layers.py:27-28 / models.py:234-235, rnn_type='LSTM'): nn.LSTM(num_layers=1,
+// batch_first=True), h_0 = c_0 = 0, PyTorch packing [i; f; g; o]:
+//   i = σ(W_ii x + b_ii + W_hi h + b_hi), f, o likewise, g = tanh(W_ig x + b_ig + W_hg h + b_hg),
+//   c' = f ⊙ c + i ⊙ g,  h' = o ⊙ tanh(c').
+// Same tiling as gru_seq_kernel; the cell state lives in shared memory next to h (each element is owned by one thread).
+template <int RM>
+__global__ void __launch_bounds__(THREADS)
+    lstm_seq_kernel(const float* __restrict__ seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h,
+                    const float* __restrict__ wt_ih, const float* __restrict__ wt_hh, const float* __restrict__ b_ih,
+                    const float* __restrict__ b_hh, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                    float eps, int mode, float* __restrict__ y, int64_t yrs, int64_t yss, const RowScatter sc) {
+    constexpr int R = Tile<RM>::R, RP = Tile<RM>::RP;
+    extern __shared__ __align__(16) float smem[];
+    const int d_pad = (d_in + KC - 1) / KC * KC, h_pad = (h + KC - 1) / KC * KC;
+    float* xs = smem;                     // [d_pad][RP]
+    float* hs = xs + d_pad * RP;          // [2][h_pad][RP]
+    float* os = hs + 2 * h_pad * RP;      // [h_pad][RP]   Σ_s h_s (SUM_LN only)
+    float* cs = os + h_pad * RP;          // [h_pad][RP]   cell state
+    float* ws = cs + h_pad * RP;          // [2][KC*4*FBW]
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int64_t row0 = blockIdx.x * (int64_t)R;
+
+    for (int i = tid; i < (d_pad + 4 * h_pad) * RP; i += THREADS) smem[i] = 0.f;
+    __syncthreads();
+
+    const int nfb = (h + FBW - 1) / FBW;
+    int cur = 0;
+    for (int s = 0; s < steps; ++s) {
+        for (int rr = ty; rr < R; rr += THREADS / 32) {
+            const int64_t row = row0 + rr;
+            const float* src = seq + row * srs + (int64_t)s * sss;
+            for (int k = tx; k < d_in; k += 32) xs[k * RP + rr] = row < n ? __ldg(src + k) : 0.f;
+        }
+        __syncthreads();
+        const float* hcur = hs + cur * h_pad * RP;
+        float* hnxt = hs + (cur ^ 1) * h_pad * RP;
+        for (int fb = 0; fb < nfb; ++fb) {
+            float acc[4][RM][4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+                for (int r = 0; r < RM; ++r)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[g][r][j] = 0.f;
+            gemm_part<RM, 4, 0, 1, 2, 3>(acc, xs, d_in, wt_ih, h, fb, ws);
+            if (s > 0) gemm_part<RM, 4, 0, 1, 2, 3>(acc, hcur, h, wt_hh, h, fb, ws);  // h_0 = 0
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int f = fb * FBW + tx + 32 * j;
+                if (f < h) {
+                    float bg[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        bg[g] = (b_ih ? __ldg(b_ih + g * h + f) : 0.f) + (b_hh ? __ldg(b_hh + g * h + f) : 0.f);
+#pragma unroll
+                    for (int r = 0; r < RM; ++r) {
+                        const int row = ty * RM + r;
+                        const float ig = sigmoid_f(acc[0][r][j] + bg[0]);
+                        const float fg = sigmoid_f(acc[1][r][j] + bg[1]);
+                        const float gg = tanhf(acc[2][r][j] + bg[2]);
+                        const float og = sigmoid_f(acc[3][r][j] + bg[3]);
+                        const float cnew = fg * cs[f * RP + row] + ig * gg;
+                        cs[f * RP + row] = cnew;
+                        const float hnew = og * tanhf(cnew);
+                        hnxt[f * RP + row] = hnew;
+                        if (mode == CTGCN_GRU_SUM_LN) os[f * RP + row] += hnew;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (mode == CTGCN_GRU_EACH_LN) {
+            layer_norm_rows<RM>(hnxt, h, ln_w, ln_b, eps, row0, n, y + (int64_t)s * yss, yrs, RowScatter());
+        }
+        cur ^= 1;
+    }
+    if (mode == CTGCN_GRU_SUM_LN) layer_norm_rows<RM>(os, h, ln_w, ln_b, eps, row0, n, y, yrs, sc);
+}
+
 // y[n, d_out] = act(x · Wᵀ + b);  wt is k-major [d_in][d_out].  CTA: 64 rows × 128 features, k chunks of 16.
 constexpr int LKC = 16;
 __global__ void __launch_bounds__(THREADS)
@@ -292,7 +371,38 @@ int launch_gru_t(const float* seq, int64_t srs, int64_t sss, int64_t n, int step
     return CTGCN_OK;
 }
 
+template <int RM>
+size_t lstm_smem_bytes(int d_in, int h) {
+    const int d_pad = (d_in + KC - 1) / KC * KC, h_pad = (h + KC - 1) / KC * KC;
+    return ((size_t)(d_pad + 4 * h_pad) * Tile<RM>::RP + 2 * KC * 4 * FBW) * sizeof(float);
+}
+
+template <int RM>
+int launch_lstm_t(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* wt_ih,
+                  const float* wt_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
+                  int mode, float* y, int64_t yrs, int64_t yss, const RowScatter& sc, cudaStream_t st) {
+    const size_t smem = lstm_smem_bytes<RM>(d_in, h);
+    CTGCN_CUDA_OK(cudaFuncSetAttribute(lstm_seq_kernel<RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned blocks = (unsigned)((n + Tile<RM>::R - 1) / Tile<RM>::R);
+    lstm_seq_kernel<RM><<<blocks, THREADS, smem, st>>>(seq, srs, sss, n, steps, d_in, h, wt_ih, wt_hh, b_ih, b_hh, ln_w, ln_b,
+                                                       eps, mode, y, yrs, yss, sc);
+    CTGCN_LAUNCH_OK("lstm_seq_kernel");
+    return CTGCN_OK;
+}
+
 }  // namespace
+
+int launch_lstm_simt(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* wt_ih,
+                     const float* wt_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
+                     int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* scp, cudaStream_t st) {
+    constexpr size_t kMaxSmem = 227 * 1024;
+    const RowScatter sc = scp ? *scp : RowScatter();
+    ProfScope prof(PROF_GRU, st);
+    if (lstm_smem_bytes<8>(d_in, h) <= kMaxSmem)
+        return launch_lstm_t<8>(seq, srs, sss, n, steps, d_in, h, wt_ih, wt_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, sc, st);
+    CTGCN_REQUIRE(lstm_smem_bytes<4>(d_in, h) <= kMaxSmem, "lstm: d_in=%d, h=%d needs more than 227 KB of shared memory", d_in, h);
+    return launch_lstm_t<4>(seq, srs, sss, n, steps, d_in, h, wt_ih, wt_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, sc, st);
+}
 
 int launch_gru_simt(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* wt_ih,
                     const float* wt_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,

@@ -226,6 +226,64 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
     }
 }
 
+// ---- backward of the cumulative SpMM w.r.t. x.
+// S_i = Σ_{j≤i} A_j x  ⇒  dx = Σ_j A_jᵀ Zo_j with Zo_j = Σ_{i≥j} g_i (g_i = dL/dS_i).  Over the union CSR of the TRANSPOSED
+// list a nested entry of level ℓ (present in A_j for every j ≥ ℓ) contributes w·Σ_{j≥ℓ} Zo_j = w·Zn_ℓ, a one-shot entry w·Zo_ℓ:
+//   dx[row] = Σ_e w_e · (one-shot ? Zo : Zn)[col_e, level_e, :]        — one gathered row per stored entry.
+__global__ void suffix_sums_kernel(const float* __restrict__ g, int64_t n, int k, int d, float* __restrict__ zo,
+                                   float* __restrict__ zn) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= n * d) return;
+    const int64_t r = idx / d, f = idx % d;
+    const int64_t base = r * (int64_t)k * d + f;
+    float a = 0.f, b = 0.f;
+    for (int i = k - 1; i >= 0; --i) {
+        a += g[base + (int64_t)i * d];
+        b += a;
+        zo[base + (int64_t)i * d] = a;
+        zn[base + (int64_t)i * d] = b;
+    }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+    levelgather_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+                       const uint8_t* __restrict__ lvl, const float* __restrict__ zo, const float* __restrict__ zn, int d, int k,
+                       int64_t n_rows, float* __restrict__ dx, int64_t lddx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = blockIdx.x * (int64_t)WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int start = rowptr[row], end = rowptr[row + 1];
+    for (int f0 = 0; f0 < d; f0 += 128) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int base = start; base < end; base += 32) {
+            const int cnt = min(32, end - base);
+            int c = 0, l = 0;
+            float w = 0.f;
+            if (lane < cnt) {
+                c = __ldg(col + base + lane);
+                w = __ldg(val + base + lane);
+                l = __ldg(lvl + base + lane);
+            }
+            for (int q = 0; q < cnt; ++q) {
+                const int cj = __shfl_sync(0xffffffffu, c, q);
+                const float wj = __shfl_sync(0xffffffffu, w, q);
+                const int lj = __shfl_sync(0xffffffffu, l, q);
+                const float* src = ((lj & 128) ? zo : zn) + ((int64_t)cj * k + (lj & 127)) * d + f0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int e = lane + 32 * j;
+                    if (f0 + e < d) acc[j] = fmaf(wj, __ldg(src + e), acc[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = f0 + lane + 32 * j;
+            if (e < d) dx[row * lddx + e] = acc[j];
+        }
+    }
+}
+
 __global__ void transpose_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, float* __restrict__ dst) {
     __shared__ float tile[32][33];
     const int64_t c0 = blockIdx.x * 32ll, r0 = blockIdx.y * 32ll;
@@ -286,6 +344,22 @@ int launch_cumspmm(const ctgcn_plan* p, const float* x, int64_t ldx, int d, floa
     if (d <= 256) return launch_scalar<8>(p, x, ldx, d, u, relu, st);
     if (d <= 512) return launch_scalar<16>(p, x, ldx, d, u, relu, st);
     return launch_scalar<32>(p, x, ldx, d, u, relu, st);
+}
+
+int launch_cumspmm_bwd(const ctgcn_plan* pt, const float* g, int d, float* zo, float* zn, float* dx, int64_t lddx,
+                       cudaStream_t st) {
+    CTGCN_REQUIRE(d >= 1 && d <= 1024, "cumspmm_bwd: feature width %d outside [1,1024]", d);
+    ProfScope prof(PROF_SPMM, st);
+    const int64_t total = pt->n_cols * (int64_t)d;
+    if (total > 0) {
+        suffix_sums_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, pt->n_cols, pt->k, d, zo, zn);
+        CTGCN_LAUNCH_OK("suffix_sums_kernel");
+    }
+    const unsigned blocks = (unsigned)((pt->n_rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    levelgather_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(pt->rowptr, pt->col, pt->val, pt->lvl, zo, zn, d, pt->k,
+                                                               pt->n_rows, dx, lddx);
+    CTGCN_LAUNCH_OK("levelgather_kernel");
+    return CTGCN_OK;
 }
 
 int launch_spmm_linear(const ctgcn_plan* p, const float* wt, const float* b, int64_t d_out, int act, float* y, int64_t ldy,

@@ -184,30 +184,29 @@ def ctgcn_forward_sharded(model, x_list, adj_list):
     mode = getattr(model, "exchange", "auto")
     if mode == "auto":
         mode = "p2p" if _p2p_available(dev) else "all_to_all"
-    if mode == "p2p":
-        seq, n, trans_list = _forward_p2p(model, x_list, adj_list, owned, T, dev)
+    # The sharded forward is inference-only (the exchange has no backward yet): compute without autograd and mark the result
+    # so that .backward() fails loudly instead of producing zero gradients.
+    with torch.no_grad():
+        if mode == "p2p":
+            seq, n, trans_list = _forward_p2p(model, x_list, adj_list, owned, T, dev)
+        else:
+            trans_list = [None] * T
+            hx_local, n = None, None
+            stager = _HostFeatureStager(x_list, owned, dev)
+            for j, t in enumerate(owned):
+                trans = model.mlp_list[t](stager.get(t))
+                trans_list[t] = trans
+                if hx_local is None:
+                    n = trans.shape[0]
+                    hx_local = torch.zeros(n, tl, model.output_dim, dtype=torch.float32, device=dev)
+                model.duffision_list[t].forward_into(trans, adj_list[t], out=hx_local[:, j, :])
+            if hx_local is None:  # more ranks than snapshots: this rank owns nothing but still takes part
+                n = int(getattr(model, "node_num", 0)) or _infer_rows(x_list, adj_list)
+                hx_local = torch.zeros(n, tl, model.output_dim, dtype=torch.float32, device=dev)
+            seq = exchange_to_node_slices(hx_local, T, mode=mode)
         out = model._temporal(seq)
         if getattr(model, "gather_output", True):
             out = gather_node_slices(out, n)
-        out = _guard(out, model).transpose(0, 1)
-        return out if model.model_type == 'C' else (out, trans_list)
-    trans_list = [None] * T
-    hx_local, n = None, None
-    stager = _HostFeatureStager(x_list, owned, dev)
-    for j, t in enumerate(owned):
-        trans = model.mlp_list[t](stager.get(t))
-        trans_list[t] = trans
-        if hx_local is None:
-            n = trans.shape[0]
-            hx_local = torch.zeros(n, tl, model.output_dim, dtype=torch.float32, device=dev)
-        model.duffision_list[t].forward_into(trans, adj_list[t], out=hx_local[:, j, :])
-    if hx_local is None:  # more ranks than snapshots: this rank owns nothing but still takes part
-        n = int(getattr(model, "node_num", 0)) or _infer_rows(x_list, adj_list)
-        hx_local = torch.zeros(n, tl, model.output_dim, dtype=torch.float32, device=dev)
-    seq = exchange_to_node_slices(hx_local, T, mode=mode)
-    out = model._temporal(seq)
-    if getattr(model, "gather_output", True):
-        out = gather_node_slices(out, n)
     out = _guard(out, model).transpose(0, 1)
     return out if model.model_type == 'C' else (out, trans_list)
 

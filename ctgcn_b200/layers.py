@@ -2,9 +2,9 @@
 signatures and ``state_dict`` keys (reference layers.py:9-63, 67-106), computing on sm_100a through
 libctgcn_b200.so.  There is no torch fallback: tensors must live on a CUDA device.
 
-Forward only (SURVEY.md §8f row N2 = autograd): the outputs carry a grad_fn whose backward raises, so
-inference / embedding export work in any grad mode and training fails loudly instead of silently
-producing zero gradients.
+Training: when gradients are required the layers go through the autograd Functions of
+ctgcn_b200/autograd.py (fused forward kernels, recomputing backward); under ``torch.no_grad()`` they write
+straight into caller-provided buffers.  ``rnn_type='LSTM'`` (layers.py:27-28) runs on the fp32 sequence kernel.
 """
 from __future__ import annotations
 
@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
+from . import autograd as _ag
 from .plan import GraphPlan, plan_for
 
 
@@ -24,7 +25,7 @@ class _ForwardOnly(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        raise NotImplementedError("ctgcn_b200 implements the forward hot path only (backward = SURVEY §8f N2)")
+        raise NotImplementedError("ctgcn_b200: backward through the snapshot-parallel (multi-GPU) forward is not implemented")
 
 
 def _guard(out, module, *inputs):
@@ -47,14 +48,14 @@ class CoreDiffusion(nn.Module):
         super().__init__()
         if rnn_type not in ('LSTM', 'GRU'):
             raise AssertionError("rnn_type must be 'LSTM' or 'GRU'")
-        if rnn_type == 'LSTM':
-            raise NotImplementedError("ctgcn_b200: rnn_type='LSTM' is not implemented (no shipped config uses it)")
         self.input_dim, self.output_dim = input_dim, output_dim
         self.bias, self.core_num, self.rnn_type = bias, core_num, rnn_type
         # same construction order as the reference → identical default initialisation under one seed
         self.linear = nn.Linear(input_dim, output_dim)
-        self.rnn = nn.GRU(input_size=input_dim, hidden_size=output_dim, num_layers=1, bias=bias, batch_first=True)
+        rnn_cls = nn.LSTM if rnn_type == 'LSTM' else nn.GRU
+        self.rnn = rnn_cls(input_size=input_dim, hidden_size=output_dim, num_layers=1, bias=bias, batch_first=True)
         self.norm = nn.LayerNorm(output_dim)
+        self._cell = _lib.CELLS[rnn_type]
 
     def _gru_params(self):
         r = self.rnn
@@ -63,16 +64,20 @@ class CoreDiffusion(nn.Module):
 
     def forward_into(self, x, adj_list, out=None, scatter=None):
         """forward() writing into `out` ([N, H] view, any row stride) or — `scatter` = (slice_ptrs, row_stride,
-        col_offset) — straight into the node slices' (peer) buffers; then nothing is returned."""
+        col_offset) — straight into the node slices' (peer) buffers; then nothing is returned.  Both are
+        inference-only fast paths: when gradients are required (grad mode on and an input / parameter requires grad)
+        the result is a fresh tensor with a grad_fn and `out` is NOT written — callers check ``requires_grad``."""
         plan = plan_for(adj_list, x.device)
         w_ih, w_hh, b_ih, b_hh = self._gru_params()
         if scatter is not None:
             ops.core_diffusion_scatter(plan, x.detach(), w_ih, w_hh, b_ih, b_hh, self.norm.weight, self.norm.bias, self.norm.eps,
-                                       *scatter)
+                                       *scatter, cell=self._cell)
             return None
-        y = ops.core_diffusion(plan, x.detach(), w_ih, w_hh, b_ih, b_hh, self.norm.weight, self.norm.bias, self.norm.eps,
-                               out=out)
-        return _guard(y, self, x)
+        if _ag.needs_grad(x, w_ih, w_hh, b_ih, b_hh, self.norm.weight, self.norm.bias):
+            return _ag.CoreDiffusionFn.apply(x, plan, self._cell, self.norm.eps, w_ih, w_hh, b_ih, b_hh, self.norm.weight,
+                                             self.norm.bias)          # `out` is left untouched: the caller checks requires_grad
+        return ops.core_diffusion(plan, x.detach(), w_ih, w_hh, b_ih, b_hh, self.norm.weight, self.norm.bias, self.norm.eps,
+                                  out=out, cell=self._cell)
 
     def forward(self, x, adj_list):
         return self.forward_into(x, adj_list)
@@ -109,7 +114,12 @@ class MLP(nn.Module):
         for j, lin in enumerate(self._layers()):
             if j == 0 and (isinstance(h, GraphPlan) or (isinstance(h, torch.Tensor) and h.layout == torch.sparse_coo)):
                 plan = plan_for(h, lin.weight.device)
-                h = ops.spmm_linear(plan, lin.weight, lin.bias, act)
+                if _ag.needs_grad(lin.weight, lin.bias):
+                    h = _ag.SparseLinearFn.apply(lin.weight, lin.bias, plan, act)
+                else:
+                    h = ops.spmm_linear(plan, lin.weight, lin.bias, act)
+            elif _ag.needs_grad(h, lin.weight, lin.bias):
+                h = _ag.LinearFn.apply(h, lin.weight, lin.bias, act)
             else:
                 h = ops.linear(h.detach(), lin.weight, lin.bias, act)
-        return _guard(h, self, x if isinstance(x, torch.Tensor) and x.layout == torch.strided else None)
+        return h

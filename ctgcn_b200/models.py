@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
+from . import autograd as _ag
 from .layers import CoreDiffusion, MLP, _guard
 from . import dist as _dist
 
@@ -135,8 +136,6 @@ class CTGCN(nn.Module):
             raise AssertionError("trans_activate_type must be 'L' or 'N'")
         if rnn_type not in ('LSTM', 'GRU'):
             raise AssertionError("rnn_type must be 'LSTM' or 'GRU'")
-        if rnn_type == 'LSTM':
-            raise NotImplementedError("ctgcn_b200: rnn_type='LSTM' is not implemented (no shipped config uses it)")
         self.input_dim, self.hidden_dim, self.output_dim = input_dim, hidden_dim, output_dim
         self.rnn_type, self.model_type, self.trans_activate_type = rnn_type, model_type, trans_activate_type
         self.method_name = 'CTGCN' + '-' + model_type
@@ -147,8 +146,10 @@ class CTGCN(nn.Module):
         for _ in range(duration):  # interleaved like the reference → same default initialisation under one seed
             self.mlp_list.append(MLP(input_dim, hidden_dim, mid, trans_num, bias=bias, activate_type=trans_activate_type))
             self.duffision_list.append(CDN(mid, output_dim, output_dim, diffusion_num, rnn_type=rnn_type))
-        self.rnn = nn.GRU(output_dim, output_dim, num_layers=1, bias=bias, batch_first=True)
+        rnn_cls = nn.LSTM if rnn_type == 'LSTM' else nn.GRU
+        self.rnn = rnn_cls(output_dim, output_dim, num_layers=1, bias=bias, batch_first=True)
         self.norm = nn.LayerNorm(output_dim)
+        self._cell = _lib.CELLS[rnn_type]
         # snapshot-parallel options (only read when torch.distributed is initialised with world size > 1)
         self.gather_output = True
 
@@ -156,21 +157,26 @@ class CTGCN(nn.Module):
         r = self.rnn
         b_ih = r.bias_ih_l0 if self.bias else None
         b_hh = r.bias_hh_l0 if self.bias else None
-        return ops.gru_seq(hx, r.weight_ih_l0, r.weight_hh_l0, b_ih, b_hh, self.norm.weight, self.norm.bias, self.norm.eps,
-                           _lib.GRU_EACH_LN, out=out)
+        if _ag.needs_grad(hx, r.weight_ih_l0, r.weight_hh_l0, b_ih, b_hh, self.norm.weight, self.norm.bias):
+            return _ag.RnnSeqFn.apply(hx, self._cell, self.norm.eps, r.weight_ih_l0, r.weight_hh_l0, b_ih, b_hh,
+                                      self.norm.weight, self.norm.bias)
+        return ops.rnn_seq(hx, r.weight_ih_l0, r.weight_hh_l0, b_ih, b_hh, self.norm.weight, self.norm.bias, self.norm.eps,
+                           _lib.GRU_EACH_LN, out=out, cell=self._cell)
 
     def forward(self, x_list, adj_list):
         if _dist.world_size() > 1:
             return _dist.ctgcn_forward_sharded(self, x_list, adj_list)
         T = len(x_list)
         dev = self.norm.weight.device
-        hx, trans_list = None, []
+        hx, trans_list, emb_list = None, [], []
         stager = _HostFeatureStager(x_list, range(T), dev)
         for t in range(T):
             trans = self.mlp_list[t](stager.get(t))
             trans_list.append(trans)
             if hx is None:
                 hx = torch.empty(trans.shape[0], T, self.output_dim, dtype=torch.float32, device=dev)
-            self.duffision_list[t].forward_into(trans, adj_list[t], out=hx[:, t, :])
-        out = _guard(self._temporal(hx), self).transpose(0, 1)
+            emb_list.append(self.duffision_list[t].forward_into(trans, adj_list[t], out=hx[:, t, :]))
+        if any(e.requires_grad for e in emb_list):
+            hx = torch.stack(emb_list, dim=1)          # training: the autograd-visible [N, T, D] (models.py:248)
+        out = self._temporal(hx).transpose(0, 1)
         return out if self.model_type == 'C' else (out, trans_list)

@@ -44,94 +44,113 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
-def cumspmm(plan: GraphPlan, x: torch.Tensor) -> torch.Tensor:
-    """relu(cumsum_i A_i x) for all K cores → [N, K, D]  (layers.py:41-48)."""
+def cumspmm(plan: GraphPlan, x: torch.Tensor, relu: bool = True) -> torch.Tensor:
+    """relu(cumsum_i A_i x) for all K cores → [N, K, D]  (layers.py:41-48); relu=False returns the sums themselves."""
     x = _f32_rows(x, "x")
     if x.shape[0] != plan.n_cols:
         raise _lib.CtgcnError(f"x has {x.shape[0]} rows, the plan expects {plan.n_cols}")
     u = torch.empty(plan.n_rows, plan.k, x.shape[1], dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib.ctgcn_cumspmm_fwd(plan.handle, _ptr(x), x.stride(0), x.shape[1], _ptr(u), _stream()),
-                   "ctgcn_cumspmm_fwd")
+        _lib.check(_lib.lib.ctgcn_cumspmm_fwd_ex(plan.handle, _ptr(x), x.stride(0), x.shape[1], 1 if relu else 0, _ptr(u),
+                                                 _stream()), "ctgcn_cumspmm_fwd_ex")
     return u
 
 
-def gru_seq(seq: torch.Tensor, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps: float, mode: int, out: torch.Tensor = None):
-    """GRU over dim 1 of seq [N, L, D_in] (any row/step strides) + LayerNorm.
+def cumspmm_bwd(plan_t: GraphPlan, g: torch.Tensor) -> torch.Tensor:
+    """dL/dx of the cumulative SpMM: g [M, K, D] = dL/dS_i (relu mask applied) → [N, D], over the plan of the transposed list."""
+    if g.dim() != 3 or not g.is_cuda or g.dtype != torch.float32:
+        raise _lib.CtgcnError("g must be a 3-D fp32 CUDA tensor [rows, K, D] (ctgcn_b200 has no CPU path)")
+    g = g.contiguous()
+    if g.shape[0] != plan_t.n_cols or g.shape[1] != plan_t.k:
+        raise _lib.CtgcnError(f"g has shape {tuple(g.shape)}, the transposed plan expects [{plan_t.n_cols}, {plan_t.k}, D]")
+    d = g.shape[2]
+    dx = torch.empty(plan_t.n_rows, d, dtype=torch.float32, device=g.device)
+    ws_bytes = _lib.lib.ctgcn_cumspmm_bwd_workspace_bytes(plan_t.handle, d)
+    ws = _workspace(ws_bytes, g.device)
+    with torch.cuda.device(g.device):
+        _lib.check(_lib.lib.ctgcn_cumspmm_bwd(plan_t.handle, _ptr(g), d, _ptr(dx), dx.stride(0), _ptr(ws), ws_bytes, _stream()),
+                   "ctgcn_cumspmm_bwd")
+    return dx
+
+
+def _rnn_weights(w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, cell, d_in):
+    h = w_hh.shape[1]
+    g = 4 if cell == _lib.CELL_LSTM else 3
+    w_ih, w_hh, b_ih, b_hh, ln_w, ln_b = (_vec(t, nm) for t, nm in
+                                           ((w_ih, "w_ih"), (w_hh, "w_hh"), (b_ih, "b_ih"), (b_hh, "b_hh"),
+                                            (ln_w, "ln_w"), (ln_b, "ln_b")))
+    if tuple(w_ih.shape) != (g * h, d_in) or tuple(w_hh.shape) != (g * h, h):
+        raise _lib.CtgcnError(f"recurrent weight shapes {tuple(w_ih.shape)}, {tuple(w_hh.shape)} do not match "
+                              f"d_in={d_in}, h={h}, gates={g}")
+    return h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b
+
+
+def rnn_seq(seq: torch.Tensor, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps: float, mode: int, out: torch.Tensor = None,
+            cell: int = _lib.CELL_GRU):
+    """GRU / LSTM over dim 1 of seq [N, L, D_in] (any row/step strides) + LayerNorm.
 
     mode GRU_SUM_LN → [N, H] = LN(Σ_s h_s); GRU_EACH_LN → [N, L, H] = LN(h_s).
     """
     if seq.dim() != 3 or not seq.is_cuda or seq.dtype != torch.float32 or seq.stride(2) != 1:
         raise _lib.CtgcnError("seq must be a 3-D fp32 CUDA tensor with a contiguous last dim")
     n, steps, d_in = seq.shape
-    h = w_hh.shape[1]
-    w_ih, w_hh, b_ih, b_hh, ln_w, ln_b = (_vec(t, nm) for t, nm in
-                                           ((w_ih, "w_ih"), (w_hh, "w_hh"), (b_ih, "b_ih"), (b_hh, "b_hh"),
-                                            (ln_w, "ln_w"), (ln_b, "ln_b")))
-    if tuple(w_ih.shape) != (3 * h, d_in) or tuple(w_hh.shape) != (3 * h, h):
-        raise _lib.CtgcnError(f"GRU weight shapes {tuple(w_ih.shape)}, {tuple(w_hh.shape)} do not match d_in={d_in}, h={h}")
+    h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b = _rnn_weights(w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, cell, d_in)
     if out is None:
         out = torch.empty((n, h) if mode == _lib.GRU_SUM_LN else (n, steps, h), dtype=torch.float32, device=seq.device)
     yrs = out.stride(0)
     yss = out.stride(1) if mode == _lib.GRU_EACH_LN else 0
     if out.stride(-1) != 1:
         raise _lib.CtgcnError("out must have a contiguous last dim")
-    ws_bytes = _lib.lib.ctgcn_gru_workspace_bytes(d_in, h)
+    ws_bytes = _lib.lib.ctgcn_rnn_workspace_bytes(cell, d_in, h)
     ws = _workspace(ws_bytes, seq.device)
     with torch.cuda.device(seq.device):
-        _lib.check(_lib.lib.ctgcn_gru_seq_fwd(_ptr(seq), seq.stride(0), seq.stride(1), n, steps, d_in, h, _ptr(w_ih),
+        _lib.check(_lib.lib.ctgcn_rnn_seq_fwd(cell, _ptr(seq), seq.stride(0), seq.stride(1), n, steps, d_in, h, _ptr(w_ih),
                                               _ptr(w_hh), _ptr(b_ih), _ptr(b_hh), _ptr(ln_w), _ptr(ln_b), float(eps), mode,
-                                              _ptr(out), yrs, yss, _ptr(ws), ws_bytes, _stream()), "ctgcn_gru_seq_fwd")
+                                              _ptr(out), yrs, yss, _ptr(ws), ws_bytes, _stream()), "ctgcn_rnn_seq_fwd")
     return out
 
 
-def core_diffusion(plan: GraphPlan, x, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps: float, out: torch.Tensor = None):
-    """layers.CoreDiffusion.forward on one plan → [N, H] (written into `out`, any row stride, if given)."""
+def gru_seq(seq, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps: float, mode: int, out: torch.Tensor = None):
+    return rnn_seq(seq, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, out=out, cell=_lib.CELL_GRU)
+
+
+def core_diffusion(plan: GraphPlan, x, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps: float, out: torch.Tensor = None,
+                   cell: int = _lib.CELL_GRU, scatter=None):
+    """layers.CoreDiffusion.forward on one plan → [N, H] (written into `out`, any row stride, if given).
+
+    scatter = (slice_ptrs int64 CUDA tensor of (peer-mapped) base pointers, slice_row_stride, slice_col_offset): the result
+    rows are stored straight into the node slices' buffers instead (nothing is returned)."""
     x = _f32_rows(x, "x")
     d_in = x.shape[1]
-    h = w_hh.shape[1]
     if x.shape[0] != plan.n_cols:
         raise _lib.CtgcnError(f"x has {x.shape[0]} rows, the plan expects {plan.n_cols}")
-    w_ih, w_hh, b_ih, b_hh, ln_w, ln_b = (_vec(t, nm) for t, nm in
-                                           ((w_ih, "w_ih"), (w_hh, "w_hh"), (b_ih, "b_ih"), (b_hh, "b_hh"),
-                                            (ln_w, "ln_w"), (ln_b, "ln_b")))
-    if tuple(w_ih.shape) != (3 * h, d_in):
-        raise _lib.CtgcnError(f"w_ih shape {tuple(w_ih.shape)} does not match input width {d_in} / hidden {h}")
-    if out is None:
-        out = torch.empty(plan.n_rows, h, dtype=torch.float32, device=x.device)
-    if out.stride(1) != 1 or tuple(out.shape) != (plan.n_rows, h):
-        raise _lib.CtgcnError("out must be [N, H] with a contiguous last dim")
-    ws_bytes = _lib.lib.ctgcn_core_diffusion_workspace_bytes(plan.handle, d_in, h)
+    h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b = _rnn_weights(w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, cell, d_in)
+    ws_bytes = _lib.lib.ctgcn_core_diffusion_rnn_workspace_bytes(plan.handle, cell, d_in, h)
     ws = _workspace(ws_bytes, x.device)
+    if scatter is not None:
+        slice_ptrs, slice_row_stride, slice_col_offset = scatter
+        if slice_ptrs.dtype != torch.int64 or not slice_ptrs.is_cuda:
+            raise _lib.CtgcnError("slice_ptrs must be an int64 CUDA tensor of device pointers")
+        y_ptr, ldy, sl = _vp(0), 0, (_ptr(slice_ptrs), slice_ptrs.numel(), int(slice_row_stride), int(slice_col_offset))
+    else:
+        if out is None:
+            out = torch.empty(plan.n_rows, h, dtype=torch.float32, device=x.device)
+        if out.stride(1) != 1 or tuple(out.shape) != (plan.n_rows, h):
+            raise _lib.CtgcnError("out must be [N, H] with a contiguous last dim")
+        y_ptr, ldy, sl = _ptr(out), out.stride(0), (_vp(0), 0, 0, 0)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib.ctgcn_core_diffusion_fwd(plan.handle, _ptr(x), x.stride(0), d_in, h, _ptr(w_ih), _ptr(w_hh),
-                                                     _ptr(b_ih), _ptr(b_hh), _ptr(ln_w), _ptr(ln_b), float(eps), _ptr(out),
-                                                     out.stride(0), _ptr(ws), ws_bytes, _stream()),
-                   "ctgcn_core_diffusion_fwd")
-    return out
+        _lib.check(_lib.lib.ctgcn_core_diffusion_rnn_fwd(plan.handle, cell, _ptr(x), x.stride(0), d_in, h, _ptr(w_ih), _ptr(w_hh),
+                                                         _ptr(b_ih), _ptr(b_hh), _ptr(ln_w), _ptr(ln_b), float(eps), y_ptr, ldy,
+                                                         *sl, _ptr(ws), ws_bytes, _stream()),
+                   "ctgcn_core_diffusion_rnn_fwd")
+    return out if scatter is None else None
 
 
 def core_diffusion_scatter(plan: GraphPlan, x, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps: float, slice_ptrs: torch.Tensor,
-                           slice_row_stride: int, slice_col_offset: int):
-    """CoreDiffusion.forward whose [N, H] result is scattered row-wise into the node slices' buffers
-    (ctgcn_core_diffusion_fwd_scatter).  slice_ptrs: int64 CUDA tensor of (peer-mapped) base pointers."""
-    x = _f32_rows(x, "x")
-    d_in = x.shape[1]
-    h = w_hh.shape[1]
-    if x.shape[0] != plan.n_cols:
-        raise _lib.CtgcnError(f"x has {x.shape[0]} rows, the plan expects {plan.n_cols}")
-    if slice_ptrs.dtype != torch.int64 or not slice_ptrs.is_cuda:
-        raise _lib.CtgcnError("slice_ptrs must be an int64 CUDA tensor of device pointers")
-    w_ih, w_hh, b_ih, b_hh, ln_w, ln_b = (_vec(t, nm) for t, nm in
-                                           ((w_ih, "w_ih"), (w_hh, "w_hh"), (b_ih, "b_ih"), (b_hh, "b_hh"),
-                                            (ln_w, "ln_w"), (ln_b, "ln_b")))
-    ws_bytes = _lib.lib.ctgcn_core_diffusion_workspace_bytes(plan.handle, d_in, h)
-    ws = _workspace(ws_bytes, x.device)
-    with torch.cuda.device(x.device):
-        _lib.check(_lib.lib.ctgcn_core_diffusion_fwd_scatter(
-            plan.handle, _ptr(x), x.stride(0), d_in, h, _ptr(w_ih), _ptr(w_hh), _ptr(b_ih), _ptr(b_hh), _ptr(ln_w), _ptr(ln_b),
-            float(eps), _ptr(slice_ptrs), slice_ptrs.numel(), int(slice_row_stride), int(slice_col_offset), _ptr(ws), ws_bytes,
-            _stream()), "ctgcn_core_diffusion_fwd_scatter")
+                           slice_row_stride: int, slice_col_offset: int, cell: int = _lib.CELL_GRU):
+    """CoreDiffusion.forward whose [N, H] result is scattered row-wise into the node slices' buffers."""
+    return core_diffusion(plan, x, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, cell=cell,
+                          scatter=(slice_ptrs, slice_row_stride, slice_col_offset))
 
 
 def linear(x, w, b, act: int):

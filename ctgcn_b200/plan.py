@@ -46,6 +46,15 @@ class GraphPlan:
         except Exception:
             pass
 
+    def transposed(self) -> "GraphPlan":
+        """Plan of the transposed list [A_0ᵀ … A_{K-1}ᵀ] (built once, on first use: the backward pass gathers over it)."""
+        if getattr(self, "_t", None) is None:
+            rowptr, col, val, lvl = self.arrays()
+            self._t = build_plan_csr(self.n_cols, self.n_rows, self.k, *transpose_csr(self.n_rows, self.n_cols, rowptr, col, val, lvl),
+                                     self.nnz_raw_sum, self.device)
+            self._t._t = self
+        return self._t
+
     def arrays(self):
         """Copies of (rowptr, col, val, level) as torch tensors (tests / inspection only)."""
         out = [torch.empty(cnt, dtype=dt, device=self.device)
@@ -56,6 +65,19 @@ class GraphPlan:
             _lib.check(_lib.lib.ctgcn_plan_arrays(self.handle, *[C.c_void_p(t.data_ptr()) for t in out],
                                                   C.c_void_p(stream)), "ctgcn_plan_arrays")
         return out
+
+
+def transpose_csr(n_rows, n_cols, rowptr, col, val, lvl):
+    """Level-tagged union CSR of the transposed matrices: entry (r, c, w, level) → (c, r, w, level), rows sorted by level.
+    torch tensors in, torch tensors out (any device): a nested entry of A_i, i ≥ ℓ is a nested entry of A_iᵀ, i ≥ ℓ."""
+    counts = (rowptr[1:] - rowptr[:-1]).to(torch.int64)
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=rowptr.device, dtype=torch.int64), counts)
+    c64 = col.to(torch.int64)
+    key = c64 * 128 + (lvl & 127).to(torch.int64)
+    order = torch.argsort(key, stable=True)
+    t_rowptr = torch.zeros(n_cols + 1, dtype=torch.int64, device=rowptr.device)
+    t_rowptr[1:] = torch.cumsum(torch.bincount(c64, minlength=n_cols), 0)
+    return t_rowptr.to(torch.int32), rows[order].to(torch.int32), val[order], lvl[order]
 
 
 def _coo_parts(m, device):

@@ -47,6 +47,10 @@ extern "C" {
 #define CTGCN_IMPL_SIMT 1
 #define CTGCN_IMPL_TCGEN05 2
 
+/* recurrent cell of the sequence kernels: the reference's rnn_type (layers.py:26-30, models.py:232-237) */
+#define CTGCN_CELL_GRU 0
+#define CTGCN_CELL_LSTM 1
+
 typedef struct ctgcn_plan ctgcn_plan;
 
 int ctgcn_version(void);
@@ -99,6 +103,18 @@ int ctgcn_plan_arrays(const ctgcn_plan* plan, int32_t* rowptr, int32_t* col, flo
  * union CSR.  x: [n_cols, d] with row stride ldx (elements); u: [n_rows, K, d] contiguous. */
 int ctgcn_cumspmm_fwd(const ctgcn_plan* plan, const float* x, int64_t ldx, int d, float* u, void* stream);
 
+/* Same pass with the relu switchable: relu = 0 returns the cumulative sums S_i themselves (with a K = 1 plan: the plain
+ * SpMM A·x, used for the weight gradient of a sparse-input Linear, layers.py:97 with a COO x). */
+int ctgcn_cumspmm_fwd_ex(const ctgcn_plan* plan, const float* x, int64_t ldx, int d, int relu, float* u, void* stream);
+
+/* Backward of the cumulative SpMM w.r.t. x (the autograd of layers.py:41-47).
+ * plan_t: plan of the TRANSPOSED list [A_0^T … A_{K-1}^T] (shape n x m; the k-core adjacencies are symmetric, but the module
+ *         API does not promise it).  g: [m, K, d] contiguous = dL/dS_i (the caller has applied the relu mask).
+ * dx[n, d] (row stride lddx) = sum_j A_j^T (sum_{i>=j} g_i).  workspace: ctgcn_cumspmm_bwd_workspace_bytes(plan_t, d). */
+size_t ctgcn_cumspmm_bwd_workspace_bytes(const ctgcn_plan* plan_t, int d);
+int ctgcn_cumspmm_bwd(const ctgcn_plan* plan_t, const float* g, int d, float* dx, int64_t lddx, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- GRU over a short sequence + LayerNorm
  * layers.py:59-62 (sequence = core axis, mode SUM_LN) and models.py:249-250 (sequence = snapshot axis,
  * mode EACH_LN).  nn.GRU(num_layers=1, batch_first=True), h0 = 0, PyTorch packing [r;z;n]:
@@ -122,6 +138,15 @@ int ctgcn_debug_gru_trace(int64_t* device_buf);
 int ctgcn_selftest_umma(const float* x, const float* h, const float* w_ih, const float* w_hh, float* out, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* rnn_type-generic form of the two functions above (cell = CTGCN_CELL_GRU: identical to ctgcn_gru_seq_fwd).
+ * CTGCN_CELL_LSTM: nn.LSTM(num_layers=1, batch_first=True), h0 = c0 = 0, PyTorch packing [i;f;g;o]:
+ *   w_ih [4H, d_in], w_hh [4H, H], b_ih/b_hh [4H] or NULL; only the output sequence h_s is used (layers.py:59, models.py:249). */
+size_t ctgcn_rnn_workspace_bytes(int cell, int d_in, int h);
+int ctgcn_rnn_seq_fwd(int cell, const float* seq, int64_t seq_row_stride, int64_t seq_step_stride, int64_t n, int steps,
+                      int d_in, int h, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                      const float* ln_w, const float* ln_b, float eps, int mode, float* y, int64_t y_row_stride,
+                      int64_t y_step_stride, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- CoreDiffusion.forward (layers.py:38-63)
  * y[n_rows, h] (row stride ldy) = LayerNorm(sum_i GRU(relu(cumsum_i A_i x))).
  * workspace: ctgcn_core_diffusion_workspace_bytes(plan, d_in, h). */
@@ -143,6 +168,15 @@ int ctgcn_core_diffusion_fwd_scatter(const ctgcn_plan* plan, const float* x, int
                                      const float* ln_w, const float* ln_b, float eps, float* const* slice_ptrs, int n_slices,
                                      int64_t slice_row_stride, int64_t slice_col_offset, void* workspace,
                                      size_t workspace_bytes, void* stream);
+
+/* rnn_type-generic CoreDiffusion.forward: `cell` selects nn.GRU / nn.LSTM over the core axis (layers.py:26-30).
+ * y != NULL: plain output (row stride ldy); y == NULL: the scatter form above (slice_ptrs …). */
+size_t ctgcn_core_diffusion_rnn_workspace_bytes(const ctgcn_plan* plan, int cell, int d_in, int h);
+int ctgcn_core_diffusion_rnn_fwd(const ctgcn_plan* plan, int cell, const float* x, int64_t ldx, int d_in, int h,
+                                 const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                 const float* ln_w, const float* ln_b, float eps, float* y, int64_t ldy,
+                                 float* const* slice_ptrs, int n_slices, int64_t slice_row_stride, int64_t slice_col_offset,
+                                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- MLP layers (layers.py:95-106)
  * dense:  y[n, d_out] = act(x[n, d_in] w^T + b),  w [d_out, d_in] (nn.Linear layout), b may be NULL.

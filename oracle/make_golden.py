@@ -75,6 +75,31 @@ def gnp_edges(n, p, seed):
     return list(zip(iu[0][keep].tolist(), iu[1][keep].tolist()))
 
 
+def chung_lu_edges(n, m, seed, exponent=2.3):
+    """Power-law (Chung–Lu) simple undirected edge list: endpoints drawn ∝ (i+1)^(-1/(exponent-1))."""
+    rng = np.random.default_rng(seed)
+    w = (np.arange(n) + 1.0) ** (-1.0 / (exponent - 1.0))
+    cdf = np.cumsum(w) / w.sum()
+    u = np.searchsorted(cdf, rng.random(3 * m))
+    v = np.searchsorted(cdf, rng.random(3 * m))
+    perm = rng.permutation(n)
+    seen, out = set(), []
+    for a, b in zip(perm[u].tolist(), perm[v].tolist()):
+        if a != b and (min(a, b), max(a, b)) not in seen:
+            seen.add((min(a, b), max(a, b)))
+            out.append((a, b))
+            if len(out) == m:
+                break
+    return out
+
+
+def powerlaw_list(n, m, seed, k_keep):
+    mats, _ = core_mats_from_edges(n, chung_lu_edges(n, m, seed))
+    mats = mats[max(0, len(mats) - k_keep):]
+    adj, _ = oracle_np.build_core_adj_list(mats)
+    return adj
+
+
 def nested_list(n, p, seed, k_keep, weighted=False):
     edges = gnp_edges(n, p, seed)
     w = None
@@ -143,26 +168,52 @@ def agree(tag, ref, np64, t32):
     assert e1 < 5e-6 and e2 < 5e-6, (tag, e1, e2)
 
 
+COT_SEED = 900
+
+
+def ref_grads(mod, outs, extra_inputs=()):
+    """Reference autograd: loss = Σ_j Σ (outs[j] ⊙ cotangent(COT_SEED + j)); returns {'grad::<param>': array} for every
+    parameter that received a gradient (CoreDiffusion.linear never does, layers.py:46) and 'grad::x' for a dense input."""
+    loss = 0.0
+    for j, o in enumerate(outs):
+        loss = loss + (o * torch.from_numpy(cases.cotangent(COT_SEED + j, tuple(o.shape)))).sum()
+    mod.zero_grad()
+    loss.backward()
+    out = {}
+    for name, prm in mod.named_parameters():
+        if prm.grad is not None:
+            out["grad::" + name] = prm.grad.numpy().astype(np.float32)
+    for name, t in extra_inputs:
+        out["grad::" + name] = t.grad.numpy().astype(np.float32)
+    return out
+
+
 # ----------------------------------------------------------------------------- case runners
-def run_core_diffusion(name, adj, d_in, d_out, x_seed, w_seed, bias=True, raw_coo=None):
+def run_core_diffusion(name, adj, d_in, d_out, x_seed, w_seed, bias=True, raw_coo=None, rnn_type="GRU", grad=False):
     n = adj[0].shape[0]
     x = cases.features(x_seed, n, d_in)
-    sd = cases.core_diffusion_params(np.random.default_rng(w_seed), "", d_in, d_out, bias)
-    mod = ref_layers.CoreDiffusion(d_in, d_out, bias=bias)
+    sd = cases.core_diffusion_params(np.random.default_rng(w_seed), "", d_in, d_out, bias, rnn_type)
+    mod = ref_layers.CoreDiffusion(d_in, d_out, bias=bias, rnn_type=rnn_type)
     mod.load_state_dict(tsd(sd), strict=True)
     tadj = raw_coo if raw_coo is not None else coo_list(adj)
     with torch.no_grad():
         y = mod(torch.from_numpy(x), tadj).numpy()
+    grads = {}
+    if grad:
+        xt = torch.from_numpy(x).requires_grad_(True)
+        grads = ref_grads(mod, [mod(xt, tadj)], [("x", xt)])
     mats = adj
     agree(name, y, oracle_np.core_diffusion(x, mats, sd), oracle_torch.core_diffusion(torch.from_numpy(x), tadj, tsd(sd)).numpy())
     # [K,N,D] fp64 from the fp32-rounded edge weights the model actually sees (utils.py:93) — checks the SpMM kernel alone
     u = oracle_np.cumulative_core_sums(x.astype(np.float64), [sp.coo_matrix(m).astype(np.float32) for m in mats])
     arrays = cases.pack_graph(mats)
     arrays.update(y=y.astype(np.float32), u_sum=u.sum(axis=2).astype(np.float64))
-    save(name, dict(kind="core_diffusion", d_in=d_in, d_out=d_out, x_seed=x_seed, w_seed=w_seed, bias=bias), arrays)
+    arrays.update(grads)
+    save(name, dict(kind="core_diffusion", d_in=d_in, d_out=d_out, x_seed=x_seed, w_seed=w_seed, bias=bias,
+                    rnn_type=rnn_type, cot_seed=COT_SEED), arrays)
 
 
-def run_mlp(name, n, d_in, hid, d_out, layer_num, act, x_kind, x_seed, w_seed, bias=True):
+def run_mlp(name, n, d_in, hid, d_out, layer_num, act, x_kind, x_seed, w_seed, bias=True, grad=False):
     sd = cases.mlp_params(np.random.default_rng(w_seed), "", d_in, hid, d_out, layer_num, bias)
     if x_kind == "dense":
         xs = cases.features(x_seed, n, d_in)
@@ -185,15 +236,21 @@ def run_mlp(name, n, d_in, hid, d_out, layer_num, act, x_kind, x_seed, w_seed, b
         y = mod(xt).numpy()
     agree(name, y, oracle_np.mlp(xs, sd, "", layer_num, act), oracle_torch.mlp(xt, tsd(sd), "", layer_num, act).numpy())
     arrays["y"] = y.astype(np.float32)
-    save(name, dict(kind="mlp", n=n, d_in=d_in, hid=hid, d_out=d_out, layer_num=layer_num, act=act, x_kind=x_kind,
+    if grad:
+        if x_kind == "dense":
+            xg = torch.from_numpy(xs).requires_grad_(True)
+            arrays.update(ref_grads(mod, [mod(xg)], [("x", xg)]))
+        else:
+            arrays.update(ref_grads(mod, [mod(xt)]))
+    save(name, dict(kind="mlp", cot_seed=COT_SEED, n=n, d_in=d_in, hid=hid, d_out=d_out, layer_num=layer_num, act=act, x_kind=x_kind,
                     x_seed=x_seed, w_seed=w_seed, bias=bias), arrays)
 
 
-def run_cdn(name, adj, d_in, hid, d_out, diffusion_num, x_seed, w_seed):
+def run_cdn(name, adj, d_in, hid, d_out, diffusion_num, x_seed, w_seed, rnn_type="GRU", grad=False):
     n = adj[0].shape[0]
     x = cases.features(x_seed, n, d_in)
-    sd = cases.cdn_params(np.random.default_rng(w_seed), "", d_in, hid, d_out, diffusion_num)
-    mod = ref_models.CDN(d_in, hid, d_out, diffusion_num)
+    sd = cases.cdn_params(np.random.default_rng(w_seed), "", d_in, hid, d_out, diffusion_num, rnn_type=rnn_type)
+    mod = ref_models.CDN(d_in, hid, d_out, diffusion_num, rnn_type=rnn_type)
     mod.load_state_dict(tsd(sd), strict=True)
     tadj = coo_list(adj)
     with torch.no_grad():
@@ -201,7 +258,11 @@ def run_cdn(name, adj, d_in, hid, d_out, diffusion_num, x_seed, w_seed):
     agree(name, y, oracle_np.cdn(x, adj, sd, "", diffusion_num), oracle_torch.cdn(torch.from_numpy(x), tadj, tsd(sd), "", diffusion_num).numpy())
     arrays = cases.pack_graph(adj)
     arrays["y"] = y.astype(np.float32)
-    save(name, dict(kind="cdn", d_in=d_in, hid=hid, d_out=d_out, diffusion_num=diffusion_num, x_seed=x_seed, w_seed=w_seed), arrays)
+    if grad:
+        xg = torch.from_numpy(x).requires_grad_(True)
+        arrays.update(ref_grads(mod, [mod(xg, tadj)], [("x", xg)]))
+    save(name, dict(kind="cdn", d_in=d_in, hid=hid, d_out=d_out, diffusion_num=diffusion_num, x_seed=x_seed, w_seed=w_seed,
+                    rnn_type=rnn_type, cot_seed=COT_SEED), arrays)
 
 
 def model_inputs(n, T, x_kind, d_in, x_seed):
@@ -213,23 +274,27 @@ def model_inputs(n, T, x_kind, d_in, x_seed):
 
 
 def run_model(name, cls, adj_lists, d_in, hid, d_out, trans_num, diffusion_num, model_type, act, x_kind, x_seed, w_seed,
-              row_stride=1, single=False):
+              row_stride=1, single=False, rnn_type="GRU", grad=False, xs_override=None):
     T = len(adj_lists)
     n = adj_lists[0][0].shape[0]
     xs, xt = model_inputs(n, T, x_kind, d_in, x_seed)
+    if xs_override is not None:
+        xs, xt = xs_override, [torch.from_numpy(x) for x in xs_override]
     rng = np.random.default_rng(w_seed)
     tadj = [coo_list(a) for a in adj_lists]
     if cls == "ctgcn":
-        sd = cases.ctgcn_params(rng, d_in, hid, d_out, trans_num, diffusion_num, T, model_type)
-        mod = ref_models.CTGCN(d_in, hid, d_out, trans_num, diffusion_num, T, model_type=model_type, trans_activate_type=act)
+        sd = cases.ctgcn_params(rng, d_in, hid, d_out, trans_num, diffusion_num, T, model_type, rnn_type=rnn_type)
+        mod = ref_models.CTGCN(d_in, hid, d_out, trans_num, diffusion_num, T, rnn_type=rnn_type, model_type=model_type,
+                               trans_activate_type=act)
         mod.load_state_dict(tsd(sd), strict=True)
         with torch.no_grad():
             res = mod(xt, tadj)
         o_np = oracle_np.ctgcn(xs, adj_lists, sd, trans_num, diffusion_num, model_type, act)
         o_t = oracle_torch.ctgcn(xt, tadj, tsd(sd), trans_num, diffusion_num, model_type, act)
     else:
-        sd = cases.cgcn_params(rng, d_in, hid, d_out, trans_num, diffusion_num, model_type)
-        mod = ref_models.CGCN(d_in, hid, d_out, trans_num, diffusion_num, model_type=model_type, trans_activate_type=act)
+        sd = cases.cgcn_params(rng, d_in, hid, d_out, trans_num, diffusion_num, model_type, rnn_type=rnn_type)
+        mod = ref_models.CGCN(d_in, hid, d_out, trans_num, diffusion_num, rnn_type=rnn_type, model_type=model_type,
+                              trans_activate_type=act)
         mod.load_state_dict(tsd(sd), strict=True)
         args = (xt[0], tadj[0]) if single else (xt, tadj)
         with torch.no_grad():
@@ -263,7 +328,12 @@ def run_model(name, cls, adj_lists, d_in, hid, d_out, trans_num, diffusion_num, 
     arrays["y"] = np.ascontiguousarray(y[:, ::row_stride]).astype(np.float32)
     if tr is not None:
         arrays["trans"] = np.ascontiguousarray(tr[:, ::row_stride]).astype(np.float32)
-    save(name, dict(kind=cls, n=n, T=T, d_in=d_in, hid=hid, d_out=d_out, trans_num=trans_num, diffusion_num=diffusion_num,
+    if grad:   # loss over the full (un-strided) outputs: cotangent COT_SEED on out [T,N,D], COT_SEED+1 on the stacked MLP outputs
+        res_g = mod(*((xt[0], tadj[0]) if (cls == "cgcn" and single) else (xt, tadj)))
+        out_g, tr_g = (res_g if model_type == "S" else (res_g, None))
+        stk = lambda v: torch.stack(list(v)) if isinstance(v, (list, tuple)) else (v if v.dim() == 3 else v[None])
+        arrays.update(ref_grads(mod, [stk(out_g)] + ([stk(tr_g)] if tr_g is not None else [])))
+    save(name, dict(kind=cls, rnn_type=rnn_type, cot_seed=COT_SEED, n=n, T=T, d_in=d_in, hid=hid, d_out=d_out, trans_num=trans_num, diffusion_num=diffusion_num,
                     model_type=model_type, act=act, x_kind=x_kind, x_seed=x_seed, w_seed=w_seed, row_stride=row_stride,
                     single=single, state_dict_keys=sorted(sd.keys())), arrays)
 
@@ -334,6 +404,41 @@ def main():
     run_model("ctgcn_C_uci_T7", "ctgcn", uci_lists, n_uci, 64, 32, 1, 2, "C", "L", "eye", 85, 86, row_stride=4)
     run_model("ctgcn_C_uci_T2_500_128", "ctgcn", uci_lists[:2], n_uci, 500, 128, 1, 2, "C", "L", "eye", 87, 88, row_stride=6)
     run_model("ctgcn_S_uci_T7", "ctgcn", uci_lists, 50, 64, 32, 3, 1, "S", "N", "dense", 89, 90, row_stride=4)
+    print("== rnn_type='LSTM' (layers.py:27-28, models.py:234-235)")
+    run_core_diffusion("cd_lstm_k5", nested_list(257, 0.14, 15, 5), 128, 128, 105, 205, rnn_type="LSTM", grad=True)
+    run_core_diffusion("cd_lstm_nobias", nested_list(120, 0.1, 4, 4), 32, 64, 33, 34, bias=False, rnn_type="LSTM")
+    run_core_diffusion("cd_lstm_uci_500_128", uci_lists[0], 500, 128, 41, 42, rnn_type="LSTM")
+    run_model("ctgcn_C_T3_lstm", "ctgcn", syn, 180, 64, 32, 1, 2, "C", "L", "eye", 79, 80, rnn_type="LSTM", grad=True)
+    run_model("ctgcn_S_T3_lstm", "ctgcn", syn, 40, 64, 32, 3, 1, "S", "N", "dense", 81, 82, rnn_type="LSTM")
+    run_model("cgcn_C_list_lstm", "cgcn", syn, 180, 64, 32, 1, 2, "C", "L", "eye", 71, 72, rnn_type="LSTM")
+
+    print("== reference gradients (autograd through the reference modules)")
+    run_core_diffusion("cd_grad_k5", nested_list(200, 0.12, 21, 5), 48, 64, 111, 211, grad=True)
+    run_core_diffusion("cd_grad_weighted", nested_list(150, 0.1, 3, 6, weighted=True), 48, 40, 31, 32, grad=True)
+    run_core_diffusion("cd_grad_nobias", nested_list(120, 0.1, 4, 4), 32, 64, 33, 34, bias=False, grad=True)
+    run_core_diffusion("cd_grad_general", gen, 20, 24, 45, 46, raw_coo=raw, grad=True)     # non-symmetric list
+    run_core_diffusion("cd_grad_128", nested_list(257, 0.14, 15, 5), 128, 128, 105, 205, grad=True)
+    run_mlp("mlp_grad_3N_dense", 211, 70, 96, 48, 3, "N", "dense", 53, 54, grad=True)
+    run_mlp("mlp_grad_3N_sparse", 211, 90, 64, 32, 3, "N", "sparse", 55, 56, grad=True)
+    run_mlp("mlp_grad_1L_eye", 150, 150, 64, 48, 1, "L", "eye", 51, 52, grad=True)
+    run_mlp("mlp_grad_1N_nobias", 130, 33, 8, 17, 1, "N", "dense", 57, 58, bias=False, grad=True)
+    run_cdn("cdn_grad_2layer", adj5, 48, 64, 32, 2, 63, 64, grad=True)
+    run_model("ctgcn_grad_C_T3", "ctgcn", syn, 180, 64, 32, 1, 2, "C", "L", "eye", 79, 80, grad=True)
+    run_model("ctgcn_grad_S_T3", "ctgcn", syn, 40, 64, 32, 3, 1, "S", "N", "dense", 81, 82, grad=True)
+    run_model("cgcn_grad_S_list", "cgcn", syn[:2], 24, 64, 32, 3, 1, "S", "N", "dense", 75, 76, grad=True)
+    run_model("ctgcn_grad_128d_T2", "ctgcn", [nested_list(300, 0.1, 90 + t, 5) for t in range(2)], 128, 128, 128, 1, 1, "C", "L",
+              "dense", 83, 84, grad=True, row_stride=3)
+
+    print("== reduced stand-ins of BASELINE.json configs[2] (Facebook-like CTGCN-S, T=12) and configs[4] (power-law, 256-d)")
+    fb = [powerlaw_list(500, 2500, 300 + t, 9) for t in range(12)]
+    deg_w = int(max(sp.csr_matrix(a[-1]).sum(axis=1).max() for a in fb)) + 1       # max degree + 1 (helper.py:128-135)
+    fb_x = [cases.degree_gaussian_features(sp.csr_matrix(a[-1]), deg_w, 1e-4, 310 + t) for t, a in enumerate(fb)]
+    run_model("ctgcn_S_fb_T12", "ctgcn", fb, deg_w, 500, 128, 3, 1, "S", "N", "degree_gaussian", 310, 311, row_stride=5,
+              xs_override=fb_x)
+    pl = powerlaw_list(420, 9000, 320, 20)
+    run_core_diffusion("cd_powerlaw_256", pl, 256, 256, 321, 322)
+    run_model("ctgcn_256d_T2_powerlaw", "ctgcn", [pl, powerlaw_list(420, 9000, 323, 20)], 256, 256, 256, 1, 1, "C", "L", "dense",
+              324, 325, row_stride=4)
     print("done")
 
 

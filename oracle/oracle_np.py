@@ -58,6 +58,36 @@ def gru_sequence(seq, w_ih, w_hh, b_ih, b_hh):
     return out
 
 
+def lstm_sequence(seq, w_ih, w_hh, b_ih, b_hh):
+    """Single-layer batch_first nn.LSTM with h0 = c0 = 0, returning every step's output h_s (layers.py:27-28,59;
+    models.py:234-235,249 with rnn_type='LSTM').  PyTorch gate packing [i; f; g; o]:
+    c' = f ⊙ c + i ⊙ g,  h' = o ⊙ tanh(c')."""
+    B, L, _ = seq.shape
+    H = w_hh.shape[1]
+    h = np.zeros((B, H), dtype=seq.dtype)
+    c = np.zeros((B, H), dtype=seq.dtype)
+    out = np.empty((B, L, H), dtype=seq.dtype)
+    if b_ih is None:
+        b_ih = np.zeros(4 * H, dtype=seq.dtype)
+        b_hh = np.zeros(4 * H, dtype=seq.dtype)
+    for s in range(L):
+        pre = seq[:, s, :] @ w_ih.T + b_ih + h @ w_hh.T + b_hh
+        i, f = _sigmoid(pre[:, :H]), _sigmoid(pre[:, H:2 * H])
+        g, o = np.tanh(pre[:, 2 * H:3 * H]), _sigmoid(pre[:, 3 * H:])
+        c = f * c + i * g
+        h = o * np.tanh(c)
+        out[:, s, :] = h
+    return out
+
+
+def rnn_sequence(seq, sd, prefix, dtype):
+    """Dispatch on the stored weight shape: [3H, ·] → GRU, [4H, ·] → LSTM (the reference's rnn_type)."""
+    w_ih, w_hh = _p(sd, prefix, "rnn.weight_ih_l0", dtype), _p(sd, prefix, "rnn.weight_hh_l0", dtype)
+    b_ih, b_hh = _p(sd, prefix, "rnn.bias_ih_l0", dtype), _p(sd, prefix, "rnn.bias_hh_l0", dtype)
+    fn = lstm_sequence if w_hh.shape[0] == 4 * w_hh.shape[1] else gru_sequence
+    return fn(seq, w_ih, w_hh, b_ih, b_hh)
+
+
 def _p(sd, prefix, name, dtype):
     key = prefix + name
     return None if key not in sd else np.asarray(sd[key], dtype=dtype)
@@ -76,7 +106,7 @@ def cumulative_core_sums(x, adj_list):
 
 
 def core_diffusion(x, adj_list, sd, prefix="", dtype=np.float64, eps=1e-5):
-    """layers.CoreDiffusion.forward (layers.py:38-63), GRU flavour.
+    """layers.CoreDiffusion.forward (layers.py:38-63); GRU or LSTM by the stored weight shapes.
 
     cumulative SpMM (:41-47) → relu (:48) → stack/transposed view [N,K,D] (:58)
     → GRU over the core axis (:59) → Σ over cores (:60) → LayerNorm (:62).
@@ -84,9 +114,7 @@ def core_diffusion(x, adj_list, sd, prefix="", dtype=np.float64, eps=1e-5):
     """
     x = np.asarray(x, dtype=dtype)
     u = cumulative_core_sums(x, adj_list).transpose(1, 0, 2)
-    hs = gru_sequence(u,
-                      _p(sd, prefix, "rnn.weight_ih_l0", dtype), _p(sd, prefix, "rnn.weight_hh_l0", dtype),
-                      _p(sd, prefix, "rnn.bias_ih_l0", dtype), _p(sd, prefix, "rnn.bias_hh_l0", dtype))
+    hs = rnn_sequence(u, sd, prefix, dtype)
     o = hs.sum(axis=1)
     return layer_norm(o, _p(sd, prefix, "norm.weight", dtype), _p(sd, prefix, "norm.bias", dtype), eps)
 
@@ -153,9 +181,7 @@ def ctgcn(x_list, adj_list, sd, trans_num, diffusion_num, model_type="C", trans_
         trans_list.append(trans)
         hx.append(cdn(trans, adj, sd, f"duffision_list.{t}.", diffusion_num, dtype))
     seq = np.stack(hx, axis=0).transpose(1, 0, 2)
-    out = gru_sequence(seq,
-                       _p(sd, "", "rnn.weight_ih_l0", dtype), _p(sd, "", "rnn.weight_hh_l0", dtype),
-                       _p(sd, "", "rnn.bias_ih_l0", dtype), _p(sd, "", "rnn.bias_hh_l0", dtype))
+    out = rnn_sequence(seq, sd, "", dtype)
     out = layer_norm(out, _p(sd, "", "norm.weight", dtype), _p(sd, "", "norm.bias", dtype), eps)
     out = out.transpose(1, 0, 2)
     return out if model_type == "C" else (out, trans_list)
@@ -195,7 +221,5 @@ def core_diffusion_rows(x, adj_list, sd, rows, prefix="", dtype=np.float64, eps=
         acc = prod if acc is None else acc + prod
         outs.append(acc)
     u = np.maximum(np.stack(outs, axis=1), 0)
-    hs = gru_sequence(u,
-                      _p(sd, prefix, "rnn.weight_ih_l0", dtype), _p(sd, prefix, "rnn.weight_hh_l0", dtype),
-                      _p(sd, prefix, "rnn.bias_ih_l0", dtype), _p(sd, prefix, "rnn.bias_hh_l0", dtype))
+    hs = rnn_sequence(u, sd, prefix, dtype)
     return layer_norm(hs.sum(axis=1), _p(sd, prefix, "norm.weight", dtype), _p(sd, prefix, "norm.bias", dtype), eps)

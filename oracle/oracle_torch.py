@@ -26,11 +26,14 @@ def to_torch_coo(spmat):
 
 
 def _gru_all_outputs(seq, sd, prefix):
-    """nn.GRU(num_layers=1, batch_first=True)(seq)[0] with h0 = 0 (layers.py:30,59; models.py:237,249)."""
+    """nn.GRU / nn.LSTM(num_layers=1, batch_first=True)(seq)[0] with zero initial state (layers.py:27-30,59;
+    models.py:234-237,249); the cell is told by the stored weight shape."""
     w_ih, w_hh = sd[prefix + "rnn.weight_ih_l0"], sd[prefix + "rnn.weight_hh_l0"]
     has_bias = (prefix + "rnn.bias_ih_l0") in sd
     flat = [w_ih, w_hh] + ([sd[prefix + "rnn.bias_ih_l0"], sd[prefix + "rnn.bias_hh_l0"]] if has_bias else [])
     h0 = torch.zeros(1, seq.shape[0], w_hh.shape[1], dtype=seq.dtype, device=seq.device)
+    if w_hh.shape[0] == 4 * w_hh.shape[1]:   # rnn_type='LSTM' (layers.py:27-28, models.py:234-235): [i;f;g;o] stacked
+        return torch._VF.lstm(seq, (h0, torch.zeros_like(h0)), flat, has_bias, 1, 0.0, False, False, True)[0]
     out, _ = torch._VF.gru(seq, h0, flat, has_bias, 1, 0.0, False, False, True)
     return out
 

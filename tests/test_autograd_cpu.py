@@ -1,0 +1,169 @@
+"""Host-side logic of the backward pass, CPU only.
+
+1. ``autograd.rnn_seq_bwd`` / ``layer_norm_bwd`` (device-agnostic torch code) against autograd of nn.GRU / nn.LSTM + LayerNorm.
+2. ``plan.transpose_csr`` on small level-tagged CSRs.
+3. The autograd Functions + module wiring against the gradients the UNMODIFIED reference produced (tests/golden/*grad*),
+   with the CUDA entry points replaced by the oracle-backed stand-in of tests/fake_backend.py (the kernels themselves are
+   checked on the GPU in tests/test_train_gpu.py)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import cases, oracle_torch
+
+GRAD_TOL = 2e-5
+
+
+@pytest.mark.parametrize("cell_name", ["GRU", "LSTM"])
+@pytest.mark.parametrize("bias", [True, False])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_rnn_seq_bwd_matches_torch_autograd(cell_name, bias, mode, lib):
+    from ctgcn_b200 import autograd as ag
+    torch.manual_seed(3)
+    n, L, d, H = 37, 5, 12, 16
+    rnn = (nn.GRU if cell_name == "GRU" else nn.LSTM)(d, H, 1, bias=bias, batch_first=True).double()
+    ln = nn.LayerNorm(H).double()
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.2, 0.2)
+    seq = torch.randn(n, L, d, dtype=torch.double, requires_grad=True)
+    out, _ = rnn(seq)
+    y = ln(out.sum(1)) if mode == 0 else ln(out)
+    dy = torch.randn_like(y)
+    params = [rnn.weight_ih_l0, rnn.weight_hh_l0] + ([rnn.bias_ih_l0, rnn.bias_hh_l0] if bias else []) + [ln.weight, ln.bias]
+    want = torch.autograd.grad(y, [seq] + params, dy)
+    with torch.no_grad():
+        got = ag.rnn_seq_bwd(seq.detach(), lib.CELLS[cell_name], rnn.weight_ih_l0, rnn.weight_hh_l0,
+                             rnn.bias_ih_l0 if bias else None, rnn.bias_hh_l0 if bias else None, ln.weight, ln.bias, ln.eps,
+                             mode, dy)
+    assert (got[3] is None) == (not bias) and (got[4] is None) == (not bias)
+    got = [g for g in got if g is not None]
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert float((a - b).norm() / b.norm()) < 1e-10
+
+
+def test_selu_bwd_from_output(lib):
+    from ctgcn_b200 import autograd as ag
+    v = torch.linspace(-4, 4, 101, dtype=torch.double, requires_grad=True)
+    y = torch.selu(v)
+    dy = torch.randn_like(y)
+    (want,) = torch.autograd.grad(y, v, dy)
+    assert torch.allclose(ag.selu_bwd_from_output(dy, y.detach()), want, rtol=1e-12, atol=1e-12)
+
+
+def test_transpose_csr(lib):
+    from ctgcn_b200.plan import transpose_csr
+    rng = np.random.default_rng(0)
+    n, m, k = 7, 5, 3
+    dense = rng.random((n, m)) < 0.5
+    rows, cols = np.nonzero(dense)
+    lvl = rng.integers(0, k, rows.shape[0]).astype(np.uint8)
+    lvl[::4] |= 128
+    order = np.lexsort((cols, lvl & 127, rows))           # rows sorted by level
+    rows, cols, lvl = rows[order], cols[order], lvl[order]
+    val = rng.standard_normal(rows.shape[0]).astype(np.float32)
+    rowptr = np.zeros(n + 1, dtype=np.int32)
+    rowptr[1:] = np.cumsum(np.bincount(rows, minlength=n))
+    t_rowptr, t_col, t_val, t_lvl = [t.numpy() for t in transpose_csr(
+        n, m, torch.from_numpy(rowptr), torch.from_numpy(cols.astype(np.int32)), torch.from_numpy(val), torch.from_numpy(lvl))]
+    assert t_rowptr.shape == (m + 1,) and t_rowptr[-1] == rows.shape[0]
+    t_rows = np.repeat(np.arange(m), np.diff(t_rowptr))
+    a = {(r, c, l): v for r, c, l, v in zip(rows, cols, lvl, val)}
+    b = {(c, r, l): v for r, c, l, v in zip(t_rows, t_col, t_lvl, t_val)}
+    assert a == b
+    for r in range(m):                                     # level order inside every transposed row
+        assert (np.diff((t_lvl[t_rowptr[r]:t_rowptr[r + 1]] & 127).astype(int)) >= 0).all()
+
+
+def _tsd(sd):
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
+
+
+def _check_grads(mod, case, extra=None):
+    want = dict(case["grads"])
+    assert want, "case stores no reference gradients"
+    got = {name: p.grad for name, p in mod.named_parameters() if p.grad is not None}
+    if extra:
+        got.update(extra)
+    assert sorted(got) == sorted(want), (sorted(got), sorted(want))
+    for name, g in got.items():
+        err = cases.relerr(g.numpy(), want[name])
+        assert err < GRAD_TOL, (name, err)
+
+
+def _loss(outs, seed):
+    return sum((o * torch.from_numpy(cases.cotangent(seed + j, tuple(o.shape)))).sum() for j, o in enumerate(outs))
+
+
+@pytest.mark.parametrize("name", cases.golden_names("core_diffusion", rnn_type=None, grads=True))
+def test_core_diffusion_backward_wiring(name, lib, monkeypatch):
+    import fake_backend
+    pkg = fake_backend.install(monkeypatch)
+    c = cases.load_case(name)
+    m = c["meta"]
+    mod = pkg.CoreDiffusion(m["d_in"], m["d_out"], bias=m["bias"], rnn_type=m["rnn_type"])
+    mod.load_state_dict(_tsd(c["sd"]), strict=True)
+    x = torch.from_numpy(c["x"]).requires_grad_(True)
+    y = mod(x, [oracle_torch.to_torch_coo(a) for a in c["adj"]])
+    _loss([y], m["cot_seed"]).backward()
+    assert mod.linear.weight.grad is None                      # unused parameter (layers.py:46), like the reference
+    _check_grads(mod, c, {"x": x.grad})
+
+
+@pytest.mark.parametrize("name", cases.golden_names("mlp", grads=True))
+def test_mlp_backward_wiring(name, lib, monkeypatch):
+    import fake_backend
+    pkg = fake_backend.install(monkeypatch)
+    c = cases.load_case(name)
+    m = c["meta"]
+    mod = pkg.MLP(m["d_in"], m["hid"], m["d_out"], m["layer_num"], bias=m["bias"], activate_type=m["act"])
+    mod.load_state_dict(_tsd(c["sd"]), strict=True)
+    if isinstance(c["x"], np.ndarray):
+        x = torch.from_numpy(c["x"]).requires_grad_(True)
+        _loss([mod(x)], m["cot_seed"]).backward()
+        _check_grads(mod, c, {"x": x.grad})
+    else:
+        _loss([mod(oracle_torch.to_torch_coo(c["x"]))], m["cot_seed"]).backward()
+        _check_grads(mod, c)
+
+
+@pytest.mark.parametrize("name", cases.golden_names("cdn", grads=True))
+def test_cdn_backward_wiring(name, lib, monkeypatch):
+    import fake_backend
+    pkg = fake_backend.install(monkeypatch)
+    c = cases.load_case(name)
+    m = c["meta"]
+    mod = pkg.CDN(m["d_in"], m["hid"], m["d_out"], m["diffusion_num"], rnn_type=m["rnn_type"])
+    mod.load_state_dict(_tsd(c["sd"]), strict=True)
+    x = torch.from_numpy(c["x"]).requires_grad_(True)
+    _loss([mod(x, [oracle_torch.to_torch_coo(a) for a in c["adj"]])], m["cot_seed"]).backward()
+    _check_grads(mod, c, {"x": x.grad})
+
+
+@pytest.mark.parametrize("name", cases.golden_names("ctgcn", rnn_type=None, grads=True) + cases.golden_names("cgcn", rnn_type=None, grads=True))
+def test_model_backward_wiring(name, lib, monkeypatch):
+    import fake_backend
+    pkg = fake_backend.install(monkeypatch)
+    c = cases.load_case(name)
+    m = c["meta"]
+    if m["kind"] == "ctgcn":
+        mod = pkg.CTGCN(m["d_in"], m["hid"], m["d_out"], m["trans_num"], m["diffusion_num"], m["T"], rnn_type=m["rnn_type"],
+                        model_type=m["model_type"], trans_activate_type=m["act"])
+    else:
+        mod = pkg.CGCN(m["d_in"], m["hid"], m["d_out"], m["trans_num"], m["diffusion_num"], rnn_type=m["rnn_type"],
+                       model_type=m["model_type"], trans_activate_type=m["act"])
+    mod.load_state_dict(_tsd(c["sd"]), strict=True)
+    xs = [torch.from_numpy(x) if isinstance(x, np.ndarray) else oracle_torch.to_torch_coo(x) for x in c["x_list"]]
+    adj = [[oracle_torch.to_torch_coo(a) for a in al] for al in c["adj_lists"]]
+    res = mod(xs[0], adj[0]) if m.get("single") else mod(xs, adj)
+    out, trans = res if m["model_type"] == "S" else (res, None)
+    stk = lambda v: torch.stack(list(v)) if isinstance(v, (list, tuple)) else (v if v.dim() == 3 else v[None])
+    _loss([stk(out)] + ([stk(trans)] if trans is not None else []), m["cot_seed"]).backward()
+    _check_grads(mod, c)
+    # the no-grad fast path (outputs written straight into the [N, T, D] buffer) gives the same forward values
+    with torch.no_grad():
+        res2 = mod(xs[0], adj[0]) if m.get("single") else mod(xs, adj)
+    out2 = res2[0] if m["model_type"] == "S" else res2
+    assert torch.allclose(stk(out2), stk(out).detach(), rtol=0, atol=0)

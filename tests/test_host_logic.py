@@ -75,19 +75,19 @@ def test_module_surface_matches_reference(lib):
                              "model_type", "trans_activate_type"]
     assert sig(pkg.CTGCN) == ["input_dim", "hidden_dim", "output_dim", "trans_num", "diffusion_num", "duration", "bias",
                               "rnn_type", "model_type", "trans_activate_type"]
-    for name in cases.golden_names("ctgcn") + cases.golden_names("cgcn"):
+    for name in cases.golden_names("ctgcn", rnn_type=None) + cases.golden_names("cgcn", rnn_type=None):
         m = cases.load_meta(name)
         cls = pkg.CTGCN if m["kind"] == "ctgcn" else pkg.CGCN
         args = (m["d_in"], m["hid"], m["d_out"], m["trans_num"], m["diffusion_num"]) + ((m["T"],) if m["kind"] == "ctgcn" else ())
-        mod = cls(*args, model_type=m["model_type"], trans_activate_type=m["act"])
+        mod = cls(*args, rnn_type=m["rnn_type"], model_type=m["model_type"], trans_activate_type=m["act"])
         assert sorted(mod.state_dict().keys()) == m["state_dict_keys"], name
         assert mod.method_name == ("CTGCN-" if m["kind"] == "ctgcn" else "CGCN-") + m["model_type"]
     with pytest.raises(AssertionError):
         pkg.MLP(4, 4, 4, 0)
     with pytest.raises(AssertionError):
         pkg.CoreDiffusion(4, 4, rnn_type="RNN")
-    with pytest.raises(NotImplementedError):
-        pkg.CoreDiffusion(4, 4, rnn_type="LSTM")
+    lstm = pkg.CoreDiffusion(4, 6, rnn_type="LSTM")          # layers.py:27-28: same parameter names, [4H, ·] shapes
+    assert tuple(lstm.rnn.weight_ih_l0.shape) == (24, 4) and tuple(lstm.rnn.weight_hh_l0.shape) == (24, 6)
     with pytest.raises(ValueError):
         pkg.CDN(4, 4, 4, 0)
 

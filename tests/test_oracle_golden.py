@@ -17,7 +17,7 @@ def _coo(mats):
     return [oracle_torch.to_torch_coo(m) for m in mats]
 
 
-@pytest.mark.parametrize("name", cases.golden_names("core_diffusion"))
+@pytest.mark.parametrize("name", cases.golden_names("core_diffusion", rnn_type=None))
 def test_core_diffusion(name):
     c = cases.load_case(name)
     y64 = oracle_np.core_diffusion(c["x"], c["adj"], c["sd"])
@@ -29,7 +29,7 @@ def test_core_diffusion(name):
     np.testing.assert_allclose(u.sum(axis=2), c["expected"]["u_sum"], rtol=1e-12, atol=1e-9)
 
 
-@pytest.mark.parametrize("name", cases.golden_names("mlp"))
+@pytest.mark.parametrize("name", cases.golden_names("mlp", rnn_type=None))
 def test_mlp(name):
     c = cases.load_case(name)
     m = c["meta"]
@@ -40,7 +40,7 @@ def test_mlp(name):
     assert cases.relerr(yt, c["expected"]["y"]) < TOL
 
 
-@pytest.mark.parametrize("name", cases.golden_names("cdn"))
+@pytest.mark.parametrize("name", cases.golden_names("cdn", rnn_type=None))
 def test_cdn(name):
     c = cases.load_case(name)
     y64 = oracle_np.cdn(c["x"], c["adj"], c["sd"], "", c["meta"]["diffusion_num"])
@@ -59,7 +59,7 @@ def _model_out(c, res):
     return out[:, ::rs], None if trans is None else trans[:, ::rs]
 
 
-@pytest.mark.parametrize("name", cases.golden_names("cgcn") + cases.golden_names("ctgcn"))
+@pytest.mark.parametrize("name", cases.golden_names("cgcn", rnn_type=None) + cases.golden_names("ctgcn", rnn_type=None))
 def test_models(name):
     c = cases.load_case(name)
     m = c["meta"]

@@ -340,9 +340,8 @@ def test_shape_errors(lib, cuda_device):
         mod(torch.zeros(11, 16, device=cuda_device), adj)
     with pytest.raises(lib.CtgcnError):
         mod(torch.zeros(10, 8, device=cuda_device), adj)
-    out = mod(torch.zeros(10, 16, device=cuda_device), adj)      # grad mode on: forward works, backward refuses
-    with pytest.raises(NotImplementedError):
-        out.sum().backward()
+    with pytest.raises(lib.CtgcnError):
+        mod(torch.zeros(10, 16), adj)                            # CPU tensor: there is no CPU path
 
 
 # ----------------------------------------------------------------------------- benchmark-size properties
