@@ -118,6 +118,31 @@ class SnapshotGraph:
         return out
 
 
+def assemble_snapshot(n: int, u, v, w, le, levels) -> SnapshotGraph:
+    """Level-tagged union CSR of one snapshot from its undirected edges: edge e belongs to list entries le[e] … K-1
+    (nested k-cores), plus the +I diagonal that helper.py:72 adds to the FIRST entry only (one-shot at level 0)."""
+    k_eff = int(len(levels))
+    dev = _work_device()
+    ut, vt = torch.as_tensor(u, dtype=torch.int64, device=dev), torch.as_tensor(v, dtype=torch.int64, device=dev)
+    lt, wt = torch.as_tensor(le, dtype=torch.uint8, device=dev), torch.as_tensor(w, dtype=torch.float32, device=dev)
+    diag = torch.arange(n, dtype=torch.int64, device=dev)
+    rows = torch.cat([ut, vt, diag])
+    cols = torch.cat([vt, ut, diag])
+    lvl = torch.cat([lt, lt, torch.full((n,), 128, dtype=torch.uint8, device=dev)])  # diagonal: one-shot at level 0
+    vals = torch.cat([wt, wt, torch.ones(n, dtype=torch.float32, device=dev)])
+    bits = max(1, int(n - 1).bit_length())
+    key = (((rows << 7) | (lvl & 127).to(torch.int64)) << bits) | cols               # (row, level, col)
+    order = torch.argsort(key)
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    rowptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0).cpu().numpy()
+    per_level = np.bincount(np.asarray(le, dtype=np.int64), minlength=k_eff) * 2
+    nnz = np.cumsum(per_level).tolist()
+    nnz[0] += n
+    return SnapshotGraph(n, k_eff, rowptr.astype(np.int32), cols[order].to(torch.int32).cpu().numpy(),
+                         vals[order].cpu().numpy(), lvl[order].cpu().numpy(), [int(x) for x in nnz],
+                         [int(x) for x in levels])
+
+
 def snapshot_from_edges(n: int, u: np.ndarray, v: np.ndarray, k: int, weights: np.ndarray = None) -> SnapshotGraph:
     core = core_numbers(n, u, v)
     ce = np.minimum(core[u], core[v])                      # the largest k-core that still contains the edge
@@ -132,25 +157,7 @@ def snapshot_from_edges(n: int, u: np.ndarray, v: np.ndarray, k: int, weights: n
     keep = le != 255
     u, v, le = u[keep], v[keep], le[keep]
     w = np.ones(u.shape[0], dtype=np.float32) if weights is None else weights[keep].astype(np.float32)
-    dev = _work_device()
-    ut, vt = torch.as_tensor(u, dtype=torch.int64, device=dev), torch.as_tensor(v, dtype=torch.int64, device=dev)
-    lt, wt = torch.as_tensor(le, device=dev), torch.as_tensor(w, device=dev)
-    diag = torch.arange(n, dtype=torch.int64, device=dev)
-    rows = torch.cat([ut, vt, diag])
-    cols = torch.cat([vt, ut, diag])
-    lvl = torch.cat([lt, lt, torch.full((n,), 128, dtype=torch.uint8, device=dev)])  # diagonal: one-shot at level 0
-    vals = torch.cat([wt, wt, torch.ones(n, dtype=torch.float32, device=dev)])
-    bits = max(1, int(n - 1).bit_length())
-    key = (((rows << 7) | (lvl & 127).to(torch.int64)) << bits) | cols               # (row, level, col)
-    order = torch.argsort(key)
-    rowptr = np.zeros(n + 1, dtype=np.int64)
-    rowptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0).cpu().numpy()
-    per_level = np.bincount(le, minlength=k_eff) * 2
-    nnz = np.cumsum(per_level).tolist()
-    nnz[0] += n
-    return SnapshotGraph(n, k_eff, rowptr.astype(np.int32), cols[order].to(torch.int32).cpu().numpy(),
-                         vals[order].cpu().numpy(), lvl[order].cpu().numpy(), [int(x) for x in nnz],
-                         [int(x) for x in levels])
+    return assemble_snapshot(n, u, v, w, le, levels)
 
 
 def make_snapshot(kind: str, n: int, m: int, k: int, seed: int) -> SnapshotGraph:

@@ -2,7 +2,12 @@
 every gradient of the drop-in modules against autograd through the UNMODIFIED reference (tests/golden/*grad*), and a short
 Adam run against the same run through the torch-CPU port of the reference.
 
-Tolerance: gradients within 1e-4 relative (relL2 per tensor) of the reference's fp32 autograd."""
+Tolerance (relL2 per gradient tensor against the reference's fp32 autograd, itself within 1e-6 of fp64):
+  * fp32 kernels (impl = simt): 1e-4 (measured ≤ 4e-6);
+  * tcgen05 split-bf16 forward (impl = auto): 3e-3.  The backward is the same fp32 code; the forward values it is evaluated at
+    carry the ≈1e-5 split-precision error, and relu (layers.py:48) / selu (layers.py:98-105) have a kink at 0: an element whose
+    pre-activation is within that error of 0 lands on the other side and changes its derivative by O(1).  One such element
+    moves a weight-gradient tensor by ≈1e-3 (reproduced on the CPU by emulating the split product; profiles/diag_grads.py)."""
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -12,7 +17,14 @@ from oracle import cases, oracle_torch
 from test_parity_gpu import close, coo, expand_plan, tsd
 
 pytestmark = pytest.mark.gpu
-GRAD_TOL = 1e-4
+GRAD_TOL = {"simt": 1e-4, "auto": 3e-3}
+
+
+@pytest.fixture(scope="module", params=["simt", "auto"])
+def impl(request, lib, cuda_device):
+    lib.set_gru_impl(lib.IMPL_SIMT if request.param == "simt" else lib.IMPL_AUTO)
+    yield request.param
+    lib.set_gru_impl(lib.IMPL_AUTO)
 
 
 @pytest.mark.parametrize("name", ["cd_nested_k5", "cd_general", "cd_nested_weighted", "cd_nested_k1"])
@@ -48,8 +60,9 @@ def test_cumspmm_no_relu_and_backward_kernel(name, d, lib, cuda_device):
     close(s, np.stack(ref_s, axis=1), name + " S")
     zo = np.flip(np.cumsum(np.flip(g.astype(np.float64), 1), 1), 1)
     ref_dx = sum(a.T @ zo[:, j] for j, a in enumerate(mats))
+    plan_t = plan.transposed()
     before = lib.launch_count()
-    dx = ops.cumspmm_bwd(plan.transposed(), torch.from_numpy(g).to(cuda_device))
+    dx = ops.cumspmm_bwd(plan_t, torch.from_numpy(g).to(cuda_device))
     assert lib.launch_count() - before == 2                       # suffix sums + level gather
     close(dx.cpu().numpy(), ref_dx, name + " dx")
     lhs, rhs = float((s.astype(np.float64) * g).sum()), float((x.astype(np.float64) * dx.cpu().numpy()).sum())
@@ -57,32 +70,32 @@ def test_cumspmm_no_relu_and_backward_kernel(name, d, lib, cuda_device):
 
 
 @pytest.mark.parametrize("name", cases.golden_names("core_diffusion", rnn_type=None, grads=True))
-def test_core_diffusion_backward(name, lib, cuda_device):
+def test_core_diffusion_backward(name, impl, lib, cuda_device):
     import grad_checks
     import ctgcn_b200 as pkg
-    grad_checks.core_diffusion_grad(pkg, cases.load_case(name), cuda_device, GRAD_TOL)
+    grad_checks.core_diffusion_grad(pkg, cases.load_case(name), cuda_device, GRAD_TOL[impl])
 
 
 @pytest.mark.parametrize("name", cases.golden_names("mlp", grads=True))
-def test_mlp_backward(name, lib, cuda_device):
+def test_mlp_backward(name, impl, lib, cuda_device):
     import grad_checks
     import ctgcn_b200 as pkg
-    grad_checks.mlp_grad(pkg, cases.load_case(name), cuda_device, GRAD_TOL)
+    grad_checks.mlp_grad(pkg, cases.load_case(name), cuda_device, GRAD_TOL[impl])
 
 
 @pytest.mark.parametrize("name", cases.golden_names("cdn", rnn_type=None, grads=True))
-def test_cdn_backward(name, lib, cuda_device):
+def test_cdn_backward(name, impl, lib, cuda_device):
     import grad_checks
     import ctgcn_b200 as pkg
-    grad_checks.cdn_grad(pkg, cases.load_case(name), cuda_device, GRAD_TOL)
+    grad_checks.cdn_grad(pkg, cases.load_case(name), cuda_device, GRAD_TOL[impl])
 
 
 @pytest.mark.parametrize("name", cases.golden_names("ctgcn", rnn_type=None, grads=True) + cases.golden_names("cgcn", rnn_type=None, grads=True))
-def test_model_backward(name, lib, cuda_device):
+def test_model_backward(name, impl, lib, cuda_device):
     import grad_checks
     import ctgcn_b200 as pkg
     # forward values of the training path (fresh tensors + stack) vs the no-grad path (in-place [N,T,D] buffer): same kernels
-    grad_checks.model_grad(pkg, cases.load_case(name), cuda_device, GRAD_TOL, fwd_tol=0.0)
+    grad_checks.model_grad(pkg, cases.load_case(name), cuda_device, GRAD_TOL[impl], fwd_tol=0.0)
 
 
 def test_frozen_parameters_and_no_grad(lib, cuda_device):
