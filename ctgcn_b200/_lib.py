@@ -65,6 +65,7 @@ SIGNATURES = {
     "ctgcn_core_diffusion_rnn_workspace_bytes": (_sz, [_p, _i32, _i32, _i32]),
     "ctgcn_core_diffusion_rnn_fwd": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _f32, _p, _i64, _p, _i32,
                                                _i64, _i64, _p, _sz, _p]),
+    "ctgcn_set_workspace_cap": (C.c_int, [_sz]),
     "ctgcn_linear_workspace_bytes": (_sz, [_i64, _i64]),
     "ctgcn_linear_fwd": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _i32, _p, _i64, _p, _sz, _p]),
     "ctgcn_spmm_linear_fwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _i64, _p, _sz, _p]),
@@ -102,6 +103,11 @@ def prof_collect(reset: bool = True) -> dict:
     cnt = (C.c_int64 * len(PROF_CLASSES))()
     check(lib.ctgcn_prof_collect(ms, cnt, 1 if reset else 0), "ctgcn_prof_collect")
     return {n: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, n in enumerate(PROF_CLASSES)}
+
+
+def set_workspace_cap(nbytes: int) -> None:
+    """Bound on the per-core-sums buffer of one CoreDiffusion call (0 = default 8 GiB); larger layers run in row chunks."""
+    check(lib.ctgcn_set_workspace_cap(int(nbytes)), "ctgcn_set_workspace_cap")
 
 
 def set_gru_impl(impl: int) -> None:

@@ -12,6 +12,8 @@ namespace ctgcn {
 static thread_local char g_err[1024] = "";
 std::atomic<int64_t> g_launches{0};
 static std::atomic<int> g_gru_impl{CTGCN_IMPL_AUTO};
+static constexpr size_t kDefaultChunkCap = (size_t)8 << 30;
+static std::atomic<size_t> g_chunk_cap{kDefaultChunkCap};   // bound on the per-core-sums buffer of a CoreDiffusion call
 
 // ---- per-kernel-class timing
 static std::atomic<int> g_prof_on{0};
@@ -219,11 +221,32 @@ extern "C" int ctgcn_gru_seq_fwd(const float* seq, int64_t srs, int64_t sss, int
 }
 
 // ---- CoreDiffusion.forward: cumulative SpMM → U [n, K, d_in] (workspace) → GRU/LSTM over cores + Σ + LayerNorm
+// Rows of one CoreDiffusion chunk: the per-core sums U [rows, K, d_in] of a chunk live in the workspace between the two
+// kernels; when all rows would need more than the cap (cfg 5: 5 M × 20 × 256 × 4 B = 102 GB) the layer runs chunk by chunk —
+// whole waves of the persistent sequence kernel (148 SMs × 128-row tiles) so that every chunk but the last fills the GPU.
+static int64_t cd_chunk_rows(const ctgcn_plan* plan, int d_in) {
+    const size_t per_row = (size_t)plan->k * d_in * sizeof(float);
+    const size_t cap = g_chunk_cap.load();
+    int64_t rows = plan->n_rows;
+    if ((size_t)rows * per_row > cap) {
+        rows = (int64_t)(cap / per_row);
+        const int64_t wave = 148 * 128;
+        rows = rows >= wave ? rows / wave * wave : (rows >= 128 ? rows / 128 * 128 : 128);
+        if (rows > plan->n_rows) rows = plan->n_rows;
+    }
+    return rows;
+}
+
+extern "C" int ctgcn_set_workspace_cap(size_t bytes) {
+    g_chunk_cap.store(bytes ? bytes : kDefaultChunkCap);
+    return CTGCN_OK;
+}
+
 extern "C" size_t ctgcn_core_diffusion_rnn_workspace_bytes(const ctgcn_plan* plan, int cell, int d_in, int h) {
     if (!plan || d_in <= 0 || h <= 0) return 0;
     const size_t r = ctgcn_rnn_workspace_bytes(cell, d_in, h);
     if (!r) return 0;
-    return align_up((size_t)plan->n_rows * plan->k * d_in * sizeof(float), 256) + r;
+    return align_up((size_t)cd_chunk_rows(plan, d_in) * plan->k * d_in * sizeof(float), 256) + r;
 }
 
 extern "C" size_t ctgcn_core_diffusion_workspace_bytes(const ctgcn_plan* plan, int d_in, int h) {
@@ -244,12 +267,23 @@ static int core_diffusion_impl(const ctgcn_plan* plan, int cell, const float* x,
         return CTGCN_ENOMEM;
     }
     float* u = (float*)workspace;
-    const size_t u_bytes = align_up((size_t)plan->n_rows * plan->k * d_in * sizeof(float), 256);
-    int rc = launch_cumspmm(plan, x, ldx, d_in, u, true, (cudaStream_t)stream);
-    if (rc) return rc;
-    return rnn_seq_impl(cell, u, (int64_t)plan->k * d_in, d_in, plan->n_rows, plan->k, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w,
-                        ln_b, eps, CTGCN_GRU_SUM_LN, y, ldy, 0, sc, (char*)workspace + u_bytes, workspace_bytes - u_bytes,
-                        stream);
+    const int64_t chunk = cd_chunk_rows(plan, d_in);
+    const size_t u_bytes = align_up((size_t)chunk * plan->k * d_in * sizeof(float), 256);
+    for (int64_t row0 = 0; row0 < plan->n_rows; row0 += chunk) {
+        const int64_t rows = plan->n_rows - row0 < chunk ? plan->n_rows - row0 : chunk;
+        int rc = launch_cumspmm(plan, x, ldx, d_in, u, true, (cudaStream_t)stream, row0, rows);
+        if (rc) return rc;
+        RowScatter sc_chunk;
+        if (sc) {
+            sc_chunk = *sc;
+            sc_chunk.row_off = row0;
+        }
+        rc = rnn_seq_impl(cell, u, (int64_t)plan->k * d_in, d_in, rows, plan->k, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps,
+                          CTGCN_GRU_SUM_LN, y ? y + row0 * ldy : nullptr, ldy, 0, sc ? &sc_chunk : nullptr,
+                          (char*)workspace + u_bytes, workspace_bytes - u_bytes, stream);
+        if (rc) return rc;
+    }
+    return CTGCN_OK;
 }
 
 static int make_scatter(const ctgcn_plan* plan, int h, float* const* slice_ptrs, int n_slices, int64_t slice_row_stride,

@@ -85,8 +85,10 @@ struct RowScatter {
     long long base = 0, rem = 0;
     long long row_stride = 0;        // elements between consecutive rows of a slice buffer (T·D)
     long long col_offset = 0;        // element offset of this output inside a slice row (t·D)
+    long long row_off = 0;           // added to the kernel's (chunk-local) row index: row-chunked CoreDiffusion launches
 #ifdef __CUDACC__
     __device__ __forceinline__ float* row_ptr(long long row) const {
+        row += row_off;
         const long long big = rem * (base + 1);
         long long g, local;
         if (row < big) {
@@ -104,7 +106,9 @@ struct RowScatter {
 
 // kernels' host launchers (defined in the respective .cu files)
 namespace ctgcn {
-int launch_cumspmm(const ctgcn_plan* p, const float* x, int64_t ldx, int d, float* u, bool relu, cudaStream_t st);
+// rows < 0: all rows from row0 on; u is the [rows, K, d] buffer of the selected row range
+int launch_cumspmm(const ctgcn_plan* p, const float* x, int64_t ldx, int d, float* u, bool relu, cudaStream_t st,
+                   int64_t row0 = 0, int64_t rows = -1);
 int launch_cumspmm_bwd(const ctgcn_plan* pt, const float* g, int d, float* zo, float* zn, float* dx, int64_t lddx,
                        cudaStream_t st);
 int launch_spmm_linear(const ctgcn_plan* p, const float* wt, const float* b, int64_t d_out, int act, float* y,

@@ -298,52 +298,60 @@ __global__ void transpose_kernel(const float* __restrict__ src, int64_t rows, in
     }
 }
 
+// Row range [row0, row0 + rows): the kernels index rows locally, so the range is selected by shifting the row-pointer array
+// (entry offsets stay absolute) — u is the chunk's own [rows, K, d] buffer.
 template <int NV, int UNROLL>
-int launch_vec(const ctgcn_plan* p, const float* x, int64_t ldx, int d, float* u, bool relu, cudaStream_t st) {
-    const unsigned blocks = (unsigned)((p->n_rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+int launch_vec(const ctgcn_plan* p, const float* x, int64_t ldx, int d, float* u, bool relu, cudaStream_t st, int64_t row0,
+               int64_t rows) {
+    const unsigned blocks = (unsigned)((rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     if (relu)
-        cumspmm_vec_kernel<NV, UNROLL, true><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p->rowptr, p->col, p->val, p->lvl, x,
-                                                                                      ldx, d, p->k, p->n_rows, u);
+        cumspmm_vec_kernel<NV, UNROLL, true><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p->rowptr + row0, p->col, p->val, p->lvl, x,
+                                                                                      ldx, d, p->k, rows, u);
     else
-        cumspmm_vec_kernel<NV, UNROLL, false><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p->rowptr, p->col, p->val, p->lvl,
-                                                                                       x, ldx, d, p->k, p->n_rows, u);
+        cumspmm_vec_kernel<NV, UNROLL, false><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p->rowptr + row0, p->col, p->val, p->lvl,
+                                                                                       x, ldx, d, p->k, rows, u);
     CTGCN_LAUNCH_OK("cumspmm_vec_kernel");
     return CTGCN_OK;
 }
 
 template <int DPL>
-int launch_scalar(const ctgcn_plan* p, const float* x, int64_t ldx, int d, float* u, bool relu, cudaStream_t st) {
-    const unsigned blocks = (unsigned)((p->n_rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+int launch_scalar(const ctgcn_plan* p, const float* x, int64_t ldx, int d, float* u, bool relu, cudaStream_t st, int64_t row0,
+                  int64_t rows) {
+    const unsigned blocks = (unsigned)((rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     if (relu)
-        cumspmm_scalar_kernel<DPL, true><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p->rowptr, p->col, p->val, p->lvl, x, ldx,
-                                                                                  d, p->k, p->n_rows, u);
+        cumspmm_scalar_kernel<DPL, true><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p->rowptr + row0, p->col, p->val, p->lvl, x, ldx,
+                                                                                  d, p->k, rows, u);
     else
-        cumspmm_scalar_kernel<DPL, false><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p->rowptr, p->col, p->val, p->lvl, x, ldx,
-                                                                                   d, p->k, p->n_rows, u);
+        cumspmm_scalar_kernel<DPL, false><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p->rowptr + row0, p->col, p->val, p->lvl, x, ldx,
+                                                                                   d, p->k, rows, u);
     CTGCN_LAUNCH_OK("cumspmm_scalar_kernel");
     return CTGCN_OK;
 }
 
 }  // namespace
 
-int launch_cumspmm(const ctgcn_plan* p, const float* x, int64_t ldx, int d, float* u, bool relu, cudaStream_t st) {
+int launch_cumspmm(const ctgcn_plan* p, const float* x, int64_t ldx, int d, float* u, bool relu, cudaStream_t st, int64_t row0,
+                   int64_t rows) {
     CTGCN_REQUIRE(d >= 1 && d <= 1024, "cumspmm: feature width %d outside [1,1024]", d);
+    if (rows < 0) rows = p->n_rows - row0;
+    CTGCN_REQUIRE(row0 >= 0 && rows >= 0 && row0 + rows <= p->n_rows, "cumspmm: row range outside the plan");
+    if (rows == 0) return CTGCN_OK;
     ProfScope prof(PROF_SPMM, st);
     const bool vec_ok = (d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(u) & 15) == 0);
     if (vec_ok) {
         const int d4 = d / 4;
-        if (d4 <= 32) return launch_vec<1, 8>(p, x, ldx, d, u, relu, st);
-        if (d4 <= 64) return launch_vec<2, 4>(p, x, ldx, d, u, relu, st);
-        if (d4 <= 128) return launch_vec<4, 2>(p, x, ldx, d, u, relu, st);
-        return launch_vec<8, 1>(p, x, ldx, d, u, relu, st);
+        if (d4 <= 32) return launch_vec<1, 8>(p, x, ldx, d, u, relu, st, row0, rows);
+        if (d4 <= 64) return launch_vec<2, 4>(p, x, ldx, d, u, relu, st, row0, rows);
+        if (d4 <= 128) return launch_vec<4, 2>(p, x, ldx, d, u, relu, st, row0, rows);
+        return launch_vec<8, 1>(p, x, ldx, d, u, relu, st, row0, rows);
     }
-    if (d <= 32) return launch_scalar<1>(p, x, ldx, d, u, relu, st);
-    if (d <= 64) return launch_scalar<2>(p, x, ldx, d, u, relu, st);
-    if (d <= 128) return launch_scalar<4>(p, x, ldx, d, u, relu, st);
-    if (d <= 256) return launch_scalar<8>(p, x, ldx, d, u, relu, st);
-    if (d <= 512) return launch_scalar<16>(p, x, ldx, d, u, relu, st);
-    return launch_scalar<32>(p, x, ldx, d, u, relu, st);
+    if (d <= 32) return launch_scalar<1>(p, x, ldx, d, u, relu, st, row0, rows);
+    if (d <= 64) return launch_scalar<2>(p, x, ldx, d, u, relu, st, row0, rows);
+    if (d <= 128) return launch_scalar<4>(p, x, ldx, d, u, relu, st, row0, rows);
+    if (d <= 256) return launch_scalar<8>(p, x, ldx, d, u, relu, st, row0, rows);
+    if (d <= 512) return launch_scalar<16>(p, x, ldx, d, u, relu, st, row0, rows);
+    return launch_scalar<32>(p, x, ldx, d, u, relu, st, row0, rows);
 }
 
 int launch_cumspmm_bwd(const ctgcn_plan* pt, const float* g, int d, float* zo, float* zn, float* dx, int64_t lddx,

@@ -156,6 +156,12 @@ int ctgcn_core_diffusion_fwd(const ctgcn_plan* plan, const float* x, int64_t ldx
                              const float* ln_w, const float* ln_b, float eps, float* y, int64_t ldy,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* The per-core sums of a CoreDiffusion call ([rows, K, d_in] fp32) live in the workspace between its two kernels.  When all
+ * rows would need more than `bytes` (default 8 GiB; 0 restores it) the layer is evaluated in row chunks — whole waves of the
+ * persistent sequence kernel — and the workspace queries return the bounded size (BASELINE.json configs[4]: 5 M nodes x K 20 x
+ * 256-d would need 102 GB otherwise).  Results do not depend on the chunking.  Process-wide setting. */
+int ctgcn_set_workspace_cap(size_t bytes);
+
 /* Same layer with the snapshot exchange of CTGCN.forward (models.py:248) fused into the epilogue: output row r is stored
  * into the buffer of the node slice that owns it (n_slices balanced contiguous slices of the n_rows nodes, the first
  * n_rows % n_slices of them one row longer) at
