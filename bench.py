@@ -37,6 +37,10 @@ CONFIGS = {
     # BASELINE.json configs[1]
     "cfg2": dict(kind="er", n=100_000, m=1_000_000, K=5, T=8, D=128,
                  name="synthetic ER 100K nodes / 1M edges, K=5 cores, T=8 snapshots, 128-d"),
+    # reduced stand-in of BASELINE.json configs[4] (power-law 5M / 50M, K=20, T=16, 256-d on 8 GPUs): same generator, K and
+    # width at 1/5 of the nodes and 2 snapshots — exercises the 256-d (fp32 SIMT) kernels and the row-chunked CoreDiffusion
+    "cfg5s": dict(kind="powerlaw", n=1_000_000, m=10_000_000, K=20, T=2, D=256, levels="loader",
+                  name="synthetic power-law (Chung-Lu, exponent 2.3) 1M nodes / 10M edges, cores 20..1, T=2 snapshots, 256-d"),
     "tiny": dict(kind="er", n=4_000, m=30_000, K=4, T=8, D=128, name="tiny ER smoke workload"),
 }
 
@@ -106,7 +110,7 @@ def cpu_reference_sample(cfg, seconds_budget=25.0):
 
     n = min(cfg["n"], 100_000)
     m = int(cfg["m"] * (n / cfg["n"]))
-    snap = synth.make_snapshot(cfg["kind"], n, m, cfg["K"], seed=0)
+    snap = synth.make_snapshot(cfg["kind"], n, m, cfg["K"], seed=0, levels=cfg.get("levels", "top"))
     adj = snap.coo_list("cpu")
     d = cfg["D"]
     x = synth.features(n, d, 1000)
@@ -226,7 +230,7 @@ def main():
     t_setup = time.perf_counter()
     plans, x_host, x_dev, stats = [None] * T, [None] * T, [None] * T, {}
     for t in owned:
-        snap = synth.make_snapshot(cfg["kind"], n, cfg["m"], K, seed=t)
+        snap = synth.make_snapshot(cfg["kind"], n, cfg["m"], K, seed=t, levels=cfg.get("levels", "top"))
         plans[t] = snap.plan(dev)
         x_host[t] = synth.features(n, d, 1000 + t).pin_memory()
         x_dev[t] = x_host[t].to(dev)
@@ -378,7 +382,7 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["name"], "config": args.config, "parallelism": f"snapshot-parallel x{world}, exchange={args.exchange}",
-                   "layers": "MLP 1x(128->128,'L') + CDN 1 layer + temporal GRU", "edges_aggregated_per_step": e_agg,
+                   "layers": f"MLP 1x({d}->{d},'L') + CDN 1 layer + temporal GRU", "edges_aggregated_per_step": e_agg,
                    "union_entries_total": entries_total, "cores_per_snapshot": [s["k"] for s in stats.values()],
                    "l2": "per-step inputs (features + graph plans + per-core sums) exceed the 126 MB L2 several times over; no flush",
                    "gru_impl": args.gru_impl, "setup_s": round(setup_s, 1)},

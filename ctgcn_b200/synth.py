@@ -160,7 +160,10 @@ def snapshot_from_edges(n: int, u: np.ndarray, v: np.ndarray, k: int, weights: n
     return assemble_snapshot(n, u, v, w, le, levels)
 
 
-def make_snapshot(kind: str, n: int, m: int, k: int, seed: int) -> SnapshotGraph:
+def make_snapshot(kind: str, n: int, m: int, k: int, seed: int, levels: str = "top") -> SnapshotGraph:
+    """levels='top': the K highest distinct core levels (for ER graphs, whose low cores coincide).
+    levels='loader': what helper.py:51-82 yields with max_core = K — the files of cores 1..K, densest first, i.e. every edge of
+    the graph (a power-law graph's top-K levels hold only its dense nucleus)."""
     rng = np.random.default_rng(seed)
     if kind == "er":
         u, v = er_edges(n, m, rng)
@@ -168,6 +171,11 @@ def make_snapshot(kind: str, n: int, m: int, k: int, seed: int) -> SnapshotGraph
         u, v = powerlaw_edges(n, m, rng)
     else:
         raise ValueError(kind)
+    if levels == "loader":
+        from . import io
+        return io.snapshot_from_graph(n, u, v, None, max_core=k)[0]
+    if levels != "top":
+        raise ValueError(levels)
     return snapshot_from_edges(n, u, v, k)
 
 

@@ -20,7 +20,6 @@ import random
 import shutil
 import sys
 import tempfile
-import types
 import warnings
 
 import numpy as np
@@ -37,30 +36,9 @@ import networkx as nx  # noqa: E402
 import pandas as pd  # noqa: E402
 import torch  # noqa: E402
 
-# ---- compatibility shim for the reference PLUMBING
-np.int = int
-np.float = float
-if not hasattr(nx, "to_scipy_sparse_matrix"):
-    nx.to_scipy_sparse_matrix = lambda g, nodelist=None, **kw: sp.csr_matrix(nx.to_scipy_sparse_array(g, nodelist=nodelist, **kw))
-if not hasattr(pd.DataFrame, "applymap"):
-    pd.DataFrame.applymap = pd.DataFrame.map
+from oracle import ref_compat  # noqa: E402
 
-
-class _Stub(types.ModuleType):
-    """Stands in for torch_geometric / torch_scatter, which train.get_gnn_model imports unconditionally (train.py:93-100)
-    for the baseline models; none of them is instantiated here."""
-    __path__ = []
-
-    def __getattr__(self, name):
-        if name.startswith("__"):
-            raise AttributeError(name)
-        return type(name, (torch.nn.Module,), {})
-
-
-for mod in ("torch_geometric", "torch_geometric.nn", "torch_geometric.nn.conv", "torch_geometric.nn.inits", "torch_geometric.utils",
-            "torch_geometric.nn.conv.gcn_conv", "torch_geometric.data", "torch_scatter", "torch_sparse", "torch_cluster"):
-    sys.modules.setdefault(mod, _Stub(mod))
-
+ref_compat.apply()
 from oracle import cases, oracle_np  # noqa: E402
 
 SNAPSHOT = "2004-04.csv"
