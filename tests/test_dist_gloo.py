@@ -51,3 +51,68 @@ def test_exchange_world2(mode, T, n):
         assert ws == 2, ws
         assert ok1, f"rank {rank}: exchange result differs from the single-process stack ({mode})"
         assert ok2, f"rank {rank}: gathered output differs"
+
+
+def _model_worker(rank, world, port, name, mode, q):
+    """The whole snapshot-parallel CTGCN.forward (ownership t mod G, exchange, node-sliced temporal GRU, output gather) on
+    CPU/gloo, with the CUDA entry points replaced by the oracle-backed stand-in (tests/fake_backend.py)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import numpy as np
+        import fake_backend
+        import grad_checks
+        from oracle import cases
+
+        class _Patch:
+            def setattr(self, obj, attr, value):
+                setattr(obj, attr, value)
+
+        pkg = fake_backend.install(_Patch())
+        c = cases.load_case(name)
+        m = c["meta"]
+        model = grad_checks.build_model(pkg, m, "cpu")
+        model.load_state_dict(grad_checks.tsd(c["sd"]), strict=True)
+        model.exchange = mode
+        xs, adj = grad_checks.model_inputs(c, "cpu")
+        owned = set(range(rank, m["T"], world))
+        xs = [x if t in owned else None for t, x in enumerate(xs)]          # other ranks' snapshots are never touched
+        adj = [a if t in owned else None for t, a in enumerate(adj)]
+        model.node_num = m["n"]
+        res = model(xs, adj)
+        out, trans = res if m["model_type"] == "S" else (res, None)
+        err = cases.relerr(out.detach().numpy()[:, ::m["row_stride"]], c["expected"]["y"])
+        ok_trans = trans is None or all((t is not None) == (i in owned) for i, t in enumerate(trans))
+        raised = False
+        try:
+            out.sum().backward()
+        except NotImplementedError:
+            raised = True                                                    # sharded forward is inference-only, loudly
+        q.put((rank, err, tuple(out.shape), ok_trans, raised))
+    except Exception as exc:
+        import traceback
+        q.put((rank, repr(exc) + traceback.format_exc(), None, False, False))
+    finally:
+        td.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,mode", [("ctgcn_C_T3", "all_to_all"), ("ctgcn_S_T3", "all_gather"), ("ctgcn_C_T1", "all_to_all")])
+def test_sharded_forward_world2(name, mode, lib):
+    from oracle import cases
+    m = cases.load_meta(name)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29950 + (os.getpid() + len(name) * 3 + (0 if mode == "all_to_all" else 17) + m["T"]) % 40
+    procs = [ctx.Process(target=_model_worker, args=(r, 2, port, name, mode, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, err, shape, ok_trans, raised in res:
+        assert shape is not None, f"rank {rank}: {err}"
+        assert shape == (m["T"], m["n"], m["d_out"]), shape
+        assert err < 5e-6, (rank, err)
+        assert ok_trans and raised
