@@ -37,6 +37,18 @@ def test_argument_validation_without_gpu(lib):
     assert L.ctgcn_linear_workspace_bytes(10, 20) >= 800
     assert L.ctgcn_cumspmm_fwd(None, None, 0, 4, None, None) == lib.EINVAL
     assert L.ctgcn_plan_destroy(None) == 0
+    # entry points added for rnn_type / autograd / chunking: argument checks happen before any CUDA call
+    assert L.ctgcn_cumspmm_fwd_ex(None, None, 0, 4, 0, None, None) == lib.EINVAL
+    assert L.ctgcn_cumspmm_bwd(None, None, 4, None, 4, None, 0, None) == lib.EINVAL
+    assert L.ctgcn_cumspmm_bwd_workspace_bytes(None, 4) == 0
+    assert L.ctgcn_rnn_workspace_bytes(lib.CELL_LSTM, 128, 128) == 4 * 128 * 256 * 4         # k-major fp32 copies of both matrices
+    assert L.ctgcn_rnn_workspace_bytes(lib.CELL_GRU, 128, 128) == L.ctgcn_gru_workspace_bytes(128, 128)
+    assert L.ctgcn_rnn_workspace_bytes(7, 128, 128) == 0
+    assert L.ctgcn_rnn_seq_fwd(7, None, 0, 0, 0, 1, 1, 1, None, None, None, None, None, None, 1e-5, 0, None, 0, 0, None, 0, None) == lib.EINVAL
+    assert "unknown cell" in lib.last_error()
+    assert L.ctgcn_core_diffusion_rnn_fwd(None, 0, None, 0, 1, 1, None, None, None, None, None, None, 1e-5, None, 0, None, 0, 0, 0,
+                                          None, 0, None) == lib.EINVAL
+    assert L.ctgcn_set_workspace_cap(1 << 20) == 0 and L.ctgcn_set_workspace_cap(0) == 0
 
 
 def test_kcore_numbers_match_networkx(lib):
