@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from . import _lib, ops
 from . import autograd as _ag
-from .layers import CoreDiffusion, MLP, _guard
+from .layers import CoreDiffusion, MLP
 from . import dist as _dist
 
 

@@ -32,7 +32,6 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, REF)
 warnings.filterwarnings("ignore")
 
-import networkx as nx  # noqa: E402
 import pandas as pd  # noqa: E402
 import torch  # noqa: E402
 

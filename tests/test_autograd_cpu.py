@@ -10,7 +10,7 @@ import pytest
 import torch
 import torch.nn as nn
 
-from oracle import cases, oracle_torch
+from oracle import cases
 
 GRAD_TOL = 2e-5
 

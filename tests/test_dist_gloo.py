@@ -61,7 +61,6 @@ def _model_worker(rank, world, port, name, mode, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     td.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        import numpy as np
         import fake_backend
         import grad_checks
         from oracle import cases

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import cases, oracle_np
-from test_parity_gpu import close, coo, tsd, xin
+from test_parity_gpu import close, coo, tsd
 
 pytestmark = pytest.mark.gpu
 
