@@ -56,6 +56,7 @@ SIGNATURES = {
     "ctgcn_rnn_seq_fwd": (C.c_int, [_i32, _p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _f32, _i32, _p, _i64,
                                     _i64, _p, _sz, _p]),
     "ctgcn_set_gru_impl": (C.c_int, [_i32]),
+    "ctgcn_set_coop_mode": (C.c_int, [_i32]),
     "ctgcn_debug_gru_trace": (C.c_int, [_p]),
     "ctgcn_selftest_umma": (C.c_int, [_p, _p, _p, _p, _p, _p, _sz, _p]),
     "ctgcn_core_diffusion_workspace_bytes": (_sz, [_p, _i32, _i32]),
@@ -108,6 +109,11 @@ def prof_collect(reset: bool = True) -> dict:
 def set_workspace_cap(nbytes: int) -> None:
     """Bound on the per-core-sums buffer of one CoreDiffusion call (0 = default 8 GiB); larger layers run in row chunks."""
     check(lib.ctgcn_set_workspace_cap(int(nbytes)), "ctgcn_set_workspace_cap")
+
+
+def set_coop_mode(on: bool) -> None:
+    """EXPERIMENTAL: reduced-register kernel variants for SpMM / GRU co-residency (see csrc/gru_tc.cu)."""
+    check(lib.ctgcn_set_coop_mode(1 if on else 0), "ctgcn_set_coop_mode")
 
 
 def set_gru_impl(impl: int) -> None:

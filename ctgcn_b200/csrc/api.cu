@@ -108,6 +108,14 @@ extern "C" int ctgcn_prof_collect(double* ms, int64_t* counts, int reset) {
 
 namespace ctgcn {
 void set_gru_trace(long long* buf);
+void set_coop_mode(int on);
+int coop_mode();
+size_t gru_tc_coop_scratch_bytes();
+}
+// EXPERIMENTAL: co-resident kernel variants (gru_tc_coop_kernel + the 64-register SpMM), see gru_tc.cu.  Default off.
+extern "C" int ctgcn_set_coop_mode(int on) {
+    set_coop_mode(on);
+    return CTGCN_OK;
 }
 extern "C" int ctgcn_debug_gru_trace(int64_t* device_buf) {
     set_gru_trace(reinterpret_cast<long long*>(device_buf));
@@ -159,7 +167,9 @@ static int cell_gates(int cell) { return cell == CTGCN_CELL_LSTM ? 4 : 3; }
 static size_t rnn_ws_simt(int cell, int d_in, int h) {
     return align_up((size_t)cell_gates(cell) * h * (d_in + h) * sizeof(float), 256);
 }
-static size_t gru_ws_tc(int d_in, int h) { return align_up((size_t)3 * h * (d_in + h) * 2 * sizeof(uint16_t), 256) + 4096; }
+static size_t gru_ws_tc(int d_in, int h) {   // packed bf16 hi|lo weights + biases (+ the Σh scratch of the co-resident variant)
+    return align_up((size_t)3 * h * (d_in + h) * 2 * sizeof(uint16_t), 256) + 4096 + (coop_mode() ? gru_tc_coop_scratch_bytes() : 0);
+}
 
 extern "C" size_t ctgcn_rnn_workspace_bytes(int cell, int d_in, int h) {
     if (d_in <= 0 || h <= 0 || (cell != CTGCN_CELL_GRU && cell != CTGCN_CELL_LSTM)) return 0;

@@ -125,6 +125,7 @@ struct Params {
     RowScatter sc;      // SUM_LN only: rows go to their node slice's buffer (fused snapshot exchange)
     int num_tiles;
     long long* trace;   // optional [24 events][64 steps] clock64 stamps of block 0 (ctgcn_debug_gru_trace), else NULL
+    float* sumh_scratch;   // gru_tc_coop_kernel only: [grid][TILE_M * H] fp32
 };
 
 // debug timeline: event e of global step gs of block 0
@@ -588,6 +589,413 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
     if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// EXPERIMENTAL (round-2 groundwork, selected by ctgcn_set_coop_mode(1), SUM_LN only; not measured yet).
+// Same pipeline as gru_tc_kernel with a smaller register footprint, so that one 256-thread block of the NEXT snapshot's
+// cumulative SpMM (HBM-bound, no shared memory) can be co-resident on every SM while this kernel runs (tensor/MUFU-bound):
+//   * Σ_s h_s is not held in 64 registers per gate thread but in an L2-resident scratch (64 KB per CTA, every element has
+//     exactly one owner thread: plain read-modify-write with .cg accesses, loaded at the start of an 8-feature pass and
+//     stored at its end) → gate warps 168 → 104 registers;
+//   * the kernel is launched with 96 registers per thread (49 152 of the SM's 65 536; setmaxnreg: warps 0-3 56, loaders 112,
+//     gate warps 104 = 48 128), which leaves 16 384 registers = 256 threads × 64 for the co-resident SpMM block.
+__global__ void __maxnreg__(96) gru_tc_coop_kernel(const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = sbase + SM_BAR;
+    auto bar = [&](int i) { return bar0 + 8u * i; };
+    const int cpx = chunks_per_part(p.d_in);   // weight chunks of one half of the input part
+    constexpr int cph = chunks_per_part(H);    // … of the recurrent part
+    const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar(BAR_W_FULL + s), 1);
+            mbar_init(bar(BAR_W_EMPTY + s), 1);
+        }
+        mbar_init(bar(BAR_U_READY), NUM_LOADER_WARPS);
+        mbar_init(bar(BAR_U_FREE), 1);
+        mbar_init(bar(BAR_H_READY), NUM_WORKER_WARPS);
+        mbar_init(bar(BAR_ACC_FULL0), 1);
+        mbar_init(bar(BAR_ACC_FULL1), 1);
+        mbar_init(bar(BAR_ACC_FREE0), NUM_WORKER_WARPS);
+        mbar_init(bar(BAR_ACC_FREE1), NUM_WORKER_WARPS);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < 4 * H; i += THREADS) reinterpret_cast<float*>(smem + SM_BIAS)[i] = p.bias4[i];
+    for (int i = threadIdx.x; i < H; i += THREADS) {
+        reinterpret_cast<float*>(smem + SM_LN)[i] = p.ln_w[i];
+        reinterpret_cast<float*>(smem + SM_LN)[H + i] = p.ln_b[i];
+    }
+    if (warp == 1) tmem_alloc(sbase + SM_TMEM_PTR, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM_PTR);
+
+    // 512 threads start with 96 registers each: every role branch starts with its warpgroup's setmaxnreg
+    // (warps 0-3: 56, loaders 4-7: 112, workers 8-15: 104)
+    if (warp == 0) {
+        // ===================================================== weight producer
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            const int nx = 2 * cpx;
+            for (int t = 0; t < my_tiles; ++t) {
+                for (int i = 0; i < p.steps; ++i) {
+                    // consumption order of the MMA issuer: X half0, [H half0], X half1, [H half1]
+                    // (packed order is X half0, X half1, H half0, H half1)
+                    for (int seg = 0; seg < 4; ++seg) {
+                        const bool rec = seg & 1;
+                        if (rec && i == 0) continue;
+                        const int half = seg >> 1;
+                        const int first = rec ? nx + half * cph : half * cpx;
+                        const int count = rec ? cph : cpx;
+                        for (int c = first; c < first + count; ++c) {
+                            mbar_wait(bar(BAR_W_EMPTY + stage), phase ^ 1);
+                            mbar_expect_tx(bar(BAR_W_FULL + stage), CHUNK_BYTES);
+                            bulk_g2s(sbase + SM_W + stage * CHUNK_BYTES, p.packed + (size_t)c * CHUNK_BYTES, CHUNK_BYTES,
+                                     bar(BAR_W_FULL + stage));
+                            if (++stage == STAGES) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        // All 32 lanes run the (warp-uniform) control flow and the barrier waits; one elected lane issues.
+        {
+            uint32_t stage = 0, phase = 0, gs = 0;
+            const uint32_t u_desc = desc_lo(sbase + SM_U, TILE_M * 16), h_desc = desc_lo(sbase + SM_H, TILE_M * 16);
+            // one part = one half (64 hidden features) of the input (A = U) or recurrent (A = h) contribution
+            auto run_part = [&](uint32_t a_desc, int ktot, int half, bool recurrent) {
+                const uint32_t d = tmem + half * 256 + (recurrent ? COL_R : COL_IN);
+                for (int kc = 0; kc < ktot / CHUNK_K; ++kc) {
+                    mbar_wait(bar(BAR_W_FULL + stage), phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        issue_chunk(a_desc + kc * (CHUNK_K / 8) * ((TILE_M * 16) >> 4),
+                                    desc_lo(sbase + SM_W + stage * CHUNK_BYTES, CHUNK_ROWS * 16), d, !recurrent && kc == 0,
+                                    recurrent && kc == 0);
+                        umma_commit(bar(BAR_W_EMPTY + stage));
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            };
+            auto commit = [&](int b) {
+                if (elect_one()) umma_commit(bar(b));
+                __syncwarp();
+            };
+            for (int t = 0; t < my_tiles; ++t) {
+                for (int i = 0; i < p.steps; ++i, ++gs) {
+                    const uint32_t par = gs & 1;
+                    if (lane == 0) GRU_TRACE(0, gs);
+                    mbar_wait(bar(BAR_U_READY), par);
+                    mbar_wait(bar(BAR_ACC_FREE0), par ^ 1);
+                    tc_fence_after();
+                    if (lane == 0) GRU_TRACE(1, gs);
+                    run_part(u_desc, p.d_in, 0, false);
+                    if (lane == 0) GRU_TRACE(2, gs);
+                    if (i == 0) {
+                        commit(BAR_ACC_FULL0);
+                    } else {
+                        // the recurrence h_{i-1} → gates → h_i is the critical chain: the first half's recurrent part
+                        // goes ahead of the second half's input part (same chunk order in the producer)
+                        mbar_wait(bar(BAR_H_READY), par ^ 1);
+                        tc_fence_after();
+                        if (lane == 0) GRU_TRACE(3, gs);
+                        run_part(h_desc, H, 0, true);
+                        commit(BAR_ACC_FULL0);
+                        if (lane == 0) GRU_TRACE(4, gs);
+                    }
+                    mbar_wait(bar(BAR_ACC_FREE1), par ^ 1);
+                    tc_fence_after();
+                    if (lane == 0) GRU_TRACE(5, gs);
+                    run_part(u_desc, p.d_in, 1, false);
+                    commit(BAR_U_FREE);
+                    if (lane == 0) GRU_TRACE(6, gs);
+                    if (i > 0) run_part(h_desc, H, 1, true);
+                    commit(BAR_ACC_FULL1);
+                    if (lane == 0) GRU_TRACE(7, gs);
+                }
+            }
+        }
+    } else if (warp < FIRST_WORKER_WARP) {
+        // ===================================================== input loaders (warps 4-7; warps 2-3 idle)
+        if (warp < FIRST_LOADER_WARP) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        } else {
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+            // A warp owns 32 tile rows.  Per load instruction its lanes cover 8 rows × 4 k-blocks (r = lane%8, c = lane/8):
+            // 128 contiguous bytes per row (8 L1 wavefronts instead of 32 for a row-per-lane mapping) and the 16-byte
+            // shared-memory stores of one 8-lane phase hit 8 consecutive rows of one k-block (conflict-free).
+            const int r8 = lane & 7, c4 = lane >> 3;
+            const int row_base = 32 * (warp - FIRST_LOADER_WARP);
+            uint8_t* u_hi = smem + SM_U;
+            const int nkg = p.d_in / 32;             // k-groups of 4 k-blocks
+            const int nit = 4 * nkg;                 // (row-group, k-group) iterations per step: 16 for d_in = 128
+            uint32_t gs = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                const int64_t tile_row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M;
+                for (int i = 0; i < p.steps; ++i, ++gs) {
+                    const float* base = p.seq + (int64_t)i * p.sss;
+                    float4 v[16];
+                    auto load_batch = [&](int it0) {   // 8 iterations = 16 LDG.128 in flight per lane
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int it = it0 + u, rg = it & 3, kg = it >> 2;
+                            const int64_t srow = tile_row0 + row_base + 8 * rg + r8;
+                            if (srow < p.n) {
+                                const float* src = base + srow * p.srs + (4 * kg + c4) * 8;
+                                v[2 * u] = __ldg(reinterpret_cast<const float4*>(src));
+                                v[2 * u + 1] = __ldg(reinterpret_cast<const float4*>(src + 4));
+                            } else {
+                                v[2 * u] = v[2 * u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                        }
+                    };
+                    auto store_batch = [&](int it0) {  // fp32 → bf16 hi/lo planes, 8 k-elements (16 B) per store
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int it = it0 + u, rg = it & 3, kg = it >> 2;
+                            const int m = row_base + 8 * rg + r8, kb = 4 * kg + c4;
+                            const float f8[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w,
+                                                 v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
+                            uint4 hi, lo;
+                            split8(f8, hi, lo);
+#ifdef GRU_EXP_NO_U_STORE
+                            if (f8[0] != 12345.678f) continue;   // timing experiment
+#endif
+                            *reinterpret_cast<uint4*>(u_hi + kb * (TILE_M * 16) + m * 16) = hi;
+                            *reinterpret_cast<uint4*>(u_hi + A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
+                        }
+                    };
+                    load_batch(0);   // global loads are issued BEFORE the buffer is free: their latency is off the loop
+                    // the input part of the previous step's MMAs must have released the single U buffer
+                    mbar_wait(bar(BAR_U_FREE), (gs & 1) ^ 1);
+                    if (threadIdx.x == FIRST_LOADER_WARP * 32) GRU_TRACE(13, gs);
+                    store_batch(0);
+                    for (int it0 = 8; it0 < nit; it0 += 8) {
+                        load_batch(it0);
+                        store_batch(it0);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(BAR_U_READY));
+                    if (threadIdx.x == FIRST_LOADER_WARP * 32) GRU_TRACE(14, gs);
+                }
+            }
+        }
+    } else {
+        // ===================================================== workers (warps 8-15): gate math, h, Σh, LayerNorm
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        // Σh scratch of this CTA: [16 feature blocks of 8][128 rows][8 floats] → a warp's 32 rows are 1 KB contiguous
+        float* const sumh = p.sumh_scratch + (size_t)blockIdx.x * (TILE_M * H);
+        const int ww = warp - FIRST_WORKER_WARP;
+        const int q = warp & 3;          // TMEM lane quarter this warp may access
+        const int ch = ww >> 2;          // which 32 of a half's 64 features this thread owns
+        const int m = 32 * q + lane;     // row inside the tile
+        const uint32_t tmem_lane = tmem + ((uint32_t)(32 * q) << 16);
+        const float* bias = reinterpret_cast<const float*>(smem + SM_BIAS);
+        const float* lnw = reinterpret_cast<const float*>(smem + SM_LN);
+        float* red = reinterpret_cast<float*>(smem + SM_RED);
+        uint8_t* h_hi = smem + SM_H;
+        uint32_t gs = 0;
+
+        // SUM_LN result of a tile: normalised rows are staged in the (now idle) h buffer with a 16-byte XOR swizzle and
+        // written out one whole 512-byte row per warp instruction — to y, or straight into the owning node slice's
+        // (peer) buffer: NVLink wants full-line stores, not 32 scattered 16-byte pieces per instruction.
+        auto layer_norm_store_rows = [&](const float (&v)[64], int64_t tile_row0) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) s += v[j];
+            red[ch * TILE_M + m] = s;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float mean = (s + red[(ch ^ 1) * TILE_M + m]) * (1.f / H);
+            float sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const float dlt = v[j] - mean;
+                sq = fmaf(dlt, dlt, sq);
+            }
+            red[2 * TILE_M + ch * TILE_M + m] = sq;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float rstd = rsqrtf((sq + red[2 * TILE_M + (ch ^ 1) * TILE_M + m]) * (1.f / H) + p.eps);
+            float* stage = reinterpret_cast<float*>(smem + SM_H);     // [128 rows][32 chunks of 4 floats], chunk c of row r at c ^ (r & 31)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                for (int j4 = 0; j4 < 32; j4 += 4) {
+                    const int f = hf * 64 + ch * 32 + j4;
+                    float4 o;
+                    o.x = (v[hf * 32 + j4 + 0] - mean) * rstd * lnw[f + 0] + lnw[H + f + 0];
+                    o.y = (v[hf * 32 + j4 + 1] - mean) * rstd * lnw[f + 1] + lnw[H + f + 1];
+                    o.z = (v[hf * 32 + j4 + 2] - mean) * rstd * lnw[f + 2] + lnw[H + f + 2];
+                    o.w = (v[hf * 32 + j4 + 3] - mean) * rstd * lnw[f + 3] + lnw[H + f + 3];
+                    *reinterpret_cast<float4*>(stage + m * H + (((f >> 2) ^ (m & 31)) << 2)) = o;
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int rr = 0; rr < TILE_M / NUM_WORKER_WARPS; ++rr) {
+                const int r = ww * (TILE_M / NUM_WORKER_WARPS) + rr;
+                const int64_t grow = tile_row0 + r;
+                if (grow >= p.n) break;   // warp-uniform
+                const float4 o = *reinterpret_cast<const float4*>(stage + r * H + ((lane ^ (r & 31)) << 2));
+                float* dst = p.sc.slices ? p.sc.row_ptr(grow) : p.y + grow * p.yrs;
+                *reinterpret_cast<float4*>(dst + 4 * lane) = o;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // the staging area is h again from the next tile's first step on
+        };
+
+        for (int t = 0; t < my_tiles; ++t) {
+            const int64_t row = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + m;
+
+            for (int i = 0; i < p.steps; ++i, ++gs) {
+                const uint32_t par = gs & 1;
+                // gates, one half (64 hidden features) at a time; this thread owns 32 of them, 8 per pass
+                float h0[32];   // first half of h_i, published only when no MMA reads h_{i-1} any more
+                auto put_h8 = [&](const float (&f8)[8], int f) {
+#ifdef GRU_EXP_NO_H_STORE
+                    if (f8[0] != 12345.678f) return;   // timing experiment: never true in practice
+#endif
+                    uint4 hi, lo;
+                    split8(f8, hi, lo);
+                    const int kb = f >> 3;
+                    *reinterpret_cast<uint4*>(h_hi + kb * (TILE_M * 16) + m * 16) = hi;
+                    *reinterpret_cast<uint4*>(h_hi + A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
+                };
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    if (threadIdx.x == FIRST_WORKER_WARP * 32) GRU_TRACE(8 + 2 * hf, gs);
+                    mbar_wait(bar(BAR_ACC_FULL0 + hf), par);
+                    tc_fence_after();
+                    if (threadIdx.x == FIRST_WORKER_WARP * 32) GRU_TRACE(9 + 2 * hf, gs);
+#pragma unroll
+                    for (int sub = 0; sub < 4; ++sub) {
+                        const int f0 = hf * 64 + ch * 32 + sub * 8;             // first of 8 features
+                        const uint32_t col = hf * 256 + ch * 32 + sub * 8;      // + gate block
+                        float gr[8], gz[8], gi[8], gh[8], hold[8];
+                        float* const sp = sumh + ((size_t)(f0 >> 3) * TILE_M + m) * 8;
+                        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+                        if (i > 0) {          // issued first: the L2 round trip hides under the TMEM loads and the gate math
+                            s0 = __ldcg(reinterpret_cast<const float4*>(sp));
+                            s1 = __ldcg(reinterpret_cast<const float4*>(sp) + 1);
+                        }
+                        tmem_ld8(tmem_lane + col + COL_R, gr);
+                        tmem_ld8(tmem_lane + col + COL_Z, gz);
+                        tmem_ld8(tmem_lane + col + COL_IN, gi);
+                        if (i > 0) {
+                            tmem_ld8(tmem_lane + col + COL_HN, gh);
+                            const int kb = f0 >> 3;
+                            const uint4 hi = *reinterpret_cast<const uint4*>(h_hi + kb * (TILE_M * 16) + m * 16);
+                            const uint4 lo = *reinterpret_cast<const uint4*>(h_hi + A_PLANE + kb * (TILE_M * 16) + m * 16);
+                            join8(hi, lo, hold);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) gh[j] = hold[j] = 0.f;
+                        }
+                        tmem_ld_wait();
+                        // Gate math written stage by stage over the 8 features so that the 8 dependent chains
+                        // (ex2 → rcp → ex2 → rcp) are interleaved.  Pre-activations are pre-scaled (pack_weights_kernel):
+                        // sigmoid(a) = 1/(1 + 2^a'), tanh(s) = 1 − 2/(1 + 2^s'); one reciprocal serves r and z.
+                        float hn8[8], ea[8], eb[8], zz[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            ea[j] = gr[j] + bias[f0 + j];
+                            eb[j] = gz[j] + bias[H + f0 + j];
+                            gi[j] += bias[2 * H + f0 + j];
+                            gh[j] += bias[3 * H + f0 + j];
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            ea[j] = ex2_approx(ea[j]);
+                            eb[j] = ex2_approx(eb[j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            ea[j] = 1.f + fminf(ea[j], 1e18f);     // clamped so that the product below stays finite
+                            eb[j] = 1.f + fminf(eb[j], 1e18f);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) hn8[j] = rcp_approx(ea[j] * eb[j]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            zz[j] = hn8[j] * ea[j];                                          // z
+                            gi[j] = fmaf(hn8[j] * eb[j], gh[j], gi[j]);                      // W_in x + b_in + r ⊙ (W_hn h + b_hn)
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) gi[j] = ex2_approx(gi[j]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) gi[j] = rcp_approx(1.f + gi[j]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float nn = fmaf(-2.f, gi[j], 1.f);                         // tanh
+                            hn8[j] = fmaf(zz[j], hold[j] - nn, nn);                          // (1 − z) n + z h
+                        }
+                        if (hf == 0) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) h0[sub * 8 + j] = hn8[j];
+                        } else {
+                            // every MMA that reads h_{i-1} has completed (acc1 full): h may be overwritten in place.
+                            // The held-back first half is published piecewise here so that its ALU work hides
+                            // under the MUFU latency of this pass.
+                            const float f8[8] = {h0[sub * 8], h0[sub * 8 + 1], h0[sub * 8 + 2], h0[sub * 8 + 3],
+                                                 h0[sub * 8 + 4], h0[sub * 8 + 5], h0[sub * 8 + 6], h0[sub * 8 + 7]};
+                            put_h8(f8, ch * 32 + sub * 8);
+                            put_h8(hn8, f0);
+                        }
+                        s0.x += hn8[0];
+                        s0.y += hn8[1];
+                        s0.z += hn8[2];
+                        s0.w += hn8[3];
+                        s1.x += hn8[4];
+                        s1.y += hn8[5];
+                        s1.z += hn8[6];
+                        s1.w += hn8[7];
+                        __stcg(reinterpret_cast<float4*>(sp), s0);
+                        __stcg(reinterpret_cast<float4*>(sp) + 1, s1);
+                        if (threadIdx.x == FIRST_WORKER_WARP * 32) GRU_TRACE(16 + hf * 4 + sub, gs);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(BAR_ACC_FREE0 + hf));
+                }
+                // h_i is complete in shared memory: the next step's recurrent MMAs may read it
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(BAR_H_READY));
+                if (threadIdx.x == FIRST_WORKER_WARP * 32) GRU_TRACE(12, gs);
+            }
+            {
+                float acc_out[64];   // Σ_s h_s of this thread's 64 features, read back once per tile (own writes: program order)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                    for (int sub = 0; sub < 4; ++sub) {
+                        const float* sp = sumh + ((size_t)((hf * 64 + ch * 32 + sub * 8) >> 3) * TILE_M + m) * 8;
+                        const float4 a0 = __ldcg(reinterpret_cast<const float4*>(sp)), a1 = __ldcg(reinterpret_cast<const float4*>(sp) + 1);
+                        float* o = acc_out + hf * 32 + sub * 8;
+                        o[0] = a0.x, o[1] = a0.y, o[2] = a0.z, o[3] = a0.w, o[4] = a1.x, o[5] = a1.y, o[6] = a1.z, o[7] = a1.w;
+                    }
+                layer_norm_store_rows(acc_out, row - m);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+
 // ------------------------------------------------------------------------------------------------ self test
 // One half-step of a GRU cell's pre-activations for d_in = 64 through exactly the packer, chunk images, bulk copies,
 // descriptors, split-bf16 MMAs (incl. the split-first recurrent MMA) and TMEM loads of the GRU kernel:
@@ -671,6 +1079,11 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
 
 static long long* g_gru_trace = nullptr;
 void set_gru_trace(long long* buf) { g_gru_trace = buf; }
+static std::atomic<int> g_coop{0};
+void set_coop_mode(int on) { g_coop.store(on ? 1 : 0); }
+int coop_mode() { return g_coop.load(); }
+// Σh scratch of the co-resident variant: one [TILE_M, H] fp32 tile per CTA of the persistent grid (≤ 256 SMs)
+size_t gru_tc_coop_scratch_bytes() { return (size_t)256 * TILE_M * H * sizeof(float); }
 
 // returns 0 = done, <0 = error, 1 = shape not supported by this path
 int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* w_ih,
@@ -685,6 +1098,8 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
     CTGCN_REQUIRE(ws && ws_bytes >= packed_bytes + 4 * H * sizeof(float), "gru_tc: workspace too small");
     uint8_t* packed = (uint8_t*)ws;
     float* bias4 = (float*)(packed + packed_bytes);
+    const size_t scratch_off = align_up(packed_bytes + 4 * H * sizeof(float), 256);
+    const bool coop = g_coop.load() && mode == CTGCN_GRU_SUM_LN && ws_bytes >= scratch_off + gru_tc_coop_scratch_bytes();
     {
         ProfScope prof(PROF_PACK, st);
         const int threads = nchunks * UNITS_PER_PLANE;
@@ -698,6 +1113,7 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
         CTGCN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
         CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_kernel<CTGCN_GRU_SUM_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_kernel<CTGCN_GRU_EACH_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     }
     Params p;
     p.seq = seq;
@@ -717,9 +1133,13 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
     p.sc = sc ? *sc : RowScatter();
     p.num_tiles = (int)((n + TILE_M - 1) / TILE_M);
     p.trace = g_gru_trace;
+    p.sumh_scratch = coop ? (float*)((char*)ws + scratch_off) : nullptr;
     const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
+    CTGCN_REQUIRE(!coop || grid <= 256, "gru_tc: co-resident variant supports at most 256 SMs");
     ProfScope prof(PROF_GRU, st);
-    if (mode == CTGCN_GRU_SUM_LN)
+    if (coop)
+        gru_tc_coop_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p);
+    else if (mode == CTGCN_GRU_SUM_LN)
         gru_tc_kernel<CTGCN_GRU_SUM_LN><<<grid, THREADS, SMEM_BYTES, st>>>(p);
     else
         gru_tc_kernel<CTGCN_GRU_EACH_LN><<<grid, THREADS, SMEM_BYTES, st>>>(p);

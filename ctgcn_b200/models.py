@@ -19,6 +19,7 @@ from . import dist as _dist
 
 
 _copy_streams = {}
+_coop_streams = {}
 
 
 class _HostFeatureStager:
@@ -163,9 +164,62 @@ class CTGCN(nn.Module):
         return ops.rnn_seq(hx, r.weight_ih_l0, r.weight_hh_l0, b_ih, b_hh, self.norm.weight, self.norm.bias, self.norm.eps,
                            _lib.GRU_EACH_LN, out=out, cell=self._cell)
 
+    def _forward_coop(self, x_list, adj_list):
+        """EXPERIMENTAL (self.coop = True; round-2 groundwork, not measured yet): the cumulative SpMM of snapshot t+1 (HBM-bound)
+        runs on the current stream while the core GRU of snapshot t (tensor-bound) runs on a high-priority stream, co-resident
+        on the same SMs (reduced-register kernel variants, ctgcn_set_coop_mode).  Needs one CoreDiffusion layer per snapshot.
+        Same arithmetic as forward(): results are bit-identical.  Timeline on the device:
+            cur:  SpMM(0) lin(1) | SpMM(1) ........ lin(2) | SpMM(2) ........ lin(3) | ...
+            hi :                 | GRU(0) ......          | GRU(1) ......          | ...                       """
+        from .plan import plan_for
+        T = len(x_list)
+        dev = self.norm.weight.device
+        cur = torch.cuda.current_stream(dev)
+        hi = _coop_streams.setdefault(str(dev), torch.cuda.Stream(device=dev, priority=-1))
+        stager = _HostFeatureStager(x_list, range(T), dev)
+        layers = [cdn.diffusion_list[0] for cdn in self.duffision_list]
+        plans = [plan_for(adj_list[t], dev) for t in range(T)]
+        trans_list = [None] * T
+        trans_list[0] = self.mlp_list[0](stager.get(0))
+        n = trans_list[0].shape[0]
+        d_mid = trans_list[0].shape[1]
+        hx = torch.empty(n, T, self.output_dim, dtype=torch.float32, device=dev)
+        ubuf = [torch.empty(n * max(p.k for p in plans) * d_mid, dtype=torch.float32, device=dev) for _ in range(2)]
+        for b in ubuf:
+            b.record_stream(hi)
+        hx.record_stream(hi)
+        gru_done = [None, None]                     # event after the GRU that last read ubuf[b]
+        u = ops.cumspmm(plans[0], trans_list[0], out=ubuf[0])
+        for t in range(T):
+            if t + 1 < T:                           # the next snapshot's MLP goes BEFORE this snapshot's GRU: its CTAs need the
+                trans_list[t + 1] = self.mlp_list[t + 1](stager.get(t + 1))   # whole shared memory and cannot be co-resident
+            ready = torch.cuda.Event()
+            ready.record(cur)                       # U(t) and lin(t+1) are done
+            hi.wait_event(ready)
+            lay = layers[t]
+            w_ih, w_hh, b_ih, b_hh = lay._gru_params()
+            with torch.cuda.stream(hi):
+                ops.rnn_seq(u, w_ih, w_hh, b_ih, b_hh, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN,
+                            out=hx[:, t, :], cell=lay._cell)
+                done = torch.cuda.Event()
+                done.record(hi)
+            gru_done[t & 1] = done
+            if t + 1 < T:
+                b = (t + 1) & 1
+                if gru_done[b] is not None:
+                    cur.wait_event(gru_done[b])     # the GRU that read this buffer two snapshots ago has finished
+                u = ops.cumspmm(plans[t + 1], trans_list[t + 1], out=ubuf[b])          # overlaps GRU(t)
+        cur.wait_event(gru_done[(T - 1) & 1])
+        if T > 1:
+            cur.wait_event(gru_done[(T - 2) & 1])
+        out = self._temporal(hx).transpose(0, 1)
+        return out if self.model_type == 'C' else (out, trans_list)
+
     def forward(self, x_list, adj_list):
         if _dist.world_size() > 1:
             return _dist.ctgcn_forward_sharded(self, x_list, adj_list)
+        if getattr(self, "coop", False) and self.diffusion_num == 1 and not torch.is_grad_enabled():
+            return self._forward_coop(x_list, adj_list)
         T = len(x_list)
         dev = self.norm.weight.device
         hx, trans_list, emb_list = None, [], []

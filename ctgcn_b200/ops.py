@@ -44,12 +44,19 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
-def cumspmm(plan: GraphPlan, x: torch.Tensor, relu: bool = True) -> torch.Tensor:
-    """relu(cumsum_i A_i x) for all K cores → [N, K, D]  (layers.py:41-48); relu=False returns the sums themselves."""
+def cumspmm(plan: GraphPlan, x: torch.Tensor, relu: bool = True, out: torch.Tensor = None) -> torch.Tensor:
+    """relu(cumsum_i A_i x) for all K cores → [N, K, D]  (layers.py:41-48); relu=False returns the sums themselves.
+    `out`: optional contiguous fp32 buffer with at least N·K·D elements (its first N·K·D elements are used)."""
     x = _f32_rows(x, "x")
     if x.shape[0] != plan.n_cols:
         raise _lib.CtgcnError(f"x has {x.shape[0]} rows, the plan expects {plan.n_cols}")
-    u = torch.empty(plan.n_rows, plan.k, x.shape[1], dtype=torch.float32, device=x.device)
+    if out is None:
+        u = torch.empty(plan.n_rows, plan.k, x.shape[1], dtype=torch.float32, device=x.device)
+    else:
+        need = plan.n_rows * plan.k * x.shape[1]
+        if out.dtype != torch.float32 or not out.is_contiguous() or out.numel() < need or out.device != x.device:
+            raise _lib.CtgcnError("out must be a contiguous fp32 buffer on x's device with at least N*K*D elements")
+        u = out.view(-1)[:need].view(plan.n_rows, plan.k, x.shape[1])
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib.ctgcn_cumspmm_fwd_ex(plan.handle, _ptr(x), x.stride(0), x.shape[1], 1 if relu else 0, _ptr(u),
                                                  _stream()), "ctgcn_cumspmm_fwd_ex")

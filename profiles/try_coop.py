@@ -1,0 +1,87 @@
+"""EXPERIMENT (round-2 groundwork, NOT run yet on a GPU): SpMM / GRU co-residency.
+
+    python profiles/try_coop.py [--config cfg2|cfg4] [--iters 10]
+
+1. numerics: the reduced-register kernel variants (ctgcn_set_coop_mode(1): gru_tc_coop_kernel with Σh in an L2 scratch, the
+   64-register SpMM) must give bit-identical results to the default kernels — first on one core-GRU launch, then on the whole
+   CTGCN.forward with model.coop = True (SpMM(t+1) on the current stream under GRU(t) on a high-priority stream);
+2. timing: ms per forward, default vs co-resident, and the per-kernel-class times (ctgcn_prof_*).
+If the GRU launch regresses alone or the overlap does not materialise (block scheduler keeps the kernels apart), check with
+`nsys`-less timeline: CUDA events around each launch on both streams."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+import __graft_entry__
+__graft_entry__.build()
+import bench
+import ctgcn_b200 as pkg
+from ctgcn_b200 import _lib, ops, synth
+
+
+def timed(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="cfg2", choices=sorted(bench.CONFIGS))
+    ap.add_argument("--iters", type=int, default=10)
+    args = ap.parse_args()
+    cfg = bench.CONFIGS[args.config]
+    dev = torch.device("cuda:0")
+    T, n, d, K = cfg["T"], cfg["n"], cfg["D"], cfg["K"]
+    plans = [synth.make_snapshot(cfg["kind"], n, cfg["m"], K, seed=t, levels=cfg.get("levels", "top")).plan(dev) for t in range(T)]
+    xs = [synth.features(n, d, 1000 + t).to(dev) for t in range(T)]
+    torch.manual_seed(0)
+    model = pkg.CTGCN(d, d, d, 1, 1, T).to(dev).eval()
+
+    # ---- 1a. one core-GRU launch: default vs co-resident variant
+    lay = model.duffision_list[0].diffusion_list[0]
+    u = ops.cumspmm(plans[0], xs[0])
+    w = lay._gru_params()
+    ref = ops.rnn_seq(u, *w, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN)
+    t_def = timed(lambda: ops.rnn_seq(u, *w, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN), args.iters)
+    t_spmm_def = timed(lambda: ops.cumspmm(plans[0], xs[0], out=u), args.iters)
+    _lib.set_coop_mode(True)
+    got = ops.rnn_seq(u, *w, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN)
+    t_coop = timed(lambda: ops.rnn_seq(u, *w, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN), args.iters)
+    u2 = ops.cumspmm(plans[0], xs[0])
+    t_spmm_coop = timed(lambda: ops.cumspmm(plans[0], xs[0], out=u2), args.iters)
+    print(f"core GRU launch: default {t_def:.3f} ms, coop variant {t_coop:.3f} ms, bit-identical: {torch.equal(ref, got)}")
+    print(f"SpMM launch:     default {t_spmm_def:.3f} ms, 64-reg variant {t_spmm_coop:.3f} ms, bit-identical: {torch.equal(u, u2)}")
+    _lib.set_coop_mode(False)
+
+    # ---- 1b / 2. whole forward
+    with torch.no_grad():
+        out_ref = model(xs, plans).clone()
+        t_fwd = timed(lambda: model(xs, plans), args.iters)
+        _lib.set_coop_mode(True)
+        model.coop = True
+        out_coop = model(xs, plans).clone()
+        t_fwd_coop = timed(lambda: model(xs, plans), args.iters)
+        _lib.prof_collect(reset=True)
+        _lib.prof_enable(True)
+        model(xs, plans)
+        print("per-class ms of one co-resident forward:", {k: round(v["ms"], 3) for k, v in _lib.prof_collect().items()})
+        _lib.prof_enable(False)
+    print(f"CTGCN.forward {args.config}: default {t_fwd:.2f} ms, co-resident {t_fwd_coop:.2f} ms "
+          f"({t_fwd / t_fwd_coop:.2f}x), bit-identical: {torch.equal(out_ref, out_coop)}")
+    _lib.set_coop_mode(False)
+
+
+if __name__ == "__main__":
+    main()
