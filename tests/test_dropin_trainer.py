@@ -24,7 +24,7 @@ def _run(mode, outdir, method, T, epochs):
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "data", "uci")), reason="needs the reference checkout with its UCI data")
-@pytest.mark.parametrize("method,T", [("CTGCN-C", 2), ("CGCN-C", 1)])
+@pytest.mark.parametrize("method,T", [("CTGCN-C", 2), ("CTGCN-S", 2), ("CGCN-C", 1)])
 def test_reference_trainer_with_swapped_modules(method, T, tmp_path, lib):
     pd = pytest.importorskip("pandas")
     _run("ref", tmp_path / "ref", method, T, 2)
