@@ -179,6 +179,8 @@ def main():
     ap.add_argument("--gru-impl", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "all_to_all", "all_gather", "p2p"])
+    ap.add_argument("--coop", action="store_true",
+                    help="EXPERIMENTAL (unmeasured): SpMM(t+1) co-resident with GRU(t), single GPU only (DESIGN.md §9)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -241,6 +243,9 @@ def main():
     model.gather_output = False      # every rank keeps (and, in e2e, reads back) its node slice of the output
     model.exchange = args.exchange
     model.node_num = n
+    if args.coop:
+        _lib.set_coop_mode(True)
+        model.coop = True
     setup_s = time.perf_counter() - t_setup
 
     def tot(v):
@@ -385,7 +390,7 @@ def main():
                    "layers": f"MLP 1x({d}->{d},'L') + CDN 1 layer + temporal GRU", "edges_aggregated_per_step": e_agg,
                    "union_entries_total": entries_total, "cores_per_snapshot": [s["k"] for s in stats.values()],
                    "l2": "per-step inputs (features + graph plans + per-core sums) exceed the 126 MB L2 several times over; no flush",
-                   "gru_impl": args.gru_impl, "setup_s": round(setup_s, 1)},
+                   "gru_impl": args.gru_impl, "coop": bool(args.coop), "setup_s": round(setup_s, 1)},
         "e2e": {"value": e_agg / (ms_e2e / args.steps * 1e-3), "unit": "edges-aggregated/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": launches_total,
