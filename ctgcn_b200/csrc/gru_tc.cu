@@ -1113,7 +1113,11 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
         CTGCN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
         CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_kernel<CTGCN_GRU_SUM_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_kernel<CTGCN_GRU_EACH_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    }
+    static bool coop_ready = false;      // set up lazily: nothing about the experimental variant can affect the default path
+    if (coop && !coop_ready) {
         CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        coop_ready = true;
     }
     Params p;
     p.seq = seq;
