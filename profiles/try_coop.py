@@ -4,7 +4,8 @@
 
 1. numerics: the reduced-register kernel variants (ctgcn_set_coop_mode(1): gru_tc_coop_kernel with Σh in an L2 scratch, the
    64-register SpMM) must give bit-identical results to the default kernels — first on one core-GRU launch, then on the whole
-   CTGCN.forward with model.coop = True (SpMM(t+1) on the current stream under GRU(t) on a high-priority stream);
+   CTGCN.forward, (a) with the chunk-pipelined CoreDiffusion inside the C-ABI call (SpMM of row chunk c+1 under the GRU of
+   chunk c) and (b) with model.coop = True (SpMM(t+1) on the current stream under GRU(t) on a high-priority stream);
 2. timing: ms per forward, default vs co-resident, and the per-kernel-class times (ctgcn_prof_*).
 If the GRU launch regresses alone or the overlap does not materialise (block scheduler keeps the kernels apart), check with
 `nsys`-less timeline: CUDA events around each launch on both streams."""
@@ -70,6 +71,10 @@ def main():
         out_ref = model(xs, plans).clone()
         t_fwd = timed(lambda: model(xs, plans), args.iters)
         _lib.set_coop_mode(True)
+        out_pipe = model(xs, plans).clone()          # C-ABI level: SpMM(chunk c+1) under GRU(chunk c) inside every CoreDiffusion call
+        t_fwd_pipe = timed(lambda: model(xs, plans), args.iters)
+        print(f"CTGCN.forward {args.config}: default {t_fwd:.2f} ms, chunk-pipelined CoreDiffusion {t_fwd_pipe:.2f} ms "
+              f"({t_fwd / t_fwd_pipe:.2f}x), bit-identical: {torch.equal(out_ref, out_pipe)}")
         model.coop = True
         out_coop = model(xs, plans).clone()
         t_fwd_coop = timed(lambda: model(xs, plans), args.iters)
