@@ -123,8 +123,9 @@ def cpu_reference_sample(cfg, seconds_budget=25.0):
 
     cores = os.cpu_count() or 1
     cand = sorted({c for c in (1, 2, 4, 8, 16, 32, 64, 128, cores) if c <= cores})
-    best, best_thr, spent = None, None, 0.0
+    best, best_thr, spent, tried = None, None, 0.0, []
     for thr in cand:
+        tried.append(thr)
         torch.set_num_threads(thr)
         t0 = time.perf_counter()
         run()                                    # warm-up for this thread count
@@ -138,7 +139,7 @@ def cpu_reference_sample(cfg, seconds_budget=25.0):
         if spent > seconds_budget:
             break
     sample = (f"1 snapshot MLP+CoreDiffusion fwd, {cfg['kind'].upper()} N={n} m={m} K={snap.k} D={d} "
-              f"(E_agg={snap.edges_aggregated}); best of thread counts {cand} = {best_thr} threads on {cores} cores; "
+              f"(E_agg={snap.edges_aggregated}); best of thread counts {tried} = {best_thr} threads on {cores} cores; "
               f"same density/K as the workload" + ("" if n == cfg["n"] else f", node count reduced from {cfg['n']}"))
     return dict(value=snap.edges_aggregated / best, unit="edges-aggregated/s", cores=best_thr, kind="port", sample=sample,
                 seconds=best, host_cores=cores)
