@@ -1,6 +1,7 @@
 """Host-side logic that needs no GPU: synthetic generator vs the reference input contract, sharding helpers,
 module surface (constructor signatures, attribute names, state_dict keys)."""
 import inspect
+import os
 
 import networkx as nx
 import numpy as np
@@ -144,3 +145,33 @@ def test_split_hub_rows_is_a_partition(lib):
             got += seg
         assert got == want, r
     assert split_hub_rows(n, torch.from_numpy(rowptr), torch.from_numpy(col), torch.from_numpy(val), torch.from_numpy(lvl), 100) is None
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under ctgcn_b200/ may import or execute it, and bench.py only in its CPU legs."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "ctgcn_b200")
+    for f in sorted(os.listdir(pkg)):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+            assert "fake_backend" not in src, f
+    bench = open(os.path.join(root, "bench.py")).read()
+    uses = [m.start() for m in re.finditer(r"from oracle import", bench)]
+    assert len(uses) == 1 and bench[:uses[0]].rfind("def cpu_reference_sample") > bench[:uses[0]].rfind("\ndef main")
+
+
+def test_import_without_the_shared_library_fails_loudly(tmp_path):
+    """No CPU / PyTorch fallback: a copy of the package without libctgcn_b200.so cannot be imported."""
+    import shutil
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dst = tmp_path / "ctgcn_b200"
+    dst.mkdir()
+    for f in os.listdir(os.path.join(root, "ctgcn_b200")):
+        if f.endswith(".py"):
+            shutil.copy(os.path.join(root, "ctgcn_b200", f), dst / f)
+    res = subprocess.run([sys.executable, "-c", "import ctgcn_b200"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert res.returncode != 0 and "libctgcn_b200.so not found" in res.stderr and "no CPU/PyTorch fallback" in res.stderr
