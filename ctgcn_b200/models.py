@@ -29,7 +29,9 @@ class _HostFeatureStager:
 
     def __init__(self, x_list, order, dev, depth=2):
         self.x_list, self.order, self.dev, self.depth = x_list, list(order), dev, depth
-        self.stream = _copy_streams.setdefault(str(dev), torch.cuda.Stream(device=dev))
+        if str(dev) not in _copy_streams:            # one copy stream per device, created on first use
+            _copy_streams[str(dev)] = torch.cuda.Stream(device=dev)
+        self.stream = _copy_streams[str(dev)]
         self.pending = {}
         self.next = 0
 
@@ -175,7 +177,9 @@ class CTGCN(nn.Module):
         T = len(x_list)
         dev = self.norm.weight.device
         cur = torch.cuda.current_stream(dev)
-        hi = _coop_streams.setdefault(str(dev), torch.cuda.Stream(device=dev, priority=-1))
+        if str(dev) not in _coop_streams:
+            _coop_streams[str(dev)] = torch.cuda.Stream(device=dev, priority=-1)
+        hi = _coop_streams[str(dev)]
         stager = _HostFeatureStager(x_list, range(T), dev)
         layers = [cdn.diffusion_list[0] for cdn in self.duffision_list]
         plans = [plan_for(adj_list[t], dev) for t in range(T)]
