@@ -111,9 +111,10 @@ def set_workspace_cap(nbytes: int) -> None:
     check(lib.ctgcn_set_workspace_cap(int(nbytes)), "ctgcn_set_workspace_cap")
 
 
-def set_coop_mode(on: bool) -> None:
-    """EXPERIMENTAL: reduced-register kernel variants for SpMM / GRU co-residency (see csrc/gru_tc.cu)."""
-    check(lib.ctgcn_set_coop_mode(1 if on else 0), "ctgcn_set_coop_mode")
+def set_coop_mode(mode) -> None:
+    """EXPERIMENTAL: 0 / False default kernels, 1 / True reduced-register variants for SpMM / GRU co-residency, 2 the SUM_LN GRU
+    kernel with 16 gate-math warps (see csrc/gru_tc.cu)."""
+    check(lib.ctgcn_set_coop_mode(int(mode)), "ctgcn_set_coop_mode")
 
 
 def set_gru_impl(impl: int) -> None:

@@ -108,13 +108,14 @@ extern "C" int ctgcn_prof_collect(double* ms, int64_t* counts, int reset) {
 
 namespace ctgcn {
 void set_gru_trace(long long* buf);
-void set_coop_mode(int on);
+void set_coop_mode(int mode);
 int coop_mode();
 size_t gru_tc_coop_scratch_bytes();
 }
 // EXPERIMENTAL: co-resident kernel variants (gru_tc_coop_kernel + the 64-register SpMM), see gru_tc.cu.  Default off.
-extern "C" int ctgcn_set_coop_mode(int on) {
-    set_coop_mode(on);
+extern "C" int ctgcn_set_coop_mode(int mode) {
+    CTGCN_REQUIRE(mode >= 0 && mode <= 2, "set_coop_mode: mode %d outside [0,2]", mode);
+    set_coop_mode(mode);
     return CTGCN_OK;
 }
 extern "C" int ctgcn_debug_gru_trace(int64_t* device_buf) {
@@ -253,7 +254,7 @@ static int64_t cd_chunk_rows(const ctgcn_plan* plan, int d_in) {
 static constexpr int kPipeChunks = 4;
 static int64_t cd_pipe_rows(const ctgcn_plan* plan, int d_in) {
     const int64_t wave = 148 * 128;
-    if (!coop_mode() || plan->n_rows < 2 * wave) return 0;
+    if (coop_mode() != 1 || plan->n_rows < 2 * wave) return 0;
     int64_t rows = (plan->n_rows + kPipeChunks - 1) / kPipeChunks;
     rows = (rows + wave - 1) / wave * wave;
     const int64_t cap_rows = cd_chunk_rows(plan, d_in);

@@ -597,7 +597,12 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
 //     stored at its end) → gate warps 168 → 104 registers;
 //   * the kernel is launched with 96 registers per thread (49 152 of the SM's 65 536; setmaxnreg: warps 0-3 56, loaders 112,
 //     gate warps 104 = 48 128), which leaves 16 384 registers = 256 threads × 64 for the co-resident SpMM block.
-__global__ void __maxnreg__(96) gru_tc_coop_kernel(const Params p) {
+template <int NW>   // gate-math warps: 8 (co-resident build, 96 registers per thread) or 16 (full register file, faster gate math)
+__device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
+    constexpr int THREADS_V = 32 * (FIRST_WORKER_WARP + NW);
+    constexpr int CHW = NW / 4;     // warps sharing one TMEM lane quarter = feature groups of a half
+    constexpr int FPT = 64 / CHW;   // features per thread and half: 32 | 16
+    constexpr int SUBS = FPT / 8;   // 8-feature passes per half: 4 | 2
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -614,15 +619,15 @@ __global__ void __maxnreg__(96) gru_tc_coop_kernel(const Params p) {
         }
         mbar_init(bar(BAR_U_READY), NUM_LOADER_WARPS);
         mbar_init(bar(BAR_U_FREE), 1);
-        mbar_init(bar(BAR_H_READY), NUM_WORKER_WARPS);
+        mbar_init(bar(BAR_H_READY), NW);
         mbar_init(bar(BAR_ACC_FULL0), 1);
         mbar_init(bar(BAR_ACC_FULL1), 1);
-        mbar_init(bar(BAR_ACC_FREE0), NUM_WORKER_WARPS);
-        mbar_init(bar(BAR_ACC_FREE1), NUM_WORKER_WARPS);
+        mbar_init(bar(BAR_ACC_FREE0), NW);
+        mbar_init(bar(BAR_ACC_FREE1), NW);
         fence_barrier_init();
     }
-    for (int i = threadIdx.x; i < 4 * H; i += THREADS) reinterpret_cast<float*>(smem + SM_BIAS)[i] = p.bias4[i];
-    for (int i = threadIdx.x; i < H; i += THREADS) {
+    for (int i = threadIdx.x; i < 4 * H; i += THREADS_V) reinterpret_cast<float*>(smem + SM_BIAS)[i] = p.bias4[i];
+    for (int i = threadIdx.x; i < H; i += THREADS_V) {
         reinterpret_cast<float*>(smem + SM_LN)[i] = p.ln_w[i];
         reinterpret_cast<float*>(smem + SM_LN)[H + i] = p.ln_b[i];
     }
@@ -636,7 +641,8 @@ __global__ void __maxnreg__(96) gru_tc_coop_kernel(const Params p) {
     // (warps 0-3: 56, loaders 4-7: 112, workers 8-15: 104)
     if (warp == 0) {
         // ===================================================== weight producer
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if constexpr (NW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             const int nx = 2 * cpx;
@@ -666,7 +672,8 @@ __global__ void __maxnreg__(96) gru_tc_coop_kernel(const Params p) {
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if constexpr (NW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         // All 32 lanes run the (warp-uniform) control flow and the barrier waits; one elected lane issues.
         {
             uint32_t stage = 0, phase = 0, gs = 0;
@@ -731,7 +738,8 @@ __global__ void __maxnreg__(96) gru_tc_coop_kernel(const Params p) {
     } else if (warp < FIRST_WORKER_WARP) {
         // ===================================================== input loaders (warps 4-7; warps 2-3 idle)
         if (warp < FIRST_LOADER_WARP) {
-            asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+            if constexpr (NW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+            else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         } else {
             asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
             // A warp owns 32 tile rows.  Per load instruction its lanes cover 8 rows × 4 k-blocks (r = lane%8, c = lane/8):
@@ -796,63 +804,71 @@ __global__ void __maxnreg__(96) gru_tc_coop_kernel(const Params p) {
         }
     } else {
         // ===================================================== workers (warps 8-15): gate math, h, Σh, LayerNorm
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        // register pools: NW = 8: 512 × 96 = 49 152 ≥ 128·56 + 128·112 + 256·104 = 48 128;
+        //                 NW = 16: 768 × 80 = 61 440 = 128·48 + 128·112 + 512·80
+        if constexpr (NW == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // Σh scratch of this CTA: [16 feature blocks of 8][128 rows][8 floats] → a warp's 32 rows are 1 KB contiguous
         float* const sumh = p.sumh_scratch + (size_t)blockIdx.x * (TILE_M * H);
         const int ww = warp - FIRST_WORKER_WARP;
         const int q = warp & 3;          // TMEM lane quarter this warp may access
-        const int ch = ww >> 2;          // which 32 of a half's 64 features this thread owns
+        const int ch = ww >> 2;          // which FPT of a half's 64 features this thread owns
         const int m = 32 * q + lane;     // row inside the tile
         const uint32_t tmem_lane = tmem + ((uint32_t)(32 * q) << 16);
         const float* bias = reinterpret_cast<const float*>(smem + SM_BIAS);
         const float* lnw = reinterpret_cast<const float*>(smem + SM_LN);
-        float* red = reinterpret_cast<float*>(smem + SM_RED);
+        float* red = reinterpret_cast<float*>(smem + SMEM_BYTES);   // [2][CHW][128] fp32, appended to the common map
         uint8_t* h_hi = smem + SM_H;
         uint32_t gs = 0;
 
         // SUM_LN result of a tile: normalised rows are staged in the (now idle) h buffer with a 16-byte XOR swizzle and
         // written out one whole 512-byte row per warp instruction — to y, or straight into the owning node slice's
         // (peer) buffer: NVLink wants full-line stores, not 32 scattered 16-byte pieces per instruction.
-        auto layer_norm_store_rows = [&](const float (&v)[64], int64_t tile_row0) {
+        auto layer_norm_store_rows = [&](const float (&v)[2 * FPT], int64_t tile_row0) {
             float s = 0.f;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) s += v[j];
+            for (int j = 0; j < 2 * FPT; ++j) s += v[j];
             red[ch * TILE_M + m] = s;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float mean = (s + red[(ch ^ 1) * TILE_M + m]) * (1.f / H);
+            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+            float tot = 0.f;
+#pragma unroll
+            for (int c = 0; c < CHW; ++c) tot += red[c * TILE_M + m];     // same order in every thread of the row
+            const float mean = tot * (1.f / H);
             float sq = 0.f;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
+            for (int j = 0; j < 2 * FPT; ++j) {
                 const float dlt = v[j] - mean;
                 sq = fmaf(dlt, dlt, sq);
             }
-            red[2 * TILE_M + ch * TILE_M + m] = sq;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float rstd = rsqrtf((sq + red[2 * TILE_M + (ch ^ 1) * TILE_M + m]) * (1.f / H) + p.eps);
+            red[(CHW + ch) * TILE_M + m] = sq;
+            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+            float totq = 0.f;
+#pragma unroll
+            for (int c = 0; c < CHW; ++c) totq += red[(CHW + c) * TILE_M + m];
+            const float rstd = rsqrtf(totq * (1.f / H) + p.eps);
             float* stage = reinterpret_cast<float*>(smem + SM_H);     // [128 rows][32 chunks of 4 floats], chunk c of row r at c ^ (r & 31)
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
-                for (int j4 = 0; j4 < 32; j4 += 4) {
-                    const int f = hf * 64 + ch * 32 + j4;
+                for (int j4 = 0; j4 < FPT; j4 += 4) {
+                    const int f = hf * 64 + ch * FPT + j4;
                     float4 o;
-                    o.x = (v[hf * 32 + j4 + 0] - mean) * rstd * lnw[f + 0] + lnw[H + f + 0];
-                    o.y = (v[hf * 32 + j4 + 1] - mean) * rstd * lnw[f + 1] + lnw[H + f + 1];
-                    o.z = (v[hf * 32 + j4 + 2] - mean) * rstd * lnw[f + 2] + lnw[H + f + 2];
-                    o.w = (v[hf * 32 + j4 + 3] - mean) * rstd * lnw[f + 3] + lnw[H + f + 3];
+                    o.x = (v[hf * FPT + j4 + 0] - mean) * rstd * lnw[f + 0] + lnw[H + f + 0];
+                    o.y = (v[hf * FPT + j4 + 1] - mean) * rstd * lnw[f + 1] + lnw[H + f + 1];
+                    o.z = (v[hf * FPT + j4 + 2] - mean) * rstd * lnw[f + 2] + lnw[H + f + 2];
+                    o.w = (v[hf * FPT + j4 + 3] - mean) * rstd * lnw[f + 3] + lnw[H + f + 3];
                     *reinterpret_cast<float4*>(stage + m * H + (((f >> 2) ^ (m & 31)) << 2)) = o;
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            for (int rr = 0; rr < TILE_M / NUM_WORKER_WARPS; ++rr) {
-                const int r = ww * (TILE_M / NUM_WORKER_WARPS) + rr;
+            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+            for (int rr = 0; rr < TILE_M / NW; ++rr) {
+                const int r = ww * (TILE_M / NW) + rr;
                 const int64_t grow = tile_row0 + r;
                 if (grow >= p.n) break;   // warp-uniform
                 const float4 o = *reinterpret_cast<const float4*>(stage + r * H + ((lane ^ (r & 31)) << 2));
                 float* dst = p.sc.slices ? p.sc.row_ptr(grow) : p.y + grow * p.yrs;
                 *reinterpret_cast<float4*>(dst + 4 * lane) = o;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");   // the staging area is h again from the next tile's first step on
+            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");   // the staging area is h again from the next tile's first step on
         };
 
         for (int t = 0; t < my_tiles; ++t) {
@@ -860,8 +876,8 @@ __global__ void __maxnreg__(96) gru_tc_coop_kernel(const Params p) {
 
             for (int i = 0; i < p.steps; ++i, ++gs) {
                 const uint32_t par = gs & 1;
-                // gates, one half (64 hidden features) at a time; this thread owns 32 of them, 8 per pass
-                float h0[32];   // first half of h_i, published only when no MMA reads h_{i-1} any more
+                // gates, one half (64 hidden features) at a time; this thread owns FPT of them, 8 per pass
+                float h0[FPT];  // first half of h_i, published only when no MMA reads h_{i-1} any more
                 auto put_h8 = [&](const float (&f8)[8], int f) {
 #ifdef GRU_EXP_NO_H_STORE
                     if (f8[0] != 12345.678f) return;   // timing experiment: never true in practice
@@ -879,9 +895,9 @@ __global__ void __maxnreg__(96) gru_tc_coop_kernel(const Params p) {
                     tc_fence_after();
                     if (threadIdx.x == FIRST_WORKER_WARP * 32) GRU_TRACE(9 + 2 * hf, gs);
 #pragma unroll
-                    for (int sub = 0; sub < 4; ++sub) {
-                        const int f0 = hf * 64 + ch * 32 + sub * 8;             // first of 8 features
-                        const uint32_t col = hf * 256 + ch * 32 + sub * 8;      // + gate block
+                    for (int sub = 0; sub < SUBS; ++sub) {
+                        const int f0 = hf * 64 + ch * FPT + sub * 8;            // first of 8 features
+                        const uint32_t col = hf * 256 + ch * FPT + sub * 8;     // + gate block
                         float gr[8], gz[8], gi[8], gh[8], hold[8];
                         float* const sp = sumh + ((size_t)(f0 >> 3) * TILE_M + m) * 8;
                         float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
@@ -949,7 +965,7 @@ __global__ void __maxnreg__(96) gru_tc_coop_kernel(const Params p) {
                             // under the MUFU latency of this pass.
                             const float f8[8] = {h0[sub * 8], h0[sub * 8 + 1], h0[sub * 8 + 2], h0[sub * 8 + 3],
                                                  h0[sub * 8 + 4], h0[sub * 8 + 5], h0[sub * 8 + 6], h0[sub * 8 + 7]};
-                            put_h8(f8, ch * 32 + sub * 8);
+                            put_h8(f8, ch * FPT + sub * 8);
                             put_h8(hn8, f0);
                         }
                         s0.x += hn8[0];
@@ -975,14 +991,14 @@ __global__ void __maxnreg__(96) gru_tc_coop_kernel(const Params p) {
                 if (threadIdx.x == FIRST_WORKER_WARP * 32) GRU_TRACE(12, gs);
             }
             {
-                float acc_out[64];   // Σ_s h_s of this thread's 64 features, read back once per tile (own writes: program order)
+                float acc_out[2 * FPT];   // Σ_s h_s of this thread's features, read back once per tile (own writes: program order)
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
-                    for (int sub = 0; sub < 4; ++sub) {
-                        const float* sp = sumh + ((size_t)((hf * 64 + ch * 32 + sub * 8) >> 3) * TILE_M + m) * 8;
+                    for (int sub = 0; sub < SUBS; ++sub) {
+                        const float* sp = sumh + ((size_t)((hf * 64 + ch * FPT + sub * 8) >> 3) * TILE_M + m) * 8;
                         const float4 a0 = __ldcg(reinterpret_cast<const float4*>(sp)), a1 = __ldcg(reinterpret_cast<const float4*>(sp) + 1);
-                        float* o = acc_out + hf * 32 + sub * 8;
+                        float* o = acc_out + hf * FPT + sub * 8;
                         o[0] = a0.x, o[1] = a0.y, o[2] = a0.z, o[3] = a0.w, o[4] = a1.x, o[5] = a1.y, o[6] = a1.z, o[7] = a1.w;
                     }
                 layer_norm_store_rows(acc_out, row - m);
@@ -995,6 +1011,10 @@ __global__ void __maxnreg__(96) gru_tc_coop_kernel(const Params p) {
     if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// co-resident build: 8 gate warps, 96 registers per thread at launch (leaves 16 384 registers per SM to a 64-register SpMM block)
+__global__ void __maxnreg__(96) gru_tc_coop_kernel(const Params p) { gru_tc_sumh_body<8>(p); }
+// fast-gate build: 16 gate warps (each thread 16 features of a half instead of 32), the whole register file: 768 × 80
+__global__ void __maxnreg__(80) gru_tc_w16_kernel(const Params p) { gru_tc_sumh_body<16>(p); }
 
 // ------------------------------------------------------------------------------------------------ self test
 // One half-step of a GRU cell's pre-activations for d_in = 64 through exactly the packer, chunk images, bulk copies,
@@ -1079,9 +1099,11 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
 
 static long long* g_gru_trace = nullptr;
 void set_gru_trace(long long* buf) { g_gru_trace = buf; }
-static std::atomic<int> g_coop{0};
-void set_coop_mode(int on) { g_coop.store(on ? 1 : 0); }
+static std::atomic<int> g_coop{0};   // 0 default kernels | 1 co-resident builds (gru_tc_coop_kernel, 64-register SpMM) | 2 gru_tc_w16_kernel
+void set_coop_mode(int mode) { g_coop.store(mode == 1 || mode == 2 ? mode : 0); }
 int coop_mode() { return g_coop.load(); }
+constexpr int SMEM_BYTES_SUMH = SMEM_BYTES + 4096;   // + the LayerNorm exchange area [2][NW/4][128] fp32 of gru_tc_sumh_body
+static_assert(SMEM_BYTES_SUMH <= 227 * 1024, "shared memory budget");
 // Σh scratch of the co-resident variant: one [TILE_M, H] fp32 tile per CTA of the persistent grid (≤ 256 SMs)
 size_t gru_tc_coop_scratch_bytes() { return (size_t)256 * TILE_M * H * sizeof(float); }
 
@@ -1099,7 +1121,7 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
     uint8_t* packed = (uint8_t*)ws;
     float* bias4 = (float*)(packed + packed_bytes);
     const size_t scratch_off = align_up(packed_bytes + 4 * H * sizeof(float), 256);
-    const bool coop = g_coop.load() && mode == CTGCN_GRU_SUM_LN && ws_bytes >= scratch_off + gru_tc_coop_scratch_bytes();
+    const int coop = (mode == CTGCN_GRU_SUM_LN && ws_bytes >= scratch_off + gru_tc_coop_scratch_bytes()) ? g_coop.load() : 0;
     {
         ProfScope prof(PROF_PACK, st);
         const int threads = nchunks * UNITS_PER_PLANE;
@@ -1116,7 +1138,8 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
     }
     static bool coop_ready = false;      // set up lazily: nothing about the experimental variant can affect the default path
     if (coop && !coop_ready) {
-        CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SUMH));
+        CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_w16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SUMH));
         coop_ready = true;
     }
     Params p;
@@ -1141,8 +1164,10 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
     const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
     CTGCN_REQUIRE(!coop || grid <= 256, "gru_tc: co-resident variant supports at most 256 SMs");
     ProfScope prof(PROF_GRU, st);
-    if (coop)
-        gru_tc_coop_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p);
+    if (coop == 1)
+        gru_tc_coop_kernel<<<grid, THREADS, SMEM_BYTES_SUMH, st>>>(p);
+    else if (coop == 2)
+        gru_tc_w16_kernel<<<grid, 32 * (FIRST_WORKER_WARP + 16), SMEM_BYTES_SUMH, st>>>(p);
     else if (mode == CTGCN_GRU_SUM_LN)
         gru_tc_kernel<CTGCN_GRU_SUM_LN><<<grid, THREADS, SMEM_BYTES, st>>>(p);
     else

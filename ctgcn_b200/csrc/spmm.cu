@@ -391,7 +391,7 @@ template <int NV, int UNROLL>
 int launch_vec(const ctgcn_plan* p, const float* x, int64_t ldx, int d, float* u, bool relu, cudaStream_t st, int64_t row0,
                int64_t rows) {
     const unsigned blocks = (unsigned)((rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    if (NV == 1 && relu && coop_mode()) {   // experimental: 64-register build of the 128-d kernel (co-residency with the GRU)
+    if (NV == 1 && relu && coop_mode() == 1) {   // experimental: 64-register build of the 128-d kernel (co-residency with the GRU)
         cumspmm_vec_coop_kernel<1, 8, true><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p->rowptr + row0, p->col, p->val, p->lvl, x,
                                                                                      ldx, d, p->k, rows, u);
         CTGCN_LAUNCH_OK("cumspmm_vec_coop_kernel");

@@ -128,10 +128,11 @@ int ctgcn_gru_seq_fwd(const float* seq, int64_t seq_row_stride, int64_t seq_step
                       const float* ln_w, const float* ln_b, float eps, int mode, float* y, int64_t y_row_stride,
                       int64_t y_step_stride, void* workspace, size_t workspace_bytes, void* stream);
 int ctgcn_set_gru_impl(int impl);
-/* EXPERIMENTAL (not measured yet, default off): kernel variants with a reduced register footprint so that a cumulative-SpMM block
- * (HBM-bound) can be co-resident on every SM with the tcgen05 GRU kernel (tensor-bound) of another snapshot launched on a second
- * stream.  Same results as the default kernels; affects the SUM_LN GRU launch and the 128-d SpMM launch of this process. */
-int ctgcn_set_coop_mode(int on);
+/* EXPERIMENTAL (not measured yet, default 0).  mode 1: kernel variants with a reduced register footprint so that a
+ * cumulative-SpMM block (HBM-bound) can be co-resident on every SM with the tcgen05 GRU kernel (tensor-bound) of another
+ * snapshot / row chunk launched on a second stream.  mode 2: the tcgen05 SUM_LN GRU kernel with 16 instead of 8 gate-math
+ * warps.  Both keep the running sum of h in an L2-resident scratch instead of registers.  Same results as the default kernels. */
+int ctgcn_set_coop_mode(int mode);
 /* debug: when non-NULL, block 0 of every following tcgen05 GRU launch writes clock64() stamps of its pipeline events
  * into device_buf[24 events][64 steps] (int64); NULL switches it off. */
 int ctgcn_debug_gru_trace(int64_t* device_buf);

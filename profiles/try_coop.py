@@ -63,6 +63,11 @@ def main():
     u2 = ops.cumspmm(plans[0], xs[0])
     t_spmm_coop = timed(lambda: ops.cumspmm(plans[0], xs[0], out=u2), args.iters)
     print(f"core GRU launch: default {t_def:.3f} ms, coop variant {t_coop:.3f} ms, bit-identical: {torch.equal(ref, got)}")
+    _lib.set_coop_mode(2)
+    got16 = ops.rnn_seq(u, *w, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN)
+    t_w16 = timed(lambda: ops.rnn_seq(u, *w, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN), args.iters)
+    print(f"core GRU launch: 16 gate warps {t_w16:.3f} ms, bit-identical: {torch.equal(ref, got16)}")
+    _lib.set_coop_mode(True)
     print(f"SpMM launch:     default {t_spmm_def:.3f} ms, 64-reg variant {t_spmm_coop:.3f} ms, bit-identical: {torch.equal(u, u2)}")
     _lib.set_coop_mode(False)
 
@@ -85,6 +90,13 @@ def main():
         _lib.prof_enable(False)
     print(f"CTGCN.forward {args.config}: default {t_fwd:.2f} ms, co-resident {t_fwd_coop:.2f} ms "
           f"({t_fwd / t_fwd_coop:.2f}x), bit-identical: {torch.equal(out_ref, out_coop)}")
+    _lib.set_coop_mode(2)
+    model.coop = False
+    with torch.no_grad():
+        out_w16 = model(xs, plans).clone()
+        t_fwd_w16 = timed(lambda: model(xs, plans), args.iters)
+    print(f"CTGCN.forward {args.config}: 16 gate warps in the core GRU {t_fwd_w16:.2f} ms ({t_fwd / t_fwd_w16:.2f}x), "
+          f"bit-identical: {torch.equal(out_ref, out_w16)}")
     _lib.set_coop_mode(False)
 
 
