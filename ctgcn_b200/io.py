@@ -35,24 +35,32 @@ def read_node_list(path: str):
 
 
 def read_edge_csv(path: str, node_index: dict, sep: str = "\t"):
-    """One snapshot file → (u, v, w) with u < v, every undirected pair once (utils.py:23-30 semantics)."""
-    last = {}
-    with open(path) as fh:
-        lines = fh.read().split("\n")
-    for ln in lines[1:]:                                  # header line ignored
-        if not ln.strip():
-            continue
-        f = ln.split(sep)
-        a, b = node_index[f[0].strip()], node_index[f[1].strip()]
-        if a == b:
-            continue
-        wgt = float(f[2]) if len(f) > 2 and f[2].strip() else 1.0
-        last[(a, b) if a < b else (b, a)] = wgt          # a repeated pair keeps its last weight
-    if not last:
+    """One snapshot file → (u, v, w) with u < v, every undirected pair once (utils.py:23-30 semantics: header line, optional
+    weight column (1.0 when missing), self-loops dropped, a repeated pair keeps its LAST weight).  Vectorised: the files of
+    the larger datasets hold millions of lines."""
+    import pandas as pd
+    df = pd.read_csv(path, sep=sep, header=0, dtype=str, keep_default_na=False, skip_blank_lines=True)
+    n = len(node_index)
+    if df.shape[0] == 0:
         z = np.zeros(0, dtype=np.int64)
         return z, z.copy(), np.zeros(0, dtype=np.float32)
-    keys = np.array(list(last.keys()), dtype=np.int64)
-    return keys[:, 0], keys[:, 1], np.array(list(last.values()), dtype=np.float32)
+    a = df.iloc[:, 0].str.strip().map(node_index)
+    b = df.iloc[:, 1].str.strip().map(node_index)
+    if a.isna().any() or b.isna().any():
+        bad = df.iloc[:, 0][a.isna()].tolist()[:1] + df.iloc[:, 1][b.isna()].tolist()[:1]
+        raise KeyError(f"{path}: node {bad[0]!r} is not in the node list")
+    a, b = a.to_numpy(dtype=np.int64), b.to_numpy(dtype=np.int64)
+    if df.shape[1] > 2:
+        wcol = df.iloc[:, 2].str.strip()
+        w = np.where(wcol.to_numpy() == "", "1.0", wcol.to_numpy()).astype(np.float64)
+    else:
+        w = np.ones(a.shape[0], dtype=np.float64)
+    keep = a != b
+    lo, hi, w = np.minimum(a, b)[keep], np.maximum(a, b)[keep], w[keep]
+    key = lo * n + hi
+    _, first_in_reversed = np.unique(key[::-1], return_index=True)       # last occurrence of every pair
+    last = key.shape[0] - 1 - first_in_reversed
+    return lo[last], hi[last], w[last].astype(np.float32)
 
 
 # ----------------------------------------------------------------------------- k-core structure
