@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--gru-impl", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "all_to_all", "all_gather", "p2p"])
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="multi-GPU runs: do not bind each rank to the CPUs / memory of its GPU's NUMA node")
     ap.add_argument("--coop", action="store_true",
                     help="EXPERIMENTAL (unmeasured): SpMM(t+1) co-resident with GRU(t), single GPU only (DESIGN.md §9)")
     args = ap.parse_args()
@@ -221,7 +223,11 @@ def main():
     if world > 1:
         td.barrier()
     import ctgcn_b200 as pkg
-    from ctgcn_b200 import _lib, dist, synth
+    from ctgcn_b200 import _lib, dist, hostmem, synth
+
+    # one process per GPU on a multi-socket host: keep this rank's pinned buffers next to its GPU (hostmem.py).  Single-GPU
+    # runs are left alone (the CPU baseline on rank 0 uses every host core).
+    host_numa = hostmem.bind_host_to_gpu(local_rank) if world > 1 and not args.no_numa_bind else None
 
     assert _lib.lib.ctgcn_device_check() == 0, _lib.last_error()
     _lib.set_gru_impl({"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tcgen05": _lib.IMPL_TCGEN05}[args.gru_impl])
@@ -331,7 +337,7 @@ def main():
         sampler.start()
     ms, launches, kern = timed(step_resident, args.steps, args.warmup, prof=True)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _, _ = timed(step_e2e, args.steps, 1, finish=finish_e2e)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, 3, finish=finish_e2e)
     launches_total = int(tot(launches))
     h2d = tot(len(owned) * n * d * 4)          # collectives stay above the rank-0-only reporting below
 
@@ -391,7 +397,7 @@ def main():
                    "layers": f"MLP 1x({d}->{d},'L') + CDN 1 layer + temporal GRU", "edges_aggregated_per_step": e_agg,
                    "union_entries_total": entries_total, "cores_per_snapshot": [s["k"] for s in stats.values()],
                    "l2": "per-step inputs (features + graph plans + per-core sums) exceed the 126 MB L2 several times over; no flush",
-                   "gru_impl": args.gru_impl, "coop": bool(args.coop), "setup_s": round(setup_s, 1)},
+                   "gru_impl": args.gru_impl, "coop": bool(args.coop), "host_numa": host_numa, "setup_s": round(setup_s, 1)},
         "e2e": {"value": e_agg / (ms_e2e / args.steps * 1e-3), "unit": "edges-aggregated/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": launches_total,

@@ -175,3 +175,29 @@ def test_import_without_the_shared_library_fails_loudly(tmp_path):
             shutil.copy(os.path.join(root, "ctgcn_b200", f), dst / f)
     res = subprocess.run([sys.executable, "-c", "import ctgcn_b200"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
     assert res.returncode != 0 and "libctgcn_b200.so not found" in res.stderr and "no CPU/PyTorch fallback" in res.stderr
+
+
+def test_hostmem_best_effort(lib, tmp_path, monkeypatch):
+    """NUMA placement helper of the multi-GPU e2e path: cpulist parsing, and a bind that never raises (no GPU here)."""
+    from ctgcn_b200 import hostmem
+    assert hostmem.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert hostmem.parse_cpulist("") == [] and hostmem.parse_cpulist("5") == [5]
+    before = os.sched_getaffinity(0)
+    rec = hostmem.bind_host_to_gpu(0)
+    assert set(rec) == {"node", "cpus", "mem_preferred", "note"}
+    assert os.sched_getaffinity(0) == before            # nothing to bind to without a GPU
+
+    # a fake sysfs node whose local CPUs are one CPU of this process: the thread is restricted to it and restored below
+    one = sorted(before)[0]
+    (tmp_path / "numa_node").write_text("-1\n")
+    (tmp_path / "local_cpulist").write_text(f"{one}\n")
+    monkeypatch.setattr(hostmem, "gpu_sysfs_dir", lambda i: str(tmp_path))
+    try:
+        rec = hostmem.bind_host_to_gpu(0)
+        assert rec["node"] == -1 and rec["cpus"] == 1 and rec["mem_preferred"] is False
+        assert os.sched_getaffinity(0) == {one}
+        (tmp_path / "local_cpulist").write_text("100000\n")      # outside the cpuset: left untouched
+        rec = hostmem.bind_host_to_gpu(0)
+        assert rec["cpus"] is None and "outside" in rec["note"]
+    finally:
+        os.sched_setaffinity(0, before)
