@@ -597,7 +597,20 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
 //     stored at its end) → gate warps 168 → 104 registers;
 //   * the kernel is launched with 96 registers per thread (49 152 of the SM's 65 536; setmaxnreg: warps 0-3 56, loaders 112,
 //     gate warps 104 = 48 128), which leaves 16 384 registers = 256 threads × 64 for the co-resident SpMM block.
-template <int NW>   // gate-math warps: 8 (co-resident build, 96 registers per thread) or 16 (full register file, faster gate math)
+//
+// FOLD (mode 3): the input-side biases are added by the tensor core instead of the gate warps.  One extra K = 16 MMA per
+// input part, A = a resident block whose k = 0 and k = 1 columns are 1.0, B = a resident block holding bf16 hi (k = 0) and
+// lo (k = 1) of the half's [b_in | b_ir + b_hr | b_iz + b_hz] rows, opens the accumulation (it replaces the "fresh" MMA):
+// +2 of 96 MMAs per tile-step, and the gate warps drop 24 of their 32 broadcast shared-memory loads per 8-feature pass
+// (only b_hn is still added there) — their shared-memory wavefronts compete with the operand fetch of the N = 192 MMA
+// streams (profiles/r01_gru_timeline.md).
+constexpr int SM_FOLD = (SMEM_BYTES + 4096 + 127) / 128 * 128;   // after the LayerNorm exchange area of the Σh-scratch variants
+constexpr int FOLD_ONES_BYTES = 2 * TILE_M * 16;                 // A block  [2 k-blocks][128 rows][8 bf16]
+constexpr int FOLD_BIAS_HALF = 2 * CHUNK_ROWS * 16;              // B block of one half [2 k-blocks][192 rows][8 bf16]
+constexpr int SMEM_BYTES_FOLD = SM_FOLD + FOLD_ONES_BYTES + 2 * FOLD_BIAS_HALF;
+static_assert(SMEM_BYTES_FOLD <= 227 * 1024, "shared memory budget (bias-fold variant)");
+
+template <int NW, bool FOLD = false>   // gate-math warps: 8 (co-resident build, 96 registers per thread) or 16 (full register file, faster gate math)
 __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
     constexpr int THREADS_V = 32 * (FIRST_WORKER_WARP + NW);
     constexpr int CHW = NW / 4;     // warps sharing one TMEM lane quarter = feature groups of a half
@@ -630,6 +643,28 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
     for (int i = threadIdx.x; i < H; i += THREADS_V) {
         reinterpret_cast<float*>(smem + SM_LN)[i] = p.ln_w[i];
         reinterpret_cast<float*>(smem + SM_LN)[H + i] = p.ln_b[i];
+    }
+    if constexpr (FOLD) {
+        // 16-byte units: the ones block (k-block 0 of every row = [1, 1, 0 …]), then per half 192 bias rows [hi, lo, 0 …];
+        // every k-block 1 is zero
+        constexpr int ONES_UNITS = FOLD_ONES_BYTES / 16, BIAS_UNITS = 2 * FOLD_BIAS_HALF / 16;
+        for (int u = threadIdx.x; u < ONES_UNITS + BIAS_UNITS; u += THREADS_V) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (u < TILE_M) {
+                v.x = 0x3f803f80u;                                   // bf16 1.0 | 1.0
+            } else if (u >= ONES_UNITS) {
+                const int b = u - ONES_UNITS, half = b / (2 * CHUNK_ROWS), r = b % (2 * CHUNK_ROWS);
+                if (r < CHUNK_ROWS) {                                // k-block 0
+                    const int blk = r / 64, f = half * 64 + r % 64;  // rows [n | r | z] like an X weight chunk
+                    const float bv = p.bias4[(blk == 0 ? 2 : blk - 1) * H + f];
+                    const __nv_bfloat16 bh = __float2bfloat16_rn(bv);
+                    const __nv_bfloat16 bl = __float2bfloat16_rn(bv - __bfloat162float(bh));
+                    v.x = (uint32_t)__bfloat16_as_ushort(bh) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+                }
+            }
+            *reinterpret_cast<uint4*>(smem + SM_FOLD + 16 * u) = v;
+        }
+        fence_proxy_async();     // read by the tensor core (async proxy)
     }
     if (warp == 1) tmem_alloc(sbase + SM_TMEM_PTR, TMEM_COLS);
     tc_fence_before();
@@ -681,12 +716,19 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
             // one part = one half (64 hidden features) of the input (A = U) or recurrent (A = h) contribution
             auto run_part = [&](uint32_t a_desc, int ktot, int half, bool recurrent) {
                 const uint32_t d = tmem + half * 256 + (recurrent ? COL_R : COL_IN);
+                if (FOLD && !recurrent) {   // biases open the accumulation of [W_in·x | r | z]
+                    if (elect_one())
+                        umma_bf16(d, desc64(desc_lo(sbase + SM_FOLD, TILE_M * 16)),
+                                  desc64(desc_lo(sbase + SM_FOLD + FOLD_ONES_BYTES + half * FOLD_BIAS_HALF, CHUNK_ROWS * 16)),
+                                  umma_idesc_bf16(TILE_M, 192), 0u);
+                    __syncwarp();
+                }
                 for (int kc = 0; kc < ktot / CHUNK_K; ++kc) {
                     mbar_wait(bar(BAR_W_FULL + stage), phase);
                     tc_fence_after();
                     if (elect_one()) {
                         issue_chunk(a_desc + kc * (CHUNK_K / 8) * ((TILE_M * 16) >> 4),
-                                    desc_lo(sbase + SM_W + stage * CHUNK_BYTES, CHUNK_ROWS * 16), d, !recurrent && kc == 0,
+                                    desc_lo(sbase + SM_W + stage * CHUNK_BYTES, CHUNK_ROWS * 16), d, !FOLD && !recurrent && kc == 0,
                                     recurrent && kc == 0);
                         umma_commit(bar(BAR_W_EMPTY + stage));
                     }
@@ -925,9 +967,14 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
                         float hn8[8], ea[8], eb[8], zz[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            ea[j] = gr[j] + bias[f0 + j];
-                            eb[j] = gz[j] + bias[H + f0 + j];
-                            gi[j] += bias[2 * H + f0 + j];
+                            if constexpr (FOLD) {          // b_r, b_z, b_in are already in the accumulators
+                                ea[j] = gr[j];
+                                eb[j] = gz[j];
+                            } else {
+                                ea[j] = gr[j] + bias[f0 + j];
+                                eb[j] = gz[j] + bias[H + f0 + j];
+                                gi[j] += bias[2 * H + f0 + j];
+                            }
                             gh[j] += bias[3 * H + f0 + j];
                         }
 #pragma unroll
@@ -1015,6 +1062,8 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
 __global__ void __maxnreg__(96) gru_tc_coop_kernel(const Params p) { gru_tc_sumh_body<8>(p); }
 // fast-gate build: 16 gate warps (each thread 16 features of a half instead of 32), the whole register file: 768 × 80
 __global__ void __maxnreg__(80) gru_tc_w16_kernel(const Params p) { gru_tc_sumh_body<16>(p); }
+// the same with the input-side biases folded into the MMAs (mode 3)
+__global__ void __maxnreg__(80) gru_tc_w16f_kernel(const Params p) { gru_tc_sumh_body<16, true>(p); }
 
 // ------------------------------------------------------------------------------------------------ self test
 // One half-step of a GRU cell's pre-activations for d_in = 64 through exactly the packer, chunk images, bulk copies,
@@ -1099,8 +1148,9 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
 
 static long long* g_gru_trace = nullptr;
 void set_gru_trace(long long* buf) { g_gru_trace = buf; }
-static std::atomic<int> g_coop{0};   // 0 default kernels | 1 co-resident builds (gru_tc_coop_kernel, 64-register SpMM) | 2 gru_tc_w16_kernel
-void set_coop_mode(int mode) { g_coop.store(mode == 1 || mode == 2 ? mode : 0); }
+// 0 default kernels | 1 co-resident builds (gru_tc_coop_kernel, 64-register SpMM) | 2 gru_tc_w16_kernel | 3 gru_tc_w16f_kernel
+static std::atomic<int> g_coop{0};
+void set_coop_mode(int mode) { g_coop.store(mode >= 1 && mode <= 3 ? mode : 0); }
 int coop_mode() { return g_coop.load(); }
 constexpr int SMEM_BYTES_SUMH = SMEM_BYTES + 4096;   // + the LayerNorm exchange area [2][NW/4][128] fp32 of gru_tc_sumh_body
 static_assert(SMEM_BYTES_SUMH <= 227 * 1024, "shared memory budget");
@@ -1140,6 +1190,7 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
     if (coop && !coop_ready) {
         CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SUMH));
         CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_w16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SUMH));
+        CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_w16f_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_FOLD));
         coop_ready = true;
     }
     Params p;
@@ -1168,6 +1219,8 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
         gru_tc_coop_kernel<<<grid, THREADS, SMEM_BYTES_SUMH, st>>>(p);
     else if (coop == 2)
         gru_tc_w16_kernel<<<grid, 32 * (FIRST_WORKER_WARP + 16), SMEM_BYTES_SUMH, st>>>(p);
+    else if (coop == 3)
+        gru_tc_w16f_kernel<<<grid, 32 * (FIRST_WORKER_WARP + 16), SMEM_BYTES_FOLD, st>>>(p);
     else if (mode == CTGCN_GRU_SUM_LN)
         gru_tc_kernel<CTGCN_GRU_SUM_LN><<<grid, THREADS, SMEM_BYTES, st>>>(p);
     else

@@ -67,6 +67,11 @@ def main():
     got16 = ops.rnn_seq(u, *w, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN)
     t_w16 = timed(lambda: ops.rnn_seq(u, *w, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN), args.iters)
     print(f"core GRU launch: 16 gate warps {t_w16:.3f} ms, bit-identical: {torch.equal(ref, got16)}")
+    _lib.set_coop_mode(3)     # + input-side biases added by the tensor core (bf16 hi+lo of the bias: not bit-identical)
+    got16f = ops.rnn_seq(u, *w, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN)
+    t_w16f = timed(lambda: ops.rnn_seq(u, *w, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN), args.iters)
+    rel = ((got16f - ref).norm() / ref.norm()).item()
+    print(f"core GRU launch: 16 gate warps + folded biases {t_w16f:.3f} ms, relL2 vs default {rel:.2e} (expect ~1e-6; bar 1e-4)")
     _lib.set_coop_mode(True)
     print(f"SpMM launch:     default {t_spmm_def:.3f} ms, 64-reg variant {t_spmm_coop:.3f} ms, bit-identical: {torch.equal(u, u2)}")
     _lib.set_coop_mode(False)
@@ -97,6 +102,13 @@ def main():
         t_fwd_w16 = timed(lambda: model(xs, plans), args.iters)
     print(f"CTGCN.forward {args.config}: 16 gate warps in the core GRU {t_fwd_w16:.2f} ms ({t_fwd / t_fwd_w16:.2f}x), "
           f"bit-identical: {torch.equal(out_ref, out_w16)}")
+    _lib.set_coop_mode(3)
+    with torch.no_grad():
+        out_w16f = model(xs, plans).clone()
+        t_fwd_w16f = timed(lambda: model(xs, plans), args.iters)
+    rel = ((out_w16f - out_ref).norm() / out_ref.norm()).item()
+    print(f"CTGCN.forward {args.config}: 16 gate warps + folded biases {t_fwd_w16f:.2f} ms ({t_fwd / t_fwd_w16f:.2f}x), "
+          f"relL2 vs default {rel:.2e}")
     _lib.set_coop_mode(False)
 
 
