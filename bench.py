@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the CTGCN forward hot path on B200 (the contract the driver relies on).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg4|cfg2|tiny] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg4|cfg2|cfg5s|cfg5|tiny] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N … bench.py --gpus N …
 
 One "step" = one CTGCN.forward over the T synthetic snapshots of the workload (MLP_t → CoreDiffusion_t for
@@ -41,6 +41,10 @@ CONFIGS = {
     # width at 1/5 of the nodes and 2 snapshots — exercises the 256-d (fp32 SIMT) kernels and the row-chunked CoreDiffusion
     "cfg5s": dict(kind="powerlaw", n=1_000_000, m=10_000_000, K=20, T=2, D=256, levels="loader",
                   name="synthetic power-law (Chung-Lu, exponent 2.3) 1M nodes / 10M edges, cores 20..1, T=2 snapshots, 256-d"),
+    # BASELINE.json configs[4] at full size: 8 GPUs, two snapshots per GPU (16 × 5.1 GB of features alone: does not fit one GPU);
+    # the 256-d layers run on the fp32 SIMT sequence kernel and the row-chunked CoreDiffusion (U would be 102 GB per snapshot)
+    "cfg5": dict(kind="powerlaw", n=5_000_000, m=50_000_000, K=20, T=16, D=256, levels="loader", min_gpus=2,
+                 name="synthetic power-law (Chung-Lu, exponent 2.3) 5M nodes / 50M edges, cores 20..1, T=16 snapshots, 256-d"),
     "tiny": dict(kind="er", n=4_000, m=30_000, K=4, T=8, D=128, name="tiny ER smoke workload"),
 }
 
@@ -198,6 +202,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world < cfg.get("min_gpus", 1):
+        raise SystemExit(f"--config {args.config} needs at least {cfg['min_gpus']} GPUs (device memory)")
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local_rank)
