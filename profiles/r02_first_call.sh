@@ -1,0 +1,30 @@
+#!/usr/bin/env bash
+# First GPU call of round 2 in ONE gpurun invocation (runbook: profiles/r02_runbook.md).  Every step has its own timeout and
+# writes into gpurun_out/, so a step that traps or hangs costs its own limit, not the call.
+#
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash profiles/r02_first_call.sh'
+#
+# Order: the green-suite check first (so that the round starts from a known state), then the unmeasured experimental modes at
+# configs[1] size (numerics + first timings), then configs[3] size, then the bench line and the launch list of the default path.
+set -u
+mkdir -p gpurun_out
+out=gpurun_out/r02a
+step() {   # step <name> <seconds> <command...>
+    local name=$1 limit=$2
+    shift 2
+    local t0=$SECONDS
+    timeout "$limit" "$@" > "${out}_${name}.log" 2>&1
+    local rc=$?
+    echo "[$name] rc=$rc $((SECONDS - t0))s" | tee -a "${out}_summary.log"
+    tail -n 6 "${out}_${name}.log" | sed "s/^/    /" | tee -a "${out}_summary.log"
+}
+
+step tests      240 python -m pytest tests -m gpu -x -q
+step coop_cfg2  150 python profiles/try_coop.py --config cfg2
+step coop_cfg4  240 python profiles/try_coop.py --config cfg4 --iters 5
+step hubsplit   150 python profiles/try_hubsplit.py
+step bench_cfg4 200 python bench.py --steps 10 --warmup 3
+# launch list of the default bench command's timed region (per-launch times under ncu are cold-cache: compare SHARES)
+step launches   200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+    --log-file "${out}_launches_cfg4.csv" python bench.py --steps 1 --warmup 3 --no-cpu-baseline
+cat "${out}_summary.log"
