@@ -60,8 +60,12 @@ def powerlaw_edges(n: int, m: int, rng: np.random.Generator, exponent: float = 2
     cdf = np.cumsum(w)
     cdf /= cdf[-1]
     k = int(m * 1.15) + 16
-    u = np.searchsorted(cdf, rng.random(k)).astype(np.int64)
-    v = np.searchsorted(cdf, rng.random(k)).astype(np.int64)
+    # inverse-CDF sampling; torch.searchsorted (same 'left' convention as numpy's, same float64 inputs → same graph) runs
+    # multi-threaded on the CPU and on the GPU when there is one: numpy needs 10 s per million-node snapshot here
+    dev = _work_device()
+    cdf_t = torch.as_tensor(cdf, device=dev)
+    u = torch.searchsorted(cdf_t, torch.as_tensor(rng.random(k), device=dev)).cpu().numpy()
+    v = torch.searchsorted(cdf_t, torch.as_tensor(rng.random(k), device=dev)).cpu().numpy()
     perm = rng.permutation(n)  # hubs are not the low node ids
     return _simple(n, perm[u], perm[v], m, rng)
 
