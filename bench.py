@@ -104,72 +104,96 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU baseline
+class CpuReference:
+    """The torch-CPU port of the reference path (oracle/oracle_torch.py: torch.sparse.mm ×K, nn.GRU, LayerNorm, nn.Linear —
+    the same library calls the reference makes) on ONE snapshot's MLP + CoreDiffusion: a bounded sample of the workload
+    (same density and K, node count capped at 100 K)."""
+
+    def __init__(self, cfg):
+        import numpy as np
+        import torch
+        from ctgcn_b200 import synth
+        from oracle import cases, oracle_torch
+
+        self.torch = torch
+        n = min(cfg["n"], 100_000)
+        m = int(cfg["m"] * (n / cfg["n"]))
+        self.snap = snap = synth.make_snapshot(cfg["kind"], n, m, cfg["K"], seed=0, levels=cfg.get("levels", "top"))
+        adj = snap.coo_list("cpu")
+        d = cfg["D"]
+        x = synth.features(n, d, 1000)
+        sd = {k: torch.from_numpy(v) for k, v in cases.ctgcn_params(np.random.default_rng(0), d, d, d, 1, 1, 1, "C").items()}
+
+        def run():
+            with torch.no_grad():
+                h = oracle_torch.mlp(x, sd, "mlp_list.0.", 1, "L")
+                return oracle_torch.cdn(h, adj, sd, "duffision_list.0.", 1)
+
+        self.run = run
+        self.host_cores = os.cpu_count() or 1
+        self.what = (f"1 snapshot MLP+CoreDiffusion fwd, {cfg['kind'].upper()} N={n} m={m} K={snap.k} D={d} "
+                     f"(E_agg={snap.edges_aggregated})")
+        self.reduced = "" if n == cfg["n"] else f", node count reduced from {cfg['n']}"
+        self.threads, self.tried = None, []
+
+    def time_once(self):
+        t0 = time.perf_counter()
+        self.run()
+        return time.perf_counter() - t0
+
+    def sweep(self, seconds_budget=25.0):
+        """Pick the thread count (mirrors main.py:51-52 `torch.set_num_threads`): one warm-up + one timed run each."""
+        cand = sorted({c for c in (1, 2, 4, 8, 16, 32, 64, 128, self.host_cores) if c <= self.host_cores})
+        best, spent = None, 0.0
+        for thr in cand:
+            self.tried.append(thr)
+            self.torch.set_num_threads(thr)
+            warm = self.time_once()
+            dt = self.time_once()
+            spent += warm + dt
+            if best is None or dt < best:
+                best, self.threads = dt, thr
+            if spent > seconds_budget:
+                break
+        self.torch.set_num_threads(self.threads)
+        return best
+
+    def record(self, seconds):
+        sample = (f"{self.what}; best of thread counts {self.tried} = {self.threads} threads on {self.host_cores} cores; "
+                  f"same density/K as the workload{self.reduced}")
+        return dict(value=self.snap.edges_aggregated / seconds, unit="edges-aggregated/s", cores=self.threads, kind="port",
+                    sample=sample, seconds=seconds, host_cores=self.host_cores)
+
+
 def cpu_reference_sample(cfg, seconds_budget=25.0):
-    """Time the torch-CPU port of the reference path (oracle/oracle_torch.py: torch.sparse.mm ×K, nn.GRU, LayerNorm,
-    nn.Linear — the same library calls the reference makes) on ONE snapshot's MLP + CoreDiffusion, thread count swept."""
-    import numpy as np
-    import torch
-    from ctgcn_b200 import synth
-    from oracle import cases, oracle_torch
-
-    n = min(cfg["n"], 100_000)
-    m = int(cfg["m"] * (n / cfg["n"]))
-    snap = synth.make_snapshot(cfg["kind"], n, m, cfg["K"], seed=0, levels=cfg.get("levels", "top"))
-    adj = snap.coo_list("cpu")
-    d = cfg["D"]
-    x = synth.features(n, d, 1000)
-    sd = {k: torch.from_numpy(v) for k, v in cases.ctgcn_params(np.random.default_rng(0), d, d, d, 1, 1, 1, "C").items()}
-
-    def run():
-        with torch.no_grad():
-            h = oracle_torch.mlp(x, sd, "mlp_list.0.", 1, "L")
-            return oracle_torch.cdn(h, adj, sd, "duffision_list.0.", 1)
-
-    cores = os.cpu_count() or 1
-    cand = sorted({c for c in (1, 2, 4, 8, 16, 32, 64, 128, cores) if c <= cores})
-    best, best_thr, spent, tried = None, None, 0.0, []
-    for thr in cand:
-        tried.append(thr)
-        torch.set_num_threads(thr)
-        t0 = time.perf_counter()
-        run()                                    # warm-up for this thread count
-        warm = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        run()
-        dt = time.perf_counter() - t0
-        spent += warm + dt
-        if best is None or dt < best:
-            best, best_thr = dt, thr
-        if spent > seconds_budget:
-            break
-    sample = (f"1 snapshot MLP+CoreDiffusion fwd, {cfg['kind'].upper()} N={n} m={m} K={snap.k} D={d} "
-              f"(E_agg={snap.edges_aggregated}); best of thread counts {tried} = {best_thr} threads on {cores} cores; "
-              f"same density/K as the workload" + ("" if n == cfg["n"] else f", node count reduced from {cfg['n']}"))
-    return dict(value=snap.edges_aggregated / best, unit="edges-aggregated/s", cores=best_thr, kind="port", sample=sample,
-                seconds=best, host_cores=cores)
+    ref = CpuReference(cfg)
+    return ref.record(ref.sweep(seconds_budget))
 
 
 def run_reference_arm(args, cfg):
+    """`--impl reference`: the reference's CPU path (kind "port", see CpuReference) on the host cores.  One step = one timed
+    pass over the bounded sample at the thread count the initial sweep picked; under torchrun rank 0 alone runs it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    ref = CpuReference(cfg)
+    ref.sweep(25.0)                                 # also the first warm-up
+    for _ in range(max(args.warmup - 1, 0)):
+        ref.time_once()
     times = []
-    base = None
-    for i in range(args.warmup + args.steps):
-        base = cpu_reference_sample(cfg, seconds_budget=12.0 if i else 25.0)
-        if i >= args.warmup:
-            times.append(base["seconds"])
-        if sum(times) > 150:
+    for _ in range(max(args.steps, 1)):
+        times.append(ref.time_once())
+        if sum(times) > 150:                        # bounded: a slow host stops early and reports the steps it did
             break
     t = sum(times) / len(times)
-    val = base["value"] * base["seconds"] / t
+    base = ref.record(t)
+    val = base["value"]
     line = {"metric": "edges-aggregated/s, CTGCN CoreDiffusion forward", "value": val, "unit": "edges-aggregated/s",
             "impl": "reference", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": t * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["name"]},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": val, "unit": "edges-aggregated/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    line["cpu_baseline"]["value"] = val
     print(json.dumps(line))
 
 
