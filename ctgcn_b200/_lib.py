@@ -18,6 +18,7 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 CELL_GRU, CELL_LSTM = 0, 1
 CELLS = {"GRU": CELL_GRU, "LSTM": CELL_LSTM}
 MAX_CORES = 64
+MAX_NEG = 64
 
 
 class CtgcnError(RuntimeError):
@@ -71,6 +72,10 @@ SIGNATURES = {
     "ctgcn_linear_fwd": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _i32, _p, _i64, _p, _sz, _p]),
     "ctgcn_spmm_linear_fwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _i64, _p, _sz, _p]),
     "ctgcn_kcore_numbers": (C.c_int, [_i64, _p, _p, _p]),
+    "ctgcn_neg_sample": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _i64, _i32, C.c_uint64, _p, _p, _p, _p]),
+    "ctgcn_neg_loss_workspace_bytes": (_sz, [_i64, _i32]),
+    "ctgcn_neg_loss_fwd": (C.c_int, [_p, _i64, _i64, _i32, _p, _i64, _p, _p, _p, _i32, _f32, _p, _p, _sz, _p]),
+    "ctgcn_neg_loss_bwd": (C.c_int, [_p, _i64, _i64, _i32, _p, _i64, _p, _p, _p, _i32, _f32, _p, _p, _i64, _p, _sz, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

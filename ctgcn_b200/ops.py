@@ -209,3 +209,55 @@ def spmm_linear(x_plan: GraphPlan, w, b, act: int):
         _lib.check(_lib.lib.ctgcn_spmm_linear_fwd(x_plan.handle, _ptr(w), _ptr(b), d_out, act, _ptr(y), y.stride(0), _ptr(ws),
                                                   ws_bytes, _stream()), "ctgcn_spmm_linear_fwd")
     return y
+
+
+# ---- negative-sampling loss (reference metrics.py:18-93)
+def neg_sample(pair_ptr: torch.Tensor, pair_idx: torch.Tensor, freq: torch.Tensor, batch: torch.Tensor, neg_num: int, seed: int):
+    """Device-side NegativeSamplingLoss.__get_node_indices (metrics.py:68-93) for one snapshot.
+    pair_ptr int64 [N+1] / pair_idx int32: CSR of the walk co-occurrence lists; freq int32: frequency-expanded negative list;
+    batch int64 node ids → (pos int32 [B, neg_num] (-1 padded), count int32 [B], neg int32 [neg_num])."""
+    for t, dt, nm in ((pair_ptr, torch.int64, "pair_ptr"), (pair_idx, torch.int32, "pair_idx"), (freq, torch.int32, "freq"),
+                      (batch, torch.int64, "batch")):
+        if not t.is_cuda or t.dtype != dt or not t.is_contiguous():
+            raise _lib.CtgcnError(f"{nm} must be a contiguous {dt} CUDA tensor (ctgcn_b200 has no CPU path)")
+    if freq.numel() < neg_num:
+        raise ValueError("Sample larger than population or is negative")     # what random.sample raises at metrics.py:88
+    nb = batch.numel()
+    dev = batch.device
+    pos = torch.empty(nb, neg_num, dtype=torch.int32, device=dev)
+    count = torch.empty(nb, dtype=torch.int32, device=dev)
+    neg = torch.empty(neg_num, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.ctgcn_neg_sample(_ptr(pair_ptr), _ptr(pair_idx), pair_ptr.numel() - 1, _ptr(freq), freq.numel(),
+                                             _ptr(batch), nb, int(neg_num), int(seed) & (2 ** 64 - 1), _ptr(pos), _ptr(count),
+                                             _ptr(neg), _stream()), "ctgcn_neg_sample")
+    return pos, count, neg
+
+
+def _loss_args(emb, batch, pos, count, neg):
+    if emb.dim() != 2 or not emb.is_cuda or emb.dtype != torch.float32 or emb.stride(1) != 1:
+        raise _lib.CtgcnError("embeddings must be a 2-D fp32 CUDA tensor with a contiguous last dim (ctgcn_b200 has no CPU path)")
+    return (_ptr(emb), emb.stride(0), emb.shape[0], emb.shape[1], _ptr(batch), batch.numel(), _ptr(pos), _ptr(count), _ptr(neg),
+            pos.shape[1])
+
+
+def neg_loss_fwd(emb, batch, pos, count, neg, q: float):
+    """(loss [1], workspace) for one snapshot — metrics.py:55-61 on the samples of neg_sample; the workspace goes to neg_loss_bwd."""
+    args = _loss_args(emb, batch, pos, count, neg)
+    ws_bytes = _lib.lib.ctgcn_neg_loss_workspace_bytes(batch.numel(), emb.shape[1])
+    ws = _workspace(ws_bytes, emb.device)
+    loss = torch.empty(1, dtype=torch.float32, device=emb.device)
+    with torch.cuda.device(emb.device):
+        _lib.check(_lib.lib.ctgcn_neg_loss_fwd(*args, float(q), _ptr(loss), _ptr(ws), ws_bytes, _stream()), "ctgcn_neg_loss_fwd")
+    return loss, ws
+
+
+def neg_loss_bwd(emb, batch, pos, count, neg, q: float, grad_loss, ws):
+    """grad_loss [1] · d loss / d emb → dense [N, D] (atomics; rows outside the samples stay zero)."""
+    args = _loss_args(emb, batch, pos, count, neg)
+    grad = torch.zeros(emb.shape[0], emb.shape[1], dtype=torch.float32, device=emb.device)
+    gl = grad_loss.detach().reshape(-1)[:1].to(torch.float32).contiguous()
+    with torch.cuda.device(emb.device):
+        _lib.check(_lib.lib.ctgcn_neg_loss_bwd(*args, float(q), _ptr(gl), _ptr(grad), grad.stride(0), _ptr(ws), ws.numel(),
+                                               _stream()), "ctgcn_neg_loss_bwd")
+    return grad

@@ -33,6 +33,7 @@ extern "C" {
 #define CTGCN_ENODEV (-4)   /* no usable sm_100 device                     */
 
 #define CTGCN_MAX_CORES 64
+#define CTGCN_MAX_NEG 64    /* largest neg_num of the negative-sampling loss entry points */
 
 /* activation codes for ctgcn_linear_fwd / ctgcn_spmm_linear_fwd (layers.py:98-99,104-105) */
 #define CTGCN_ACT_NONE 0
@@ -202,6 +203,32 @@ int ctgcn_linear_fwd(const float* x, int64_t ldx, int64_t n, int64_t d_in, const
  * helper.py:136-155): x given as a K=1 plan of shape [n, d_in].  Same workspace size query. */
 int ctgcn_spmm_linear_fwd(const ctgcn_plan* x_plan, const float* w, const float* b, int64_t d_out, int act,
                           float* y, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- negative-sampling loss (metrics.py:18-93)
+ * The unsupervised loss the trainer evaluates on every batch (embedding.py:347).  One snapshot per call.
+ *
+ * ctgcn_neg_sample replaces NegativeSamplingLoss.__get_node_indices (metrics.py:68-93, a Python loop with random.sample per
+ * batch node).  pair_ptr int64[n_nodes+1] / pair_idx int32[]: CSR of the walk co-occurrence lists (helper.py:85-94);
+ * freq int32[freq_len]: the frequency-expanded negative list (helper.py:97-106); batch int64[n_batch] node ids.
+ * Outputs: pos int32[n_batch, neg_num] — the kept neighbours of batch node b in pos[b, 0..count[b]), -1 after; all of them in
+ * stored order when the node has at most neg_num, else neg_num distinct ones drawn uniformly; count int32[n_batch];
+ * neg int32[neg_num] — node ids at neg_num distinct positions of freq.  Batch ids outside [0, n_nodes) keep nothing.
+ * Counter-based generator: the same (seed, inputs) gives the same draw on every device. */
+int ctgcn_neg_sample(const int64_t* pair_ptr, const int32_t* pair_idx, int64_t n_nodes, const int32_t* freq, int64_t freq_len,
+                     const int64_t* batch, int64_t n_batch, int neg_num, uint64_t seed, int32_t* pos, int32_t* count,
+                     int32_t* neg, void* stream);
+/* loss[0] = mean_s softplus(-<e_node, e_pos>) + q * mean_s softplus(<e_node, sum_j e_neg_j>) over the S = sum_b count[b]
+ * samples (metrics.py:55-61: BCEWithLogits, mean reduction; pos_score by mul+sum, neg_score by matmul+sum); 0 when S = 0.
+ * emb [n_nodes, d] fp32 with row stride ld.  The backward ACCUMULATES grad_loss[0] * dloss/demb into grad_emb (row stride
+ * ldg; the caller zeroes it) and must get the workspace the forward filled for the same arguments. */
+size_t ctgcn_neg_loss_workspace_bytes(int64_t n_batch, int d);
+int ctgcn_neg_loss_fwd(const float* emb, int64_t ld, int64_t n_nodes, int d, const int64_t* batch, int64_t n_batch,
+                       const int32_t* pos, const int32_t* count, const int32_t* neg, int neg_num, float q, float* loss,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int ctgcn_neg_loss_bwd(const float* emb, int64_t ld, int64_t n_nodes, int d, const int64_t* batch, int64_t n_batch,
+                       const int32_t* pos, const int32_t* count, const int32_t* neg, int neg_num, float q,
+                       const float* grad_loss, float* grad_emb, int64_t ldg, void* workspace, size_t workspace_bytes,
+                       void* stream);
 
 /* ---------------------------------------------------------------- host helper (no GPU needed)
  * Exact k-core numbers by bucket peeling (replaces networkx.core_number used at

@@ -20,6 +20,8 @@ step() {   # step <name> <seconds> <command...>
 }
 
 step tests      240 python -m pytest tests -m gpu -x -q
+# kernels written after the round-1 GPU budget was spent (negative-sampling loss): opt-in until green once
+step loss_tests 120 env CTGCN_UNVERIFIED_GPU_TESTS=1 python -m pytest tests/test_loss_gpu.py -m gpu -q
 step coop_cfg2  150 python profiles/try_coop.py --config cfg2
 step coop_cfg4  240 python profiles/try_coop.py --config cfg4 --iters 5
 step hubsplit   150 python profiles/try_hubsplit.py

@@ -84,6 +84,37 @@ def spmm_linear(plan, w, b, act):
     return torch.selu(y) if act == 1 else y
 
 
+# ---- negative-sampling loss (ctgcn_b200/loss.py): numpy stand-ins with the padded sample format of ctgcn_neg_sample
+def neg_sample(pair_ptr, pair_idx, freq, batch, neg_num, seed):
+    rng = np.random.default_rng(seed % (2 ** 63))
+    ptr, idx, fr, bt = (t.numpy() for t in (pair_ptr, pair_idx, freq, batch))
+    if len(fr) < neg_num:
+        raise ValueError("Sample larger than population or is negative")
+    pos = np.full((len(bt), neg_num), -1, dtype=np.int32)
+    count = np.zeros(len(bt), dtype=np.int32)
+    for b, node in enumerate(bt):
+        nb = idx[ptr[node]:ptr[node + 1]]
+        take = nb if len(nb) <= neg_num else rng.choice(nb, size=neg_num, replace=False)
+        pos[b, :len(take)] = take
+        count[b] = len(take)
+    neg = fr[rng.choice(len(fr), size=neg_num, replace=False)].astype(np.int32)
+    return torch.from_numpy(pos), torch.from_numpy(count), torch.from_numpy(neg)
+
+
+def neg_loss_fwd(emb, batch, pos, count, neg, q):
+    from oracle import oracle_loss
+    ni, pi = oracle_loss.from_padded(batch.numpy(), pos.numpy(), count.numpy())
+    loss, _ = oracle_loss.snapshot_loss(emb.detach().numpy(), ni, pi, neg.numpy(), q)
+    return torch.tensor([loss], dtype=torch.float32), torch.zeros(1)
+
+
+def neg_loss_bwd(emb, batch, pos, count, neg, q, grad_loss, ws):
+    from oracle import oracle_loss
+    ni, pi = oracle_loss.from_padded(batch.numpy(), pos.numpy(), count.numpy())
+    _, grad = oracle_loss.snapshot_loss(emb.detach().numpy(), ni, pi, neg.numpy(), q)
+    return torch.from_numpy((grad * float(grad_loss.reshape(-1)[0])).astype(np.float32))
+
+
 class PassThroughStager:
     def __init__(self, x_list, order, dev, depth=2):
         self.x_list = x_list
@@ -95,7 +126,8 @@ class PassThroughStager:
 def install(monkeypatch):
     import ctgcn_b200
     from ctgcn_b200 import layers, models, ops
-    for name in ("cumspmm", "cumspmm_bwd", "rnn_seq", "core_diffusion", "linear", "spmm_linear"):
+    for name in ("cumspmm", "cumspmm_bwd", "rnn_seq", "core_diffusion", "linear", "spmm_linear", "neg_sample", "neg_loss_fwd",
+                 "neg_loss_bwd"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(layers, "plan_for", plan_for)
     monkeypatch.setattr(models, "_HostFeatureStager", PassThroughStager)
