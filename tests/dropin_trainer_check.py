@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE, launched by tests/test_dropin_trainer.py in a subprocess (it imports the reference's top-level modules
 `train`, `models`, `layers`, … which must not leak into the pytest process).
 
-    python tests/dropin_trainer_check.py {ref|dropin} OUTDIR METHOD T EPOCHS
+    python tests/dropin_trainer_check.py {ref|dropin|dropin_loss} OUTDIR METHOD T EPOCHS
 
 Runs the UNMODIFIED reference pipeline from /root/reference on the first T UCI snapshots — preprocessing, then
 train.gnn_embedding(METHOD) with the shipped hyper-parameters — and copies the exported embeddings and the saved checkpoint to
@@ -65,11 +65,20 @@ def main():
         preprocess("CTGCN-C", dict(cfg["preprocessing"]["CTGCN-C"], base_path=base, worker=-1))
 
         import models as ref_models
+        if mode == "dropin_loss":      # the unsupervised loss too: rebound BEFORE train.py binds the name (train.py:8)
+            import metrics as ref_metrics
+            import fake_backend
+            pkg = fake_backend.install(_Patch())
+            pkg.install_as_reference_modules(ref_models, ref_metrics)
+            assert ref_metrics.NegativeSamplingLoss is pkg.loss.NegativeSamplingLoss
         import train
+        if mode == "dropin_loss":
+            assert train.NegativeSamplingLoss is pkg.loss.NegativeSamplingLoss
         if mode == "dropin":
             import fake_backend
             pkg = fake_backend.install(_Patch())
             pkg.install_as_reference_modules(ref_models)
+        if mode != "ref":
             assert ref_models.CTGCN is pkg.CTGCN and ref_models.CGCN is pkg.CGCN and sys.modules["layers"] is pkg.layers
         random.seed(1)
         np.random.seed(1)

@@ -45,3 +45,22 @@ def test_reference_trainer_with_swapped_modules(method, T, tmp_path, lib):
         upd_a, upd_b = sa[k].astype(np.float64), sb[k].astype(np.float64)
         assert np.abs(upd_a - upd_b).max() <= 2.5e-3, k
         assert np.linalg.norm(upd_a - upd_b) <= 0.02 * max(np.linalg.norm(upd_a), 1e-12), k
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "data", "uci")), reason="needs the reference checkout with its UCI data")
+def test_reference_trainer_with_swapped_loss(tmp_path, lib):
+    """the reference's trainer also drives ctgcn_b200.loss.NegativeSamplingLoss (constructed by train.get_loss from
+    the loader's lil rows / json lists, called as loss_model([embeddings, batch_indices]), .backward(), .item()).  Its draws come
+    from another generator than the reference's, so the runs are compared loosely: same files, same checkpoint keys, finite
+    embeddings that stay close to the reference run's after two epochs."""
+    pd = pytest.importorskip("pandas")
+    _run("ref", tmp_path / "ref", "CGCN-C", 1, 2)
+    _run("dropin_loss", tmp_path / "dropin", "CGCN-C", 1, 2)
+    files = sorted(f for f in os.listdir(tmp_path / "ref") if f.endswith(".csv"))
+    assert len(files) == 1 and files == sorted(f for f in os.listdir(tmp_path / "dropin") if f.endswith(".csv"))
+    a = pd.read_csv(tmp_path / "ref" / files[0], sep="\t", index_col=0)
+    b = pd.read_csv(tmp_path / "dropin" / files[0], sep="\t", index_col=0)
+    assert a.shape == b.shape == (1899, 128) and np.isfinite(b.values).all()
+    assert np.linalg.norm(a.values - b.values) / np.linalg.norm(a.values) < 0.25
+    sa, sb = np.load(tmp_path / "ref" / "state_dict.npz"), np.load(tmp_path / "dropin" / "state_dict.npz")
+    assert sorted(sa.files) == sorted(sb.files)
