@@ -206,7 +206,7 @@ using namespace ctgcn;
 extern "C" int ctgcn_neg_sample(const int64_t* pair_ptr, const int32_t* pair_idx, int64_t n_nodes, const int32_t* freq,
                                 int64_t freq_len, const int64_t* batch, int64_t n_batch, int neg_num, uint64_t seed,
                                 int32_t* pos, int32_t* count, int32_t* neg, void* stream) {
-    CTGCN_REQUIRE(pair_ptr && pair_idx && freq && batch && pos && count && neg, "neg_sample: NULL argument");
+    CTGCN_REQUIRE(pair_ptr && freq && neg && (n_batch <= 0 || (pair_idx && batch && pos && count)), "neg_sample: NULL argument");
     CTGCN_REQUIRE(neg_num >= 1 && neg_num <= MAX_NEG, "neg_sample: neg_num=%d outside [1,%d]", neg_num, MAX_NEG);
     CTGCN_REQUIRE(n_nodes > 0 && n_batch >= 0, "neg_sample: bad sizes");
     CTGCN_REQUIRE(freq_len >= neg_num, "neg_sample: the frequency list holds %lld entries, fewer than neg_num=%d",
@@ -225,7 +225,7 @@ extern "C" size_t ctgcn_neg_loss_workspace_bytes(int64_t n_batch, int d) {
 
 static int loss_args_ok(const float* emb, int64_t ld, int64_t n_nodes, int d, const int64_t* batch, int64_t n_batch,
                         const int32_t* pos, const int32_t* count, const int32_t* neg, int neg_num, void* ws, size_t ws_b) {
-    CTGCN_REQUIRE(emb && batch && pos && count && neg, "neg_loss: NULL argument");
+    CTGCN_REQUIRE(emb && neg && (n_batch <= 0 || (batch && pos && count)), "neg_loss: NULL argument");   // empty tensors have no address
     CTGCN_REQUIRE(d >= 1 && ld >= d && n_nodes > 0 && n_batch >= 0, "neg_loss: bad sizes");
     CTGCN_REQUIRE(neg_num >= 1 && neg_num <= MAX_NEG, "neg_loss: neg_num=%d outside [1,%d]", neg_num, MAX_NEG);
     if (!ws || ws_b < ws_bytes(n_batch, d)) {

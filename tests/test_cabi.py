@@ -49,6 +49,16 @@ def test_argument_validation_without_gpu(lib):
     assert L.ctgcn_core_diffusion_rnn_fwd(None, 0, None, 0, 1, 1, None, None, None, None, None, None, 1e-5, None, 0, None, 0, 0, 0,
                                           None, 0, None) == lib.EINVAL
     assert L.ctgcn_set_workspace_cap(1 << 20) == 0 and L.ctgcn_set_workspace_cap(0) == 0
+    # negative-sampling loss entry points
+    one = C.c_void_p(8)
+    assert L.ctgcn_neg_sample(None, None, 10, None, 100, None, 4, 20, 1, None, None, None, None) == lib.EINVAL
+    assert L.ctgcn_neg_sample(one, one, 10, one, 100, one, 4, lib.MAX_NEG + 1, 1, one, one, one, None) == lib.EINVAL
+    assert L.ctgcn_neg_sample(one, one, 10, one, 5, one, 4, 20, 1, one, one, one, None) == lib.EINVAL
+    assert "fewer than neg_num" in lib.last_error()
+    assert L.ctgcn_neg_loss_workspace_bytes(4, 128) == 2 * 512 + 256 + 4 * 8 and L.ctgcn_neg_loss_workspace_bytes(-1, 128) == 0
+    assert L.ctgcn_neg_loss_fwd(one, 128, 10, 128, one, 4, one, one, one, 20, 1.0, one, None, 0, None) == lib.ENOMEM
+    assert L.ctgcn_neg_loss_fwd(one, 64, 10, 128, one, 4, one, one, one, 20, 1.0, one, one, 1 << 20, None) == lib.EINVAL   # ld < d
+    assert L.ctgcn_neg_loss_bwd(one, 128, 10, 128, one, 4, one, one, one, 20, 1.0, None, None, 128, one, 1 << 20, None) == lib.EINVAL
 
 
 def test_kcore_numbers_match_networkx(lib):
