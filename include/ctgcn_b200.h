@@ -204,6 +204,12 @@ int ctgcn_linear_fwd(const float* x, int64_t ldx, int64_t n, int64_t d_in, const
 int ctgcn_spmm_linear_fwd(const ctgcn_plan* x_plan, const float* w, const float* b, int64_t d_out, int act,
                           float* y, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
 
+/* EXPERIMENTAL test hook (never run yet): one GRU half-step through tcgen05.mma.cta_group::2 on a CTA pair (csrc/umma2_selftest.cu,
+ * profiles/r02_gru_design.md step 2).  out[256,256] = [x W_in^T | x W_ir^T + h W_hr^T | x W_iz^T + h W_hz^T | h W_hn^T] for hidden
+ * features 0..63 from x[256,64], h[256,128], w_ih[384,64], w_hh[384,128]; workspace >= 512 KB of device memory. */
+int ctgcn_selftest_umma_pair(const float* x, const float* h, const float* w_ih, const float* w_hh, float* out, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- negative-sampling loss (metrics.py:18-93)
  * The unsupervised loss the trainer evaluates on every batch (embedding.py:347).  One snapshot per call.
  *

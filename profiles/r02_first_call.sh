@@ -20,8 +20,10 @@ step() {   # step <name> <seconds> <command...>
 }
 
 step tests      240 python -m pytest tests -m gpu -x -q
-# kernels written after the round-1 GPU budget was spent (negative-sampling loss): opt-in until green once
+# kernels written after the round-1 GPU budget was spent (negative-sampling loss; the 2-CTA MMA building block):
+# opt-in until green once.  Separate processes: a trap in one must not take the other down.
 step loss_tests 120 env CTGCN_UNVERIFIED_GPU_TESTS=1 python -m pytest tests/test_loss_gpu.py -m gpu -q
+step pair_umma   90 env CTGCN_UNVERIFIED_GPU_TESTS=1 python -m pytest tests/test_experimental_gpu.py -m gpu -q
 step coop_cfg2  150 python profiles/try_coop.py --config cfg2
 step coop_cfg4  240 python profiles/try_coop.py --config cfg4 --iters 5
 step hubsplit   150 python profiles/try_hubsplit.py
