@@ -204,6 +204,12 @@ int ctgcn_linear_fwd(const float* x, int64_t ldx, int64_t n, int64_t d_in, const
 int ctgcn_spmm_linear_fwd(const ctgcn_plan* x_plan, const float* w, const float* b, int64_t d_out, int act,
                           float* y, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
 
+/* EXPERIMENTAL (never run yet; csrc/spmm_packed.cu, profiles/r02_gru_design.md step 3): ctgcn_cumspmm_fwd for d = 128 whose output
+ * is pre-split into the tensor-core operand layout instead of fp32 rows: per 128-row tile and level one 64 KB image
+ * [plane hi|lo][k-block 16][row 128][8 bf16], hi = bf16_rn(u), lo = bf16_rn(u - hi); u: ctgcn_cumspmm_packed_bytes(plan) bytes. */
+size_t ctgcn_cumspmm_packed_bytes(const ctgcn_plan* plan);
+int ctgcn_cumspmm_fwd_packed(const ctgcn_plan* plan, const float* x, int64_t ldx, int d, void* u, void* stream);
+
 /* EXPERIMENTAL test hook (never run yet): one GRU half-step through tcgen05.mma.cta_group::2 on a CTA pair (csrc/umma2_selftest.cu,
  * profiles/r02_gru_design.md step 2).  out[256,256] = [x W_in^T | x W_ir^T + h W_hr^T | x W_iz^T + h W_hz^T | h W_hn^T] for hidden
  * features 0..63 from x[256,64], h[256,128], w_ih[384,64], w_hh[384,128]; workspace >= 512 KB of device memory. */

@@ -75,6 +75,10 @@ def main():
     _lib.set_coop_mode(True)
     print(f"SpMM launch:     default {t_spmm_def:.3f} ms, 64-reg variant {t_spmm_coop:.3f} ms, bit-identical: {torch.equal(u, u2)}")
     _lib.set_coop_mode(False)
+    # pre-split U (design note step 3): does the 16-byte plane store pattern cost the SpMM anything?
+    t_packed = timed(lambda: ops.cumspmm_packed(plans[0], xs[0]), args.iters)      # includes a memset of the 5 GB buffer at cfg4:
+    t_zero = timed(lambda: torch.zeros(u.numel() * 4, dtype=torch.uint8, device=dev), args.iters)   # … measured and subtracted
+    print(f"SpMM launch:     pre-split output {t_packed - t_zero:.3f} ms (default {t_spmm_def:.3f} ms)")
 
     # ---- 1b / 2. whole forward
     with torch.no_grad():

@@ -2,7 +2,9 @@
     CTGCN_UNVERIFIED_GPU_TESTS=1 python -m pytest tests/test_experimental_gpu.py -m gpu
 * ctgcn_selftest_umma_pair — one GRU half-step through tcgen05.mma.cta_group::2 on a CTA pair (csrc/umma2_selftest.cu,
   profiles/r02_gru_design.md step 2).  A trap or a wrong block tells which mechanism is off: columns [0,64) only the N = 192
-  input stream, [64,192) input + the N = 128 recurrent stream, [192,256) the N = 64 stream; rows 128.. are the follower CTA."""
+  input stream, [64,192) input + the N = 128 recurrent stream, [192,256) the N = 64 stream; rows 128.. are the follower CTA.
+* ops.cumspmm_packed — the cumulative SpMM storing U pre-split in the operand layout (csrc/spmm_packed.cu, design note step 3):
+  bit for bit the bf16 hi / lo planes of the fp32 kernel's output."""
 import ctypes as C
 import os
 
@@ -41,3 +43,21 @@ def test_umma_pair_selftest(lib, cuda_device):
         for blk, name in enumerate(("W_in x", "r", "z", "W_hn h")):
             err = cases.relerr(got[rows, 64 * blk:64 * blk + 64], ref[rows, 64 * blk:64 * blk + 64])
             assert err < 3e-5, (f"CTA {cta}", name, err)
+
+
+@pytest.mark.parametrize("n,m,k", [(1000, 6000, 4), (128, 900, 3), (4099, 30000, 7)])
+def test_cumspmm_packed_matches_the_split_of_the_fp32_kernel(n, m, k, lib, cuda_device):
+    from ctgcn_b200 import ops, synth
+    snap = synth.make_snapshot("er", n, m, k, seed=n)
+    plan = snap.plan(cuda_device)
+    x = synth.features(n, 128, 7).to(cuda_device)
+    u = ops.cumspmm(plan, x)                                            # [N, K, 128] fp32
+    packed = ops.cumspmm_packed(plan, x)                                # uint8 [tiles, K, 2, 16, 128, 16]
+    tiles = packed.shape[0]
+    bits = packed.view(torch.int16).view(tiles, plan.k, 2, 16, 128, 8)   # [tile, level, plane, kb, row, k%8]
+    rows = bits.permute(2, 0, 4, 1, 3, 5).reshape(2, tiles * 128, plan.k, 128)[:, :n]   # [plane, row, level, feature]
+    hi = u.to(torch.bfloat16)
+    lo = (u - hi.float()).to(torch.bfloat16)
+    assert torch.equal(rows[0], hi.view(torch.int16)) and torch.equal(rows[1], lo.view(torch.int16))
+    if tiles * 128 > n:                                                 # rows beyond N are left untouched
+        assert int(bits.permute(2, 0, 4, 1, 3, 5).reshape(2, tiles * 128, plan.k, 128)[:, n:].abs().sum()) == 0
