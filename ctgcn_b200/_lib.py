@@ -62,6 +62,8 @@ SIGNATURES = {
     "ctgcn_selftest_umma": (C.c_int, [_p, _p, _p, _p, _p, _p, _sz, _p]),
     "ctgcn_cumspmm_packed_bytes": (_sz, [_p]),
     "ctgcn_cumspmm_fwd_packed": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),
+    "ctgcn_core_diffusion_packed_workspace_bytes": (_sz, [_p]),
+    "ctgcn_core_diffusion_fwd_packed": (C.c_int, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _f32, _p, _i64, _p, _sz, _p]),
     "ctgcn_selftest_umma_pair": (C.c_int, [_p, _p, _p, _p, _p, _p, _sz, _p]),
     "ctgcn_core_diffusion_workspace_bytes": (_sz, [_p, _i32, _i32]),
     "ctgcn_core_diffusion_fwd": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _f32, _p, _i64, _p, _sz, _p]),

@@ -126,6 +126,7 @@ struct Params {
     int num_tiles;
     long long* trace;   // optional [24 events][64 steps] clock64 stamps of block 0 (ctgcn_debug_gru_trace), else NULL
     float* sumh_scratch;   // gru_tc_coop_kernel only: [grid][TILE_M * H] fp32
+    const uint8_t* packed_u;   // gru_tc_packed_kernel only: U pre-split by the SpMM, [tile][step][64 KB operand image] (spmm_packed.cu)
 };
 
 // debug timeline: event e of global step gs of block 0
@@ -610,8 +611,17 @@ constexpr int FOLD_BIAS_HALF = 2 * CHUNK_ROWS * 16;              // B block of o
 constexpr int SMEM_BYTES_FOLD = SM_FOLD + FOLD_ONES_BYTES + 2 * FOLD_BIAS_HALF;
 static_assert(SMEM_BYTES_FOLD <= 227 * 1024, "shared memory budget (bias-fold variant)");
 
-template <int NW, bool FOLD = false>   // gate-math warps: 8 (co-resident build, 96 registers per thread) or 16 (full register file, faster gate math)
+//
+// PACKED (mode 4): U arrives pre-split in the operand layout (ctgcn_cumspmm_fwd_packed) and is fetched by bulk copies — one lane
+// of warp 2 instead of the four loader warps (which idle at 24 registers) — and the registers they give up let the 16 gate
+// warps keep Σh in registers again (104 each) instead of the L2 scratch.  Stepping stone to two tiles in flight
+// (profiles/r02_gru_design.md step 3), where a bulk-copy ring is the only way to feed U.
+template <int NW, bool FOLD = false, bool PACKED = false>   // gate-math warps: 8 (co-resident build, 96 registers per thread) or 16 (faster gate math)
 __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
+    static_assert(!PACKED || NW == 16, "the bulk-copy-fed variant is built for 16 gate warps");
+    // setmaxnreg budgets per warpgroup: warps 0-3 | loaders 4-7 | gate warps (0 = keep the launch value)
+    //   NW = 8  (launch 96): 56 | 112 | 104      NW = 16 (launch 80): 48 | 112 | 80      PACKED (launch 80): 40 | 24 | 104
+    constexpr int WG0_REGS = PACKED ? 40 : (NW == 8 ? 56 : 48);
     constexpr int THREADS_V = 32 * (FIRST_WORKER_WARP + NW);
     constexpr int CHW = NW / 4;     // warps sharing one TMEM lane quarter = feature groups of a half
     constexpr int FPT = 64 / CHW;   // features per thread and half: 32 | 16
@@ -630,7 +640,7 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
             mbar_init(bar(BAR_W_FULL + s), 1);
             mbar_init(bar(BAR_W_EMPTY + s), 1);
         }
-        mbar_init(bar(BAR_U_READY), NUM_LOADER_WARPS);
+        mbar_init(bar(BAR_U_READY), PACKED ? 1 : NUM_LOADER_WARPS);
         mbar_init(bar(BAR_U_FREE), 1);
         mbar_init(bar(BAR_H_READY), NW);
         mbar_init(bar(BAR_ACC_FULL0), 1);
@@ -676,8 +686,7 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
     // (warps 0-3: 56, loaders 4-7: 112, workers 8-15: 104)
     if (warp == 0) {
         // ===================================================== weight producer
-        if constexpr (NW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WG0_REGS));
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             const int nx = 2 * cpx;
@@ -707,8 +716,7 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        if constexpr (NW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WG0_REGS));
         // All 32 lanes run the (warp-uniform) control flow and the barrier waits; one elected lane issues.
         {
             uint32_t stage = 0, phase = 0, gs = 0;
@@ -780,8 +788,27 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
     } else if (warp < FIRST_WORKER_WARP) {
         // ===================================================== input loaders (warps 4-7; warps 2-3 idle)
         if (warp < FIRST_LOADER_WARP) {
-            if constexpr (NW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-            else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WG0_REGS));
+            if constexpr (PACKED) {
+                // ===================================================== U producer (warp 2, one lane): the SpMM stored this tile-step's
+                // operand image contiguously — four 16 KB bulk copies straight into the U buffer, no conversion, no registers
+                if (warp == 2 && lane == 0) {
+                    uint32_t gs = 0;
+                    for (int t = 0; t < my_tiles; ++t) {
+                        const size_t tile = (size_t)blockIdx.x + (size_t)t * gridDim.x;
+                        for (int i = 0; i < p.steps; ++i, ++gs) {
+                            mbar_wait(bar(BAR_U_FREE), (gs & 1) ^ 1);       // the previous step's input MMAs released the buffer
+                            mbar_expect_tx(bar(BAR_U_READY), 2 * A_PLANE);
+                            const uint8_t* src = p.packed_u + (tile * p.steps + i) * (size_t)(2 * A_PLANE);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                bulk_g2s(sbase + SM_U + q * (A_PLANE / 2), src + q * (A_PLANE / 2), A_PLANE / 2, bar(BAR_U_READY));
+                        }
+                    }
+                }
+            }
+        } else if constexpr (PACKED) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");          // warps 4-7 have nothing to do in this variant
         } else {
             asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
             // A warp owns 32 tile rows.  Per load instruction its lanes cover 8 rows × 4 k-blocks (r = lane%8, c = lane/8):
@@ -848,7 +875,7 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
         // ===================================================== workers (warps 8-15): gate math, h, Σh, LayerNorm
         // register pools: NW = 8: 512 × 96 = 49 152 ≥ 128·56 + 128·112 + 256·104 = 48 128;
         //                 NW = 16: 768 × 80 = 61 440 = 128·48 + 128·112 + 512·80
-        if constexpr (NW == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        if constexpr (NW == 8 || PACKED) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // Σh scratch of this CTA: [16 feature blocks of 8][128 rows][8 floats] → a warp's 32 rows are 1 KB contiguous
         float* const sumh = p.sumh_scratch + (size_t)blockIdx.x * (TILE_M * H);
         const int ww = warp - FIRST_WORKER_WARP;
@@ -915,6 +942,9 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
 
         for (int t = 0; t < my_tiles; ++t) {
             const int64_t row = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + m;
+            float sum_regs[PACKED ? 2 * FPT : 1];   // PACKED: Σ_s h_s of this thread's features stays in registers
+#pragma unroll
+            for (int j = 0; j < (PACKED ? 2 * FPT : 1); ++j) sum_regs[j] = 0.f;
 
             for (int i = 0; i < p.steps; ++i, ++gs) {
                 const uint32_t par = gs & 1;
@@ -943,7 +973,7 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
                         float gr[8], gz[8], gi[8], gh[8], hold[8];
                         float* const sp = sumh + ((size_t)(f0 >> 3) * TILE_M + m) * 8;
                         float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-                        if (i > 0) {          // issued first: the L2 round trip hides under the TMEM loads and the gate math
+                        if (!PACKED && i > 0) {   // issued first: the L2 round trip hides under the TMEM loads and the gate math
                             s0 = __ldcg(reinterpret_cast<const float4*>(sp));
                             s1 = __ldcg(reinterpret_cast<const float4*>(sp) + 1);
                         }
@@ -1015,16 +1045,21 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
                             put_h8(f8, ch * FPT + sub * 8);
                             put_h8(hn8, f0);
                         }
-                        s0.x += hn8[0];
-                        s0.y += hn8[1];
-                        s0.z += hn8[2];
-                        s0.w += hn8[3];
-                        s1.x += hn8[4];
-                        s1.y += hn8[5];
-                        s1.z += hn8[6];
-                        s1.w += hn8[7];
-                        __stcg(reinterpret_cast<float4*>(sp), s0);
-                        __stcg(reinterpret_cast<float4*>(sp) + 1, s1);
+                        if constexpr (PACKED) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) sum_regs[hf * FPT + sub * 8 + j] += hn8[j];
+                        } else {
+                            s0.x += hn8[0];
+                            s0.y += hn8[1];
+                            s0.z += hn8[2];
+                            s0.w += hn8[3];
+                            s1.x += hn8[4];
+                            s1.y += hn8[5];
+                            s1.z += hn8[6];
+                            s1.w += hn8[7];
+                            __stcg(reinterpret_cast<float4*>(sp), s0);
+                            __stcg(reinterpret_cast<float4*>(sp) + 1, s1);
+                        }
                         if (threadIdx.x == FIRST_WORKER_WARP * 32) GRU_TRACE(16 + hf * 4 + sub, gs);
                     }
                     tc_fence_before();
@@ -1043,6 +1078,11 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
                 for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
                     for (int sub = 0; sub < SUBS; ++sub) {
+                        if constexpr (PACKED) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) acc_out[hf * FPT + sub * 8 + j] = sum_regs[hf * FPT + sub * 8 + j];
+                            continue;
+                        }
                         const float* sp = sumh + ((size_t)((hf * 64 + ch * FPT + sub * 8) >> 3) * TILE_M + m) * 8;
                         const float4 a0 = __ldcg(reinterpret_cast<const float4*>(sp)), a1 = __ldcg(reinterpret_cast<const float4*>(sp) + 1);
                         float* o = acc_out + hf * FPT + sub * 8;
@@ -1064,6 +1104,8 @@ __global__ void __maxnreg__(96) gru_tc_coop_kernel(const Params p) { gru_tc_sumh
 __global__ void __maxnreg__(80) gru_tc_w16_kernel(const Params p) { gru_tc_sumh_body<16>(p); }
 // the same with the input-side biases folded into the MMAs (mode 3)
 __global__ void __maxnreg__(80) gru_tc_w16f_kernel(const Params p) { gru_tc_sumh_body<16, true>(p); }
+// bulk-copy-fed U, Σh in registers, 16 gate warps (mode 4 building block; launched by launch_gru_tc_packed only)
+__global__ void __maxnreg__(80) gru_tc_packed_kernel(const Params p) { gru_tc_sumh_body<16, false, true>(p); }
 
 // ------------------------------------------------------------------------------------------------ self test
 // One half-step of a GRU cell's pre-activations for d_in = 64 through exactly the packer, chunk images, bulk copies,
@@ -1212,6 +1254,7 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
     p.num_tiles = (int)((n + TILE_M - 1) / TILE_M);
     p.trace = g_gru_trace;
     p.sumh_scratch = coop ? (float*)((char*)ws + scratch_off) : nullptr;
+    p.packed_u = nullptr;
     const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
     CTGCN_REQUIRE(!coop || grid <= 256, "gru_tc: co-resident variant supports at most 256 SMs");
     ProfScope prof(PROF_GRU, st);
@@ -1226,6 +1269,51 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
     else
         gru_tc_kernel<CTGCN_GRU_EACH_LN><<<grid, THREADS, SMEM_BYTES, st>>>(p);
     CTGCN_LAUNCH_OK("gru_tc_kernel");
+    return CTGCN_OK;
+}
+
+// EXPERIMENTAL (never run): the SUM_LN core GRU (128 → 128) fed by the pre-split U of ctgcn_cumspmm_fwd_packed.
+// ws: packed weights + biases as for launch_gru_tc (no Σh scratch).
+int launch_gru_tc_packed(const uint8_t* packed_u, int64_t n, int steps, const float* w_ih, const float* w_hh, const float* b_ih,
+                         const float* b_hh, const float* ln_w, const float* ln_b, float eps, float* y, int64_t yrs, void* ws,
+                         size_t ws_bytes, cudaStream_t st) {
+    constexpr int d_in = 128;
+    const int nchunks = 2 * chunks_per_part(d_in) + 2 * chunks_per_part(H);
+    const size_t packed_bytes = (size_t)nchunks * CHUNK_BYTES;
+    CTGCN_REQUIRE(ws && ws_bytes >= packed_bytes + 4 * H * sizeof(float), "gru_tc_packed: workspace too small");
+    CTGCN_REQUIRE((reinterpret_cast<uintptr_t>(packed_u) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (yrs & 3) == 0,
+                  "gru_tc_packed: unaligned buffers");
+    uint8_t* packed = (uint8_t*)ws;
+    float* bias4 = (float*)(packed + packed_bytes);
+    pack_weights_kernel<<<(nchunks * UNITS_PER_PLANE + 255) / 256, 256, 0, st>>>(w_ih, w_hh, b_ih, b_hh, d_in, packed, bias4, 1);
+    CTGCN_LAUNCH_OK("pack_weights_kernel");
+    int dev = 0, sms = 0;
+    CTGCN_CUDA_OK(cudaGetDevice(&dev));
+    CTGCN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SUMH));
+    Params p;
+    p.seq = nullptr;
+    p.srs = p.sss = 0;
+    p.n = n;
+    p.steps = steps;
+    p.d_in = d_in;
+    p.packed = packed;
+    p.bias4 = bias4;
+    p.ln_w = ln_w;
+    p.ln_b = ln_b;
+    p.eps = eps;
+    p.y = y;
+    p.yrs = yrs;
+    p.yss = 0;
+    p.sc = RowScatter();
+    p.num_tiles = (int)((n + TILE_M - 1) / TILE_M);
+    p.trace = g_gru_trace;
+    p.sumh_scratch = nullptr;
+    p.packed_u = packed_u;
+    const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+    ProfScope prof(PROF_GRU, st);
+    gru_tc_packed_kernel<<<grid, 32 * (FIRST_WORKER_WARP + 16), SMEM_BYTES_SUMH, st>>>(p);
+    CTGCN_LAUNCH_OK("gru_tc_packed_kernel");
     return CTGCN_OK;
 }
 

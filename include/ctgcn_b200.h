@@ -210,6 +210,13 @@ int ctgcn_spmm_linear_fwd(const ctgcn_plan* x_plan, const float* w, const float*
 size_t ctgcn_cumspmm_packed_bytes(const ctgcn_plan* plan);
 int ctgcn_cumspmm_fwd_packed(const ctgcn_plan* plan, const float* x, int64_t ldx, int d, void* u, void* stream);
 
+/* EXPERIMENTAL (never run yet): CoreDiffusion.forward for 128 -> 128 GRU layers through the pre-split U (the SpMM above, then a GRU
+ * kernel that fetches its U tiles with bulk copies; csrc/core_diffusion_packed.cu).  Arguments as ctgcn_core_diffusion_fwd. */
+size_t ctgcn_core_diffusion_packed_workspace_bytes(const ctgcn_plan* plan);
+int ctgcn_core_diffusion_fwd_packed(const ctgcn_plan* plan, const float* x, int64_t ldx, const float* w_ih, const float* w_hh,
+                                    const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps, float* y,
+                                    int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
+
 /* EXPERIMENTAL test hook (never run yet): one GRU half-step through tcgen05.mma.cta_group::2 on a CTA pair (csrc/umma2_selftest.cu,
  * profiles/r02_gru_design.md step 2).  out[256,256] = [x W_in^T | x W_ir^T + h W_hr^T | x W_iz^T + h W_hz^T | h W_hn^T] for hidden
  * features 0..63 from x[256,64], h[256,128], w_ih[384,64], w_hh[384,128]; workspace >= 512 KB of device memory. */

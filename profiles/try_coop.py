@@ -75,11 +75,6 @@ def main():
     _lib.set_coop_mode(True)
     print(f"SpMM launch:     default {t_spmm_def:.3f} ms, 64-reg variant {t_spmm_coop:.3f} ms, bit-identical: {torch.equal(u, u2)}")
     _lib.set_coop_mode(False)
-    # pre-split U (design note step 3): does the 16-byte plane store pattern cost the SpMM anything?
-    t_packed = timed(lambda: ops.cumspmm_packed(plans[0], xs[0]), args.iters)      # includes a memset of the 5 GB buffer at cfg4:
-    t_zero = timed(lambda: torch.zeros(u.numel() * 4, dtype=torch.uint8, device=dev), args.iters)   # … measured and subtracted
-    print(f"SpMM launch:     pre-split output {t_packed - t_zero:.3f} ms (default {t_spmm_def:.3f} ms)")
-
     # ---- 1b / 2. whole forward
     with torch.no_grad():
         out_ref = model(xs, plans).clone()
@@ -114,6 +109,23 @@ def main():
     print(f"CTGCN.forward {args.config}: 16 gate warps + folded biases {t_fwd_w16f:.2f} ms ({t_fwd / t_fwd_w16f:.2f}x), "
           f"relL2 vs default {rel:.2e}")
     _lib.set_coop_mode(False)
+
+    # ---- 3. LAST, because a trap here would poison the context: the pre-split-U path (profiles/r02_gru_design.md step 3)
+    try:
+        # pre-split U (design note step 3): does the 16-byte plane store pattern cost the SpMM anything?
+        t_packed = timed(lambda: ops.cumspmm_packed(plans[0], xs[0]), args.iters)      # includes a memset of the 5 GB buffer at cfg4:
+        t_zero = timed(lambda: torch.zeros(u.numel() * 4, dtype=torch.uint8, device=dev), args.iters)   # … measured and subtracted
+        print(f"SpMM launch:     pre-split output {t_packed - t_zero:.3f} ms (default {t_spmm_def:.3f} ms)")
+        # bulk-copy-fed GRU (16 gate warps, Σh in registers) behind the pre-split SpMM: one CoreDiffusion call, default vs packed
+        cd_args = (*w, lay.norm.weight, lay.norm.bias, lay.norm.eps)
+        y_def = ops.core_diffusion(plans[0], xs[0], *cd_args)
+        t_cd_def = timed(lambda: ops.core_diffusion(plans[0], xs[0], *cd_args), args.iters)
+        y_pk = ops.core_diffusion_packed(plans[0], xs[0], *cd_args)
+        t_cd_pk = timed(lambda: ops.core_diffusion_packed(plans[0], xs[0], *cd_args), args.iters)
+        rel = ((y_pk - y_def).norm() / y_def.norm()).item()
+        print(f"CoreDiffusion call: default {t_cd_def:.3f} ms, pre-split U + bulk-copy-fed GRU {t_cd_pk:.3f} ms, relL2 {rel:.1e}")
+    except Exception as exc:  # noqa: BLE001 - report and keep the measurements above
+        print("pre-split-U path failed:", repr(exc))
 
 
 if __name__ == "__main__":
