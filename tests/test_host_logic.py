@@ -159,7 +159,10 @@ def test_product_never_touches_the_oracle():
             assert "fake_backend" not in src, f
     bench = open(os.path.join(root, "bench.py")).read()
     uses = [m.start() for m in re.finditer(r"from oracle import", bench)]
-    assert len(uses) == 1 and bench[:uses[0]].rfind("def cpu_reference_sample") > bench[:uses[0]].rfind("\ndef main")
+    # … exactly once, inside the CPU-baseline class (used by the cpu_baseline leg and by --impl reference), which precedes main()
+    head = bench[:uses[0]]
+    assert len(uses) == 1 and head.rfind("\nclass CpuReference") >= 0 and "\ndef " not in head[head.rfind("\nclass CpuReference"):]
+    assert bench.find("\ndef main") > uses[0]
 
 
 def test_import_without_the_shared_library_fails_loudly(tmp_path):
