@@ -16,6 +16,7 @@ of random numbers — the reference reseeds from the OS on every call, so its dr
 """
 from __future__ import annotations
 
+import itertools
 import random
 
 import numpy as np
@@ -34,7 +35,7 @@ def _csr_from_rows(rows):
     lens = np.fromiter((len(r) for r in rows), dtype=np.int64, count=len(rows))
     ptr = np.zeros(len(rows) + 1, dtype=np.int64)
     np.cumsum(lens, out=ptr[1:])
-    idx = np.fromiter((c for r in rows for c in r), dtype=np.int32, count=int(ptr[-1]))
+    idx = np.fromiter(itertools.chain.from_iterable(rows), dtype=np.int32, count=int(ptr[-1]))
     return ptr, idx
 
 
