@@ -27,6 +27,8 @@ step pair_umma   90 env CTGCN_UNVERIFIED_GPU_TESTS=1 python -m pytest tests/test
 step coop_cfg2  150 python profiles/try_coop.py --config cfg2
 step coop_cfg4  240 python profiles/try_coop.py --config cfg4 --iters 5
 step hubsplit   150 python profiles/try_hubsplit.py
+# context number: the reference's own library calls (cuSPARSE / cuDNN through torch) on the GPU next to this repo's forward
+step library    150 python profiles/library_gpu_baseline.py --config cfg2
 step bench_cfg4 200 python bench.py --steps 10 --warmup 3
 # launch list of the default bench command's timed region (per-launch times under ncu are cold-cache: compare SHARES)
 step launches   200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
