@@ -151,6 +151,56 @@ __device__ __forceinline__ float rcp_approx(float v) {
 }
 #endif
 
+// Packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 — one issue slot for two IEEE operations, same rounding as the scalar forms).
+// Used by the PK2 build of the experimental gate math only: the gate warps are issue-bound (≈ 30 fp32 instructions per feature).
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+
+// packed forms of tc_common.cuh's split2 / join8 (same values: a − hi is one rounding either way)
+__device__ __forceinline__ void split2_pk(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    const float2 r = fma2(make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u)), make_float2(-1.f, -1.f),
+                          make_float2(a, b));
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(r.x, r.y);
+    lo = *reinterpret_cast<const uint32_t*>(&l2);
+}
+__device__ __forceinline__ void split8_pk(const float (&v)[8], uint4& hi, uint4& lo) {
+    split2_pk(v[0], v[1], hi.x, lo.x);
+    split2_pk(v[2], v[3], hi.y, lo.y);
+    split2_pk(v[4], v[5], hi.z, lo.z);
+    split2_pk(v[6], v[7], hi.w, lo.w);
+}
+__device__ __forceinline__ void join8_pk(const uint4& hi, const uint4& lo, float (&v)[8]) {
+    const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float2 r = add2(make_float2(bf_lo(h[q]), bf_hi(h[q])), make_float2(bf_lo(l[q]), bf_hi(l[q])));
+        v[2 * q] = r.x;
+        v[2 * q + 1] = r.y;
+    }
+}
+
 // One 24 KB weight chunk (192 rows × 32 k): 2 K-steps × 3 split products (hi·hi, lo·hi, hi·lo) of N = 192 into 192
 // consecutive accumulator columns starting at d_tmem.  a_lo32 / b_lo32: descriptor low words of the A hi plane at this
 // chunk's first k and of the chunk's hi plane.
@@ -616,7 +666,8 @@ static_assert(SMEM_BYTES_FOLD <= 227 * 1024, "shared memory budget (bias-fold va
 // of warp 2 instead of the four loader warps (which idle at 24 registers) — and the registers they give up let the 16 gate
 // warps keep Σh in registers again (104 each) instead of the L2 scratch.  Stepping stone to two tiles in flight
 // (profiles/r02_gru_design.md step 3), where a bulk-copy ring is the only way to feed U.
-template <int NW, bool FOLD = false, bool PACKED = false>   // gate-math warps: 8 (co-resident build, 96 registers per thread) or 16 (faster gate math)
+// PK2 (mode 5): the gate math on packed fp32 pairs (helpers above) — bit-identical arithmetic, about half the issue slots.
+template <int NW, bool FOLD = false, bool PACKED = false, bool PK2 = false>   // gate-math warps: 8 (co-resident build, 96 registers per thread) or 16 (faster gate math)
 __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
     static_assert(!PACKED || NW == 16, "the bulk-copy-fed variant is built for 16 gate warps");
     // setmaxnreg budgets per warpgroup: warps 0-3 | loaders 4-7 | gate warps (0 = keep the launch value)
@@ -955,7 +1006,8 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
                     if (f8[0] != 12345.678f) return;   // timing experiment: never true in practice
 #endif
                     uint4 hi, lo;
-                    split8(f8, hi, lo);
+                    if constexpr (PK2) split8_pk(f8, hi, lo);
+                    else split8(f8, hi, lo);
                     const int kb = f >> 3;
                     *reinterpret_cast<uint4*>(h_hi + kb * (TILE_M * 16) + m * 16) = hi;
                     *reinterpret_cast<uint4*>(h_hi + A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
@@ -985,7 +1037,8 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
                             const int kb = f0 >> 3;
                             const uint4 hi = *reinterpret_cast<const uint4*>(h_hi + kb * (TILE_M * 16) + m * 16);
                             const uint4 lo = *reinterpret_cast<const uint4*>(h_hi + A_PLANE + kb * (TILE_M * 16) + m * 16);
-                            join8(hi, lo, hold);
+                            if constexpr (PK2) join8_pk(hi, lo, hold);
+                            else join8(hi, lo, hold);
                         } else {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) gh[j] = hold[j] = 0.f;
@@ -995,6 +1048,59 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
                         // (ex2 → rcp → ex2 → rcp) are interleaved.  Pre-activations are pre-scaled (pack_weights_kernel):
                         // sigmoid(a) = 1/(1 + 2^a'), tanh(s) = 1 − 2/(1 + 2^s'); one reciprocal serves r and z.
                         float hn8[8], ea[8], eb[8], zz[8];
+                        if constexpr (PK2) {
+                            // the same operations in the same order on pairs (j, j+1): FADD2 / FMUL2 / FFMA2, MUFU and min stay scalar
+                            const float2 one = make_float2(1.f, 1.f), mtwo = make_float2(-2.f, -2.f), mone = make_float2(-1.f, -1.f);
+                            float2 a2[4], b2[4], i2[4], h2[4], z2[4], o2[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                a2[q] = make_float2(gr[2 * q], gr[2 * q + 1]);
+                                b2[q] = make_float2(gz[2 * q], gz[2 * q + 1]);
+                                i2[q] = make_float2(gi[2 * q], gi[2 * q + 1]);
+                                h2[q] = make_float2(gh[2 * q], gh[2 * q + 1]);
+                                if constexpr (!FOLD) {
+                                    a2[q] = add2(a2[q], *reinterpret_cast<const float2*>(bias + f0 + 2 * q));
+                                    b2[q] = add2(b2[q], *reinterpret_cast<const float2*>(bias + H + f0 + 2 * q));
+                                    i2[q] = add2(i2[q], *reinterpret_cast<const float2*>(bias + 2 * H + f0 + 2 * q));
+                                }
+                                h2[q] = add2(h2[q], *reinterpret_cast<const float2*>(bias + 3 * H + f0 + 2 * q));
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                a2[q] = make_float2(ex2_approx(a2[q].x), ex2_approx(a2[q].y));
+                                b2[q] = make_float2(ex2_approx(b2[q].x), ex2_approx(b2[q].y));
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                a2[q] = add2(one, make_float2(fminf(a2[q].x, 1e18f), fminf(a2[q].y, 1e18f)));
+                                b2[q] = add2(one, make_float2(fminf(b2[q].x, 1e18f), fminf(b2[q].y, 1e18f)));
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 pr = mul2(a2[q], b2[q]);
+                                o2[q] = make_float2(rcp_approx(pr.x), rcp_approx(pr.y));
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                z2[q] = mul2(o2[q], a2[q]);                                   // z
+                                i2[q] = fma2(mul2(o2[q], b2[q]), h2[q], i2[q]);               // W_in x + b_in + r ⊙ (W_hn h + b_hn)
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) i2[q] = make_float2(ex2_approx(i2[q].x), ex2_approx(i2[q].y));
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 dn = add2(one, i2[q]);
+                                i2[q] = make_float2(rcp_approx(dn.x), rcp_approx(dn.y));
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 nn = fma2(mtwo, i2[q], one);                     // tanh
+                                const float2 dl = fma2(nn, mone, make_float2(hold[2 * q], hold[2 * q + 1]));   // h − n (one rounding, as hold − nn)
+                                const float2 hv = fma2(z2[q], dl, nn);                        // (1 − z) n + z h
+                                hn8[2 * q] = hv.x;
+                                hn8[2 * q + 1] = hv.y;
+                            }
+                        } else {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             if constexpr (FOLD) {          // b_r, b_z, b_in are already in the accumulators
@@ -1033,6 +1139,7 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
                             const float nn = fmaf(-2.f, gi[j], 1.f);                         // tanh
                             hn8[j] = fmaf(zz[j], hold[j] - nn, nn);                          // (1 − z) n + z h
                         }
+                        }   // !PK2
                         if (hf == 0) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) h0[sub * 8 + j] = hn8[j];
@@ -1048,6 +1155,13 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
                         if constexpr (PACKED) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) sum_regs[hf * FPT + sub * 8 + j] += hn8[j];
+                        } else if constexpr (PK2) {
+                            const float2 t0 = add2(make_float2(s0.x, s0.y), make_float2(hn8[0], hn8[1]));
+                            const float2 t1 = add2(make_float2(s0.z, s0.w), make_float2(hn8[2], hn8[3]));
+                            const float2 t2 = add2(make_float2(s1.x, s1.y), make_float2(hn8[4], hn8[5]));
+                            const float2 t3 = add2(make_float2(s1.z, s1.w), make_float2(hn8[6], hn8[7]));
+                            __stcg(reinterpret_cast<float4*>(sp), make_float4(t0.x, t0.y, t1.x, t1.y));
+                            __stcg(reinterpret_cast<float4*>(sp) + 1, make_float4(t2.x, t2.y, t3.x, t3.y));
                         } else {
                             s0.x += hn8[0];
                             s0.y += hn8[1];
@@ -1106,6 +1220,8 @@ __global__ void __maxnreg__(80) gru_tc_w16_kernel(const Params p) { gru_tc_sumh_
 __global__ void __maxnreg__(80) gru_tc_w16f_kernel(const Params p) { gru_tc_sumh_body<16, true>(p); }
 // bulk-copy-fed U, Σh in registers, 16 gate warps (mode 4 building block; launched by launch_gru_tc_packed only)
 __global__ void __maxnreg__(80) gru_tc_packed_kernel(const Params p) { gru_tc_sumh_body<16, false, true>(p); }
+// mode 5: mode 3 with the gate math on packed fp32 pairs
+__global__ void __maxnreg__(80) gru_tc_w16fp_kernel(const Params p) { gru_tc_sumh_body<16, true, false, true>(p); }
 
 // ------------------------------------------------------------------------------------------------ self test
 // One half-step of a GRU cell's pre-activations for d_in = 64 through exactly the packer, chunk images, bulk copies,
@@ -1192,7 +1308,7 @@ static long long* g_gru_trace = nullptr;
 void set_gru_trace(long long* buf) { g_gru_trace = buf; }
 // 0 default kernels | 1 co-resident builds (gru_tc_coop_kernel, 64-register SpMM) | 2 gru_tc_w16_kernel | 3 gru_tc_w16f_kernel
 static std::atomic<int> g_coop{0};
-void set_coop_mode(int mode) { g_coop.store(mode >= 1 && mode <= 3 ? mode : 0); }
+void set_coop_mode(int mode) { g_coop.store(mode >= 1 && mode <= 3 ? mode : (mode == 5 ? 5 : 0)); }   // 4 is the separate packed entry point
 int coop_mode() { return g_coop.load(); }
 constexpr int SMEM_BYTES_SUMH = SMEM_BYTES + 4096;   // + the LayerNorm exchange area [2][NW/4][128] fp32 of gru_tc_sumh_body
 static_assert(SMEM_BYTES_SUMH <= 227 * 1024, "shared memory budget");
@@ -1233,6 +1349,7 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
         CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SUMH));
         CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_w16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SUMH));
         CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_w16f_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_FOLD));
+        CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_w16fp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_FOLD));
         coop_ready = true;
     }
     Params p;
@@ -1264,6 +1381,8 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
         gru_tc_w16_kernel<<<grid, 32 * (FIRST_WORKER_WARP + 16), SMEM_BYTES_SUMH, st>>>(p);
     else if (coop == 3)
         gru_tc_w16f_kernel<<<grid, 32 * (FIRST_WORKER_WARP + 16), SMEM_BYTES_FOLD, st>>>(p);
+    else if (coop == 5)
+        gru_tc_w16fp_kernel<<<grid, 32 * (FIRST_WORKER_WARP + 16), SMEM_BYTES_FOLD, st>>>(p);
     else if (mode == CTGCN_GRU_SUM_LN)
         gru_tc_kernel<CTGCN_GRU_SUM_LN><<<grid, THREADS, SMEM_BYTES, st>>>(p);
     else

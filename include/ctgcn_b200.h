@@ -133,8 +133,10 @@ int ctgcn_set_gru_impl(int impl);
  * cumulative-SpMM block (HBM-bound) can be co-resident on every SM with the tcgen05 GRU kernel (tensor-bound) of another
  * snapshot / row chunk launched on a second stream.  mode 2: the tcgen05 SUM_LN GRU kernel with 16 instead of 8 gate-math
  * warps.  mode 3: mode 2 with the input-side biases added by one extra MMA per input part instead of by the gate warps (the
- * bias enters as bf16 hi+lo: results agree with the default kernels to ~1e-6, not bit for bit).  All keep the running sum of
- * h in an L2-resident scratch instead of registers; modes 1 and 2 give the same results as the default kernels. */
+ * bias enters as bf16 hi+lo: results agree with the default kernels to ~1e-6, not bit for bit).  mode 5: mode 3 with the gate math
+ * on packed fp32 pairs (FADD2 / FMUL2 / FFMA2: same arithmetic as mode 3, fewer issue slots).  All keep the running sum of h in an
+ * L2-resident scratch instead of registers; modes 1 and 2 give the same results as the default kernels.  (4 is not a mode: the
+ * bulk-copy-fed variant has an entry point of its own, ctgcn_core_diffusion_fwd_packed.) */
 int ctgcn_set_coop_mode(int mode);
 /* debug: when non-NULL, block 0 of every following tcgen05 GRU launch writes clock64() stamps of its pipeline events
  * into device_buf[24 events][64 steps] (int64); NULL switches it off. */

@@ -72,6 +72,10 @@ def main():
     t_w16f = timed(lambda: ops.rnn_seq(u, *w, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN), args.iters)
     rel = ((got16f - ref).norm() / ref.norm()).item()
     print(f"core GRU launch: 16 gate warps + folded biases {t_w16f:.3f} ms, relL2 vs default {rel:.2e} (expect ~1e-6; bar 1e-4)")
+    _lib.set_coop_mode(5)     # mode 3 with FADD2 / FMUL2 / FFMA2 gate math: the same arithmetic, so bit-identical to mode 3
+    got16p = ops.rnn_seq(u, *w, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN)
+    t_w16p = timed(lambda: ops.rnn_seq(u, *w, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN), args.iters)
+    print(f"core GRU launch: … + packed fp32x2 gate math {t_w16p:.3f} ms, bit-identical to mode 3: {torch.equal(got16f, got16p)}")
     _lib.set_coop_mode(True)
     print(f"SpMM launch:     default {t_spmm_def:.3f} ms, 64-reg variant {t_spmm_coop:.3f} ms, bit-identical: {torch.equal(u, u2)}")
     _lib.set_coop_mode(False)
