@@ -652,8 +652,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
 // FOLD (mode 3): the input-side biases are added by the tensor core instead of the gate warps.  One extra K = 16 MMA per
 // input part, A = a resident block whose k = 0 and k = 1 columns are 1.0, B = a resident block holding bf16 hi (k = 0) and
 // lo (k = 1) of the half's [b_in | b_ir + b_hr | b_iz + b_hz] rows, opens the accumulation (it replaces the "fresh" MMA):
-// +2 of 96 MMAs per tile-step, and the gate warps drop 24 of their 32 broadcast shared-memory loads per 8-feature pass
-// (only b_hn is still added there) — their shared-memory wavefronts compete with the operand fetch of the N = 192 MMA
+// +2 of 96 MMAs per tile-step, and the gate warps drop 24 of the 80 FADDs and 6 of the 8 broadcast LDS.128 of an 8-feature
+// pass (only b_hn is still added there) — their shared-memory wavefronts compete with the operand fetch of the N = 192 MMA
 // streams (profiles/r01_gru_timeline.md).
 constexpr int SM_FOLD = (SMEM_BYTES + 4096 + 127) / 128 * 128;   // after the LayerNorm exchange area of the Σh-scratch variants
 constexpr int FOLD_ONES_BYTES = 2 * TILE_M * 16;                 // A block  [2 k-blocks][128 rows][8 bf16]
