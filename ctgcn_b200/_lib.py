@@ -124,7 +124,7 @@ def set_workspace_cap(nbytes: int) -> None:
 def set_coop_mode(mode) -> None:
     """EXPERIMENTAL: 0 / False default kernels, 1 / True reduced-register variants for SpMM / GRU co-residency, 2 the SUM_LN GRU
     kernel with 16 gate-math warps, 3 the same with the input-side biases folded into the MMAs, 5 = 3 with the gate math on packed fp32
-    pairs (see csrc/gru_tc.cu)."""
+    pairs, 6 = 5 with the reordered MMA schedule / early accumulator release (see csrc/gru_tc.cu)."""
     check(lib.ctgcn_set_coop_mode(int(mode)), "ctgcn_set_coop_mode")
 
 

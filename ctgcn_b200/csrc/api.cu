@@ -114,7 +114,7 @@ size_t gru_tc_coop_scratch_bytes();
 }
 // EXPERIMENTAL: co-resident kernel variants (gru_tc_coop_kernel + the 64-register SpMM), see gru_tc.cu.  Default off.
 extern "C" int ctgcn_set_coop_mode(int mode) {
-    CTGCN_REQUIRE((mode >= 0 && mode <= 3) || mode == 5, "set_coop_mode: mode %d is not one of 0, 1, 2, 3, 5", mode);
+    CTGCN_REQUIRE((mode >= 0 && mode <= 3) || mode == 5 || mode == 6, "set_coop_mode: mode %d is not one of 0, 1, 2, 3, 5, 6", mode);
     set_coop_mode(mode);
     return CTGCN_OK;
 }

@@ -667,7 +667,11 @@ static_assert(SMEM_BYTES_FOLD <= 227 * 1024, "shared memory budget (bias-fold va
 // warps keep Σh in registers again (104 each) instead of the L2 scratch.  Stepping stone to two tiles in flight
 // (profiles/r02_gru_design.md step 3), where a bulk-copy ring is the only way to feed U.
 // PK2 (mode 5): the gate math on packed fp32 pairs (helpers above) — bit-identical arithmetic, about half the issue slots.
-template <int NW, bool FOLD = false, bool PACKED = false, bool PK2 = false>   // gate-math warps: 8 (co-resident build, 96 registers per thread) or 16 (faster gate math)
+// REORD (mode 6): both input parts of step i+1 are issued BEFORE h_i is awaited — the gate warps release an accumulator set right
+// after the last TMEM load of its last pass (the values are in registers by then), not after the math — so that only the two
+// recurrent parts (2 × 2.3 K cycles) stand between "h ready" and the last accumulator set; weight chunks are consumed in packed
+// order (X half0, X half1, H half0, H half1).  Model with 16 gate warps: period ≈ 10.3 K cycles instead of 12.2 K (design note).
+template <int NW, bool FOLD = false, bool PACKED = false, bool PK2 = false, bool REORD = false>   // gate-math warps: 8 (co-resident build, 96 registers per thread) or 16 (faster gate math)
 __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
     static_assert(!PACKED || NW == 16, "the bulk-copy-fed variant is built for 16 gate warps");
     // setmaxnreg budgets per warpgroup: warps 0-3 | loaders 4-7 | gate warps (0 = keep the launch value)
@@ -746,9 +750,9 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
                     // consumption order of the MMA issuer: X half0, [H half0], X half1, [H half1]
                     // (packed order is X half0, X half1, H half0, H half1)
                     for (int seg = 0; seg < 4; ++seg) {
-                        const bool rec = seg & 1;
+                        const bool rec = REORD ? seg >= 2 : (seg & 1);
                         if (rec && i == 0) continue;
-                        const int half = seg >> 1;
+                        const int half = REORD ? (seg & 1) : (seg >> 1);
                         const int first = rec ? nx + half * cph : half * cpx;
                         const int count = rec ? cph : cpx;
                         for (int c = first; c < first + count; ++c) {
@@ -812,6 +816,26 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
                     if (lane == 0) GRU_TRACE(1, gs);
                     run_part(u_desc, p.d_in, 0, false);
                     if (lane == 0) GRU_TRACE(2, gs);
+                    if constexpr (REORD) {
+                        mbar_wait(bar(BAR_ACC_FREE1), par ^ 1);
+                        tc_fence_after();
+                        if (lane == 0) GRU_TRACE(5, gs);
+                        run_part(u_desc, p.d_in, 1, false);
+                        commit(BAR_U_FREE);
+                        if (lane == 0) GRU_TRACE(6, gs);
+                        if (i > 0) {
+                            mbar_wait(bar(BAR_H_READY), par ^ 1);
+                            tc_fence_after();
+                            if (lane == 0) GRU_TRACE(3, gs);
+                            run_part(h_desc, H, 0, true);
+                        }
+                        commit(BAR_ACC_FULL0);
+                        if (lane == 0) GRU_TRACE(4, gs);
+                        if (i > 0) run_part(h_desc, H, 1, true);
+                        commit(BAR_ACC_FULL1);
+                        if (lane == 0) GRU_TRACE(7, gs);
+                        continue;
+                    }
                     if (i == 0) {
                         commit(BAR_ACC_FULL0);
                     } else {
@@ -1044,6 +1068,13 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
                             for (int j = 0; j < 8; ++j) gh[j] = hold[j] = 0.f;
                         }
                         tmem_ld_wait();
+                        if constexpr (REORD) {
+                            if (sub == SUBS - 1) {   // every accumulator value of this half is in registers: hand the set back now
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(bar(BAR_ACC_FREE0 + hf));
+                            }
+                        }
                         // Gate math written stage by stage over the 8 features so that the 8 dependent chains
                         // (ex2 → rcp → ex2 → rcp) are interleaved.  Pre-activations are pre-scaled (pack_weights_kernel):
                         // sigmoid(a) = 1/(1 + 2^a'), tanh(s) = 1 − 2/(1 + 2^s'); one reciprocal serves r and z.
@@ -1176,9 +1207,11 @@ __device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
                         }
                         if (threadIdx.x == FIRST_WORKER_WARP * 32) GRU_TRACE(16 + hf * 4 + sub, gs);
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(BAR_ACC_FREE0 + hf));
+                    if constexpr (!REORD) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar(BAR_ACC_FREE0 + hf));
+                    }
                 }
                 // h_i is complete in shared memory: the next step's recurrent MMAs may read it
                 fence_proxy_async();
@@ -1222,6 +1255,8 @@ __global__ void __maxnreg__(80) gru_tc_w16f_kernel(const Params p) { gru_tc_sumh
 __global__ void __maxnreg__(80) gru_tc_packed_kernel(const Params p) { gru_tc_sumh_body<16, false, true>(p); }
 // mode 5: mode 3 with the gate math on packed fp32 pairs
 __global__ void __maxnreg__(80) gru_tc_w16fp_kernel(const Params p) { gru_tc_sumh_body<16, true, false, true>(p); }
+// mode 6: mode 5 with the reordered MMA schedule and the early accumulator release
+__global__ void __maxnreg__(80) gru_tc_w16r_kernel(const Params p) { gru_tc_sumh_body<16, true, false, true, true>(p); }
 
 // ------------------------------------------------------------------------------------------------ self test
 // One half-step of a GRU cell's pre-activations for d_in = 64 through exactly the packer, chunk images, bulk copies,
@@ -1308,7 +1343,7 @@ static long long* g_gru_trace = nullptr;
 void set_gru_trace(long long* buf) { g_gru_trace = buf; }
 // 0 default kernels | 1 co-resident builds (gru_tc_coop_kernel, 64-register SpMM) | 2 gru_tc_w16_kernel | 3 gru_tc_w16f_kernel
 static std::atomic<int> g_coop{0};
-void set_coop_mode(int mode) { g_coop.store(mode >= 1 && mode <= 3 ? mode : (mode == 5 ? 5 : 0)); }   // 4 is the separate packed entry point
+void set_coop_mode(int mode) { g_coop.store((mode >= 1 && mode <= 3) || mode == 5 || mode == 6 ? mode : 0); }   // 4: separate entry point
 int coop_mode() { return g_coop.load(); }
 constexpr int SMEM_BYTES_SUMH = SMEM_BYTES + 4096;   // + the LayerNorm exchange area [2][NW/4][128] fp32 of gru_tc_sumh_body
 static_assert(SMEM_BYTES_SUMH <= 227 * 1024, "shared memory budget");
@@ -1350,6 +1385,7 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
         CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_w16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SUMH));
         CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_w16f_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_FOLD));
         CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_w16fp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_FOLD));
+        CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_w16r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_FOLD));
         coop_ready = true;
     }
     Params p;
@@ -1383,6 +1419,8 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
         gru_tc_w16f_kernel<<<grid, 32 * (FIRST_WORKER_WARP + 16), SMEM_BYTES_FOLD, st>>>(p);
     else if (coop == 5)
         gru_tc_w16fp_kernel<<<grid, 32 * (FIRST_WORKER_WARP + 16), SMEM_BYTES_FOLD, st>>>(p);
+    else if (coop == 6)
+        gru_tc_w16r_kernel<<<grid, 32 * (FIRST_WORKER_WARP + 16), SMEM_BYTES_FOLD, st>>>(p);
     else if (mode == CTGCN_GRU_SUM_LN)
         gru_tc_kernel<CTGCN_GRU_SUM_LN><<<grid, THREADS, SMEM_BYTES, st>>>(p);
     else

@@ -134,7 +134,8 @@ int ctgcn_set_gru_impl(int impl);
  * snapshot / row chunk launched on a second stream.  mode 2: the tcgen05 SUM_LN GRU kernel with 16 instead of 8 gate-math
  * warps.  mode 3: mode 2 with the input-side biases added by one extra MMA per input part instead of by the gate warps (the
  * bias enters as bf16 hi+lo: results agree with the default kernels to ~1e-6, not bit for bit).  mode 5: mode 3 with the gate math
- * on packed fp32 pairs (FADD2 / FMUL2 / FFMA2: same arithmetic as mode 3, fewer issue slots).  All keep the running sum of h in an
+ * on packed fp32 pairs (FADD2 / FMUL2 / FFMA2: same arithmetic as mode 3, fewer issue slots).  mode 6: mode 5 with both input
+ * parts of the next step issued before h is awaited (accumulator sets released right after their last TMEM load).  All keep the running sum of h in an
  * L2-resident scratch instead of registers; modes 1 and 2 give the same results as the default kernels.  (4 is not a mode: the
  * bulk-copy-fed variant has an entry point of its own, ctgcn_core_diffusion_fwd_packed.) */
 int ctgcn_set_coop_mode(int mode);

@@ -76,6 +76,10 @@ def main():
     got16p = ops.rnn_seq(u, *w, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN)
     t_w16p = timed(lambda: ops.rnn_seq(u, *w, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN), args.iters)
     print(f"core GRU launch: … + packed fp32x2 gate math {t_w16p:.3f} ms, bit-identical to mode 3: {torch.equal(got16f, got16p)}")
+    _lib.set_coop_mode(6)     # + both input parts issued before h is awaited, accumulator sets released after their last TMEM load
+    got16r = ops.rnn_seq(u, *w, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN)
+    t_w16r = timed(lambda: ops.rnn_seq(u, *w, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN), args.iters)
+    print(f"core GRU launch: … + reordered MMA schedule {t_w16r:.3f} ms, bit-identical to mode 3: {torch.equal(got16f, got16r)}")
     _lib.set_coop_mode(True)
     print(f"SpMM launch:     default {t_spmm_def:.3f} ms, 64-reg variant {t_spmm_coop:.3f} ms, bit-identical: {torch.equal(u, u2)}")
     _lib.set_coop_mode(False)
@@ -112,6 +116,12 @@ def main():
     rel = ((out_w16f - out_ref).norm() / out_ref.norm()).item()
     print(f"CTGCN.forward {args.config}: 16 gate warps + folded biases {t_fwd_w16f:.2f} ms ({t_fwd / t_fwd_w16f:.2f}x), "
           f"relL2 vs default {rel:.2e}")
+    _lib.set_coop_mode(6)
+    with torch.no_grad():
+        out_w16r = model(xs, plans).clone()
+        t_fwd_w16r = timed(lambda: model(xs, plans), args.iters)
+    print(f"CTGCN.forward {args.config}: mode 6 (16 gate warps, folded biases, packed math, reordered MMAs) {t_fwd_w16r:.2f} ms "
+          f"({t_fwd / t_fwd_w16r:.2f}x), bit-identical to mode 3: {torch.equal(out_w16f, out_w16r)}")
     _lib.set_coop_mode(False)
 
     # ---- 3. LAST, because a trap here would poison the context: the pre-split-U path (profiles/r02_gru_design.md step 3)
