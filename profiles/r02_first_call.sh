@@ -24,6 +24,13 @@ step tests      240 python -m pytest tests -m gpu -x -q
 # opt-in until green once.  Separate processes: a trap in one must not take the other down.
 step loss_tests 120 env CTGCN_UNVERIFIED_GPU_TESTS=1 python -m pytest tests/test_loss_gpu.py -m gpu -q
 step pair_umma   90 env CTGCN_UNVERIFIED_GPU_TESTS=1 python -m pytest tests/test_experimental_gpu.py -m gpu -q
+# every experimental core-GRU build in a process of its own (a trap in one must not cost the others); checksums of modes 3, 5, 6 must agree
+for m in 2 3 5 6; do
+    step "mode${m}_cfg2" 60 python profiles/try_mode.py --mode "$m" --config cfg2
+done
+for m in 2 3 5 6; do
+    step "mode${m}_cfg4" 90 python profiles/try_mode.py --mode "$m" --config cfg4 --iters 5
+done
 step coop_cfg2  150 python profiles/try_coop.py --config cfg2
 step coop_cfg4  240 python profiles/try_coop.py --config cfg4 --iters 5
 step hubsplit   150 python profiles/try_hubsplit.py
