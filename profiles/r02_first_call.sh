@@ -2,7 +2,7 @@
 # First GPU call of round 2 in ONE gpurun invocation (runbook: profiles/r02_runbook.md).  Every step has its own timeout and
 # writes into gpurun_out/, so a step that traps or hangs costs its own limit, not the call.
 #
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash profiles/r02_first_call.sh'
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash profiles/r02_first_call.sh'
 #
 # Order: the green-suite check first (so that the round starts from a known state), then the unmeasured experimental modes at
 # configs[1] size (numerics + first timings), then configs[3] size, then the bench line and the launch list of the default path.
