@@ -209,7 +209,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "all_to_all", "all_gather", "p2p"])
     ap.add_argument("--no-numa-bind", action="store_true",
-                    help="multi-GPU runs: do not bind each rank to the CPUs / memory of its GPU's NUMA node")
+                    help="do not place this rank's pinned buffers (multi-GPU: and its CPU affinity) on its GPU's NUMA node")
     ap.add_argument("--coop", action="store_true",
                     help="EXPERIMENTAL (unmeasured): SpMM(t+1) co-resident with GRU(t), single GPU only (DESIGN.md §9)")
     args = ap.parse_args()
@@ -255,9 +255,10 @@ def main():
     import ctgcn_b200 as pkg
     from ctgcn_b200 import _lib, dist, hostmem, synth
 
-    # one process per GPU on a multi-socket host: keep this rank's pinned buffers next to its GPU (hostmem.py).  Single-GPU
-    # runs are left alone (the CPU baseline on rank 0 uses every host core).
-    host_numa = hostmem.bind_host_to_gpu(local_rank) if world > 1 and not args.no_numa_bind else None
+    # Keep this rank's pinned buffers next to its GPU (hostmem.py): the e2e step is PCIe-bound (4.1 GB each way per step at
+    # cfg4), and DMA to pages on the other socket also crosses the inter-socket link.  One process per GPU: CPUs and memory;
+    # a single-GPU run only PREFERS the GPU's node for new pages (the CPU baseline on rank 0 keeps every host core).
+    host_numa = None if args.no_numa_bind else hostmem.bind_host_to_gpu(local_rank, cpus=world > 1, memory=True)
 
     assert _lib.lib.ctgcn_device_check() == 0, _lib.last_error()
     _lib.set_gru_impl({"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tcgen05": _lib.IMPL_TCGEN05}[args.gru_impl])
