@@ -438,6 +438,7 @@ def main():
         "other_kernel_ms": other_ms,
     }
     if not args.no_cpu_baseline and world == 1:
+        hostmem.reset_memory_policy()             # the CPU baseline allocates wherever its threads run
         base = cpu_reference_sample(cfg)
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))

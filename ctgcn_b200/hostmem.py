@@ -68,6 +68,18 @@ def _prefer_node(node: int) -> bool:
         return False
 
 
+def reset_memory_policy() -> bool:
+    """Back to the default page placement (MPOL_DEFAULT) for the calling thread."""
+    nr = _SYS_SET_MEMPOLICY.get(os.uname().machine)
+    if nr is None:
+        return False
+    try:
+        libc = ctypes.CDLL(None, use_errno=True)
+        return libc.syscall(ctypes.c_long(nr), ctypes.c_int(0), None, ctypes.c_ulong(0)) == 0
+    except (OSError, AttributeError, ValueError):
+        return False
+
+
 def bind_host_to_gpu(device_index: int, cpus: bool = True, memory: bool = True) -> dict:
     """Pin the calling process to the CPUs of the GPU's NUMA node and prefer that node for new pages.  Never raises;
     returns {"node": int|None, "cpus": n_bound|None, "mem_preferred": bool, "note": str}."""
