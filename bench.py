@@ -210,10 +210,6 @@ def main():
     ap.add_argument("--exchange", default="auto", choices=["auto", "all_to_all", "all_gather", "p2p"])
     ap.add_argument("--no-numa-bind", action="store_true",
                     help="do not place this rank's pinned buffers (multi-GPU: and its CPU affinity) on its GPU's NUMA node")
-    ap.add_argument("--gru-mode", type=int, default=0, choices=[0, 2, 3, 5, 6],
-                    help="EXPERIMENTAL (unmeasured): core-GRU build selected with ctgcn_set_coop_mode (DESIGN.md §9); 0 = shipped kernels")
-    ap.add_argument("--coop", action="store_true",
-                    help="EXPERIMENTAL (unmeasured): SpMM(t+1) co-resident with GRU(t), single GPU only (DESIGN.md §9)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -280,14 +276,10 @@ def main():
         del snap
     torch.manual_seed(0)
     model = pkg.CTGCN(d, d, d, 1, 1, T, model_type="C", trans_activate_type="L").to(dev).eval()
+    model.snapshot_parallel = world > 1
     model.gather_output = False      # every rank keeps (and, in e2e, reads back) its node slice of the output
     model.exchange = args.exchange
     model.node_num = n
-    if args.coop:
-        _lib.set_coop_mode(True)
-        model.coop = True
-    elif args.gru_mode:
-        _lib.set_coop_mode(args.gru_mode)
     setup_s = time.perf_counter() - t_setup
 
     def tot(v):
@@ -432,7 +424,7 @@ def main():
                    "layers": f"MLP 1x({d}->{d},'L') + CDN 1 layer + temporal GRU", "edges_aggregated_per_step": e_agg,
                    "union_entries_total": entries_total, "cores_per_snapshot": [s["k"] for s in stats.values()],
                    "l2": "per-step inputs (features + graph plans + per-core sums) exceed the 126 MB L2 several times over; no flush",
-                   "gru_impl": args.gru_impl, "coop": bool(args.coop), "gru_mode": args.gru_mode, "host_numa": host_numa, "setup_s": round(setup_s, 1)},
+                   "gru_impl": args.gru_impl, "host_numa": host_numa, "setup_s": round(setup_s, 1)},
         "e2e": {"value": e_agg / (ms_e2e / args.steps * 1e-3), "unit": "edges-aggregated/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": launches_total,

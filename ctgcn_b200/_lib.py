@@ -57,13 +57,8 @@ SIGNATURES = {
     "ctgcn_rnn_seq_fwd": (C.c_int, [_i32, _p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _f32, _i32, _p, _i64,
                                     _i64, _p, _sz, _p]),
     "ctgcn_set_gru_impl": (C.c_int, [_i32]),
-    "ctgcn_set_coop_mode": (C.c_int, [_i32]),
     "ctgcn_debug_gru_trace": (C.c_int, [_p]),
     "ctgcn_selftest_umma": (C.c_int, [_p, _p, _p, _p, _p, _p, _sz, _p]),
-    "ctgcn_cumspmm_packed_bytes": (_sz, [_p]),
-    "ctgcn_cumspmm_fwd_packed": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),
-    "ctgcn_core_diffusion_packed_workspace_bytes": (_sz, [_p]),
-    "ctgcn_core_diffusion_fwd_packed": (C.c_int, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _f32, _p, _i64, _p, _sz, _p]),
     "ctgcn_selftest_umma_pair": (C.c_int, [_p, _p, _p, _p, _p, _p, _sz, _p]),
     "ctgcn_core_diffusion_workspace_bytes": (_sz, [_p, _i32, _i32]),
     "ctgcn_core_diffusion_fwd": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _f32, _p, _i64, _p, _sz, _p]),
@@ -120,12 +115,6 @@ def set_workspace_cap(nbytes: int) -> None:
     """Bound on the per-core-sums buffer of one CoreDiffusion call (0 = default 8 GiB); larger layers run in row chunks."""
     check(lib.ctgcn_set_workspace_cap(int(nbytes)), "ctgcn_set_workspace_cap")
 
-
-def set_coop_mode(mode) -> None:
-    """EXPERIMENTAL: 0 / False default kernels, 1 / True reduced-register variants for SpMM / GRU co-residency, 2 the SUM_LN GRU
-    kernel with 16 gate-math warps, 3 the same with the input-side biases folded into the MMAs, 5 = 3 with the gate math on packed fp32
-    pairs, 6 = 5 with the reordered MMA schedule / early accumulator release (see csrc/gru_tc.cu)."""
-    check(lib.ctgcn_set_coop_mode(int(mode)), "ctgcn_set_coop_mode")
 
 
 def set_gru_impl(impl: int) -> None:

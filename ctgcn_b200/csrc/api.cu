@@ -108,15 +108,6 @@ extern "C" int ctgcn_prof_collect(double* ms, int64_t* counts, int reset) {
 
 namespace ctgcn {
 void set_gru_trace(long long* buf);
-void set_coop_mode(int mode);
-int coop_mode();
-size_t gru_tc_coop_scratch_bytes();
-}
-// EXPERIMENTAL: co-resident kernel variants (gru_tc_coop_kernel + the 64-register SpMM), see gru_tc.cu.  Default off.
-extern "C" int ctgcn_set_coop_mode(int mode) {
-    CTGCN_REQUIRE((mode >= 0 && mode <= 3) || mode == 5 || mode == 6, "set_coop_mode: mode %d is not one of 0, 1, 2, 3, 5, 6", mode);
-    set_coop_mode(mode);
-    return CTGCN_OK;
 }
 extern "C" int ctgcn_debug_gru_trace(int64_t* device_buf) {
     set_gru_trace(reinterpret_cast<long long*>(device_buf));
@@ -168,8 +159,8 @@ static int cell_gates(int cell) { return cell == CTGCN_CELL_LSTM ? 4 : 3; }
 static size_t rnn_ws_simt(int cell, int d_in, int h) {
     return align_up((size_t)cell_gates(cell) * h * (d_in + h) * sizeof(float), 256);
 }
-static size_t gru_ws_tc(int d_in, int h) {   // packed bf16 hi|lo weights + biases (+ the Σh scratch of the co-resident variant)
-    return align_up((size_t)3 * h * (d_in + h) * 2 * sizeof(uint16_t), 256) + 4096 + (coop_mode() ? gru_tc_coop_scratch_bytes() : 0);
+static size_t gru_ws_tc(int d_in, int h) {   // packed bf16 hi|lo weights + biases
+    return align_up((size_t)3 * h * (d_in + h) * 2 * sizeof(uint16_t), 256) + 4096;
 }
 
 extern "C" size_t ctgcn_rnn_workspace_bytes(int cell, int d_in, int h) {
@@ -248,31 +239,6 @@ static int64_t cd_chunk_rows(const ctgcn_plan* plan, int d_in) {
     return rows;
 }
 
-// EXPERIMENTAL (ctgcn_set_coop_mode(1), unmeasured): inside ONE CoreDiffusion call the SpMM of row chunk c+1 runs on the
-// caller's stream while the sequence kernel of chunk c runs on an internal high-priority stream (co-resident kernel variants):
-// about four chunks of whole waves, two U buffers.  Only the first chunk's SpMM and the last chunk's GRU are not overlapped.
-static constexpr int kPipeChunks = 4;
-static int64_t cd_pipe_rows(const ctgcn_plan* plan, int d_in) {
-    const int64_t wave = 148 * 128;
-    if (coop_mode() != 1 || plan->n_rows < 2 * wave) return 0;
-    int64_t rows = (plan->n_rows + kPipeChunks - 1) / kPipeChunks;
-    rows = (rows + wave - 1) / wave * wave;
-    const int64_t cap_rows = cd_chunk_rows(plan, d_in);
-    if (rows > cap_rows) rows = cap_rows;            // cap_rows is a multiple of a wave whenever it is below n_rows
-    return rows < plan->n_rows ? rows : 0;
-}
-static cudaStream_t pipe_stream() {
-    static cudaStream_t streams[64] = {};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!streams[dev]) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (cudaStreamCreateWithPriority(&streams[dev], cudaStreamNonBlocking, hi) != cudaSuccess) streams[dev] = nullptr;
-    }
-    return streams[dev];
-}
-
 extern "C" int ctgcn_set_workspace_cap(size_t bytes) {
     g_chunk_cap.store(bytes ? bytes : kDefaultChunkCap);
     return CTGCN_OK;
@@ -282,8 +248,6 @@ extern "C" size_t ctgcn_core_diffusion_rnn_workspace_bytes(const ctgcn_plan* pla
     if (!plan || d_in <= 0 || h <= 0) return 0;
     const size_t r = ctgcn_rnn_workspace_bytes(cell, d_in, h);
     if (!r) return 0;
-    const int64_t pipe = cd_pipe_rows(plan, d_in);
-    if (pipe) return 2 * align_up((size_t)pipe * plan->k * d_in * sizeof(float), 256) + r;
     return align_up((size_t)cd_chunk_rows(plan, d_in) * plan->k * d_in * sizeof(float), 256) + r;
 }
 
@@ -305,51 +269,6 @@ static int core_diffusion_impl(const ctgcn_plan* plan, int cell, const float* x,
         return CTGCN_ENOMEM;
     }
     float* u = (float*)workspace;
-    const int64_t pipe = cd_pipe_rows(plan, d_in);
-    cudaStream_t hi = pipe ? pipe_stream() : nullptr;
-    if (pipe && hi) {
-        cudaStream_t st = (cudaStream_t)stream;
-        const size_t u_bytes = align_up((size_t)pipe * plan->k * d_in * sizeof(float), 256);
-        cudaEvent_t gru_done[2] = {nullptr, nullptr};
-        int rc = CTGCN_OK;
-        int c = 0;
-        for (int64_t row0 = 0; row0 < plan->n_rows && rc == CTGCN_OK; row0 += pipe, ++c) {
-            const int64_t rows = plan->n_rows - row0 < pipe ? plan->n_rows - row0 : pipe;
-            float* ub = (float*)((char*)workspace + (size_t)(c & 1) * u_bytes);
-            if (gru_done[c & 1]) {                                   // the GRU that read this buffer two chunks ago
-                cudaStreamWaitEvent(st, gru_done[c & 1], 0);
-                cudaEventDestroy(gru_done[c & 1]);
-                gru_done[c & 1] = nullptr;
-            }
-            rc = launch_cumspmm(plan, x, ldx, d_in, ub, true, st, row0, rows);
-            if (rc) break;
-            cudaEvent_t spmm_done;
-            if (cudaEventCreateWithFlags(&spmm_done, cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&gru_done[c & 1], cudaEventDisableTiming) != cudaSuccess) {
-                set_error("core_diffusion_fwd: cudaEventCreate failed");
-                rc = CTGCN_ECUDA;
-                break;
-            }
-            cudaEventRecord(spmm_done, st);
-            cudaStreamWaitEvent(hi, spmm_done, 0);
-            cudaEventDestroy(spmm_done);
-            RowScatter sc_chunk;
-            if (sc) {
-                sc_chunk = *sc;
-                sc_chunk.row_off = row0;
-            }
-            rc = rnn_seq_impl(cell, ub, (int64_t)plan->k * d_in, d_in, rows, plan->k, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b,
-                              eps, CTGCN_GRU_SUM_LN, y ? y + row0 * ldy : nullptr, ldy, 0, sc ? &sc_chunk : nullptr,
-                              (char*)workspace + 2 * u_bytes, workspace_bytes - 2 * u_bytes, hi);
-            cudaEventRecord(gru_done[c & 1], hi);
-        }
-        for (int b = 0; b < 2; ++b)
-            if (gru_done[b]) {                                       // the caller's stream continues after the last GRUs
-                cudaStreamWaitEvent(st, gru_done[b], 0);
-                cudaEventDestroy(gru_done[b]);
-            }
-        return rc;
-    }
     const int64_t chunk = cd_chunk_rows(plan, d_in);
     const size_t u_bytes = align_up((size_t)chunk * plan->k * d_in * sizeof(float), 256);
     for (int64_t row0 = 0; row0 < plan->n_rows; row0 += chunk) {

@@ -125,8 +125,6 @@ struct Params {
     RowScatter sc;      // SUM_LN only: rows go to their node slice's buffer (fused snapshot exchange)
     int num_tiles;
     long long* trace;   // optional [24 events][64 steps] clock64 stamps of block 0 (ctgcn_debug_gru_trace), else NULL
-    float* sumh_scratch;   // gru_tc_coop_kernel only: [grid][TILE_M * H] fp32
-    const uint8_t* packed_u;   // gru_tc_packed_kernel only: U pre-split by the SpMM, [tile][step][64 KB operand image] (spmm_packed.cu)
 };
 
 // debug timeline: event e of global step gs of block 0
@@ -150,56 +148,6 @@ __device__ __forceinline__ float rcp_approx(float v) {
     return r;
 }
 #endif
-
-// Packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 — one issue slot for two IEEE operations, same rounding as the scalar forms).
-// Used by the PK2 build of the experimental gate math only: the gate warps are issue-bound (≈ 30 fp32 instructions per feature).
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-    float2 d;
-    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d.x), "=f"(d.y)
-        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return d;
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-    float2 d;
-    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d.x), "=f"(d.y)
-        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return d;
-}
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-    float2 d;
-    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d.x), "=f"(d.y)
-        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-    return d;
-}
-
-// packed forms of tc_common.cuh's split2 / join8 (same values: a − hi is one rounding either way)
-__device__ __forceinline__ void split2_pk(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-    hi = *reinterpret_cast<const uint32_t*>(&h2);
-    const float2 r = fma2(make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u)), make_float2(-1.f, -1.f),
-                          make_float2(a, b));
-    const __nv_bfloat162 l2 = __floats2bfloat162_rn(r.x, r.y);
-    lo = *reinterpret_cast<const uint32_t*>(&l2);
-}
-__device__ __forceinline__ void split8_pk(const float (&v)[8], uint4& hi, uint4& lo) {
-    split2_pk(v[0], v[1], hi.x, lo.x);
-    split2_pk(v[2], v[3], hi.y, lo.y);
-    split2_pk(v[4], v[5], hi.z, lo.z);
-    split2_pk(v[6], v[7], hi.w, lo.w);
-}
-__device__ __forceinline__ void join8_pk(const uint4& hi, const uint4& lo, float (&v)[8]) {
-    const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float2 r = add2(make_float2(bf_lo(h[q]), bf_hi(h[q])), make_float2(bf_lo(l[q]), bf_hi(l[q])));
-        v[2 * q] = r.x;
-        v[2 * q + 1] = r.y;
-    }
-}
 
 // One 24 KB weight chunk (192 rows × 32 k): 2 K-steps × 3 split products (hi·hi, lo·hi, hi·lo) of N = 192 into 192
 // consecutive accumulator columns starting at d_tmem.  a_lo32 / b_lo32: descriptor low words of the A hi plane at this
@@ -640,624 +588,6 @@ __global__ void __launch_bounds__(THREADS, 1) gru_tc_kernel(const Params p) {
     if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// EXPERIMENTAL (round-2 groundwork, selected by ctgcn_set_coop_mode(1), SUM_LN only; not measured yet).
-// Same pipeline as gru_tc_kernel with a smaller register footprint, so that one 256-thread block of the NEXT snapshot's
-// cumulative SpMM (HBM-bound, no shared memory) can be co-resident on every SM while this kernel runs (tensor/MUFU-bound):
-//   * Σ_s h_s is not held in 64 registers per gate thread but in an L2-resident scratch (64 KB per CTA, every element has
-//     exactly one owner thread: plain read-modify-write with .cg accesses, loaded at the start of an 8-feature pass and
-//     stored at its end) → gate warps 168 → 104 registers;
-//   * the kernel is launched with 96 registers per thread (49 152 of the SM's 65 536; setmaxnreg: warps 0-3 56, loaders 112,
-//     gate warps 104 = 48 128), which leaves 16 384 registers = 256 threads × 64 for the co-resident SpMM block.
-//
-// FOLD (mode 3): the input-side biases are added by the tensor core instead of the gate warps.  One extra K = 16 MMA per
-// input part, A = a resident block whose k = 0 and k = 1 columns are 1.0, B = a resident block holding bf16 hi (k = 0) and
-// lo (k = 1) of the half's [b_in | b_ir + b_hr | b_iz + b_hz] rows, opens the accumulation (it replaces the "fresh" MMA):
-// +2 of 96 MMAs per tile-step, and the gate warps drop 24 of the 80 FADDs and 6 of the 8 broadcast LDS.128 of an 8-feature
-// pass (only b_hn is still added there) — their shared-memory wavefronts compete with the operand fetch of the N = 192 MMA
-// streams (profiles/r01_gru_timeline.md).
-constexpr int SM_FOLD = (SMEM_BYTES + 4096 + 127) / 128 * 128;   // after the LayerNorm exchange area of the Σh-scratch variants
-constexpr int FOLD_ONES_BYTES = 2 * TILE_M * 16;                 // A block  [2 k-blocks][128 rows][8 bf16]
-constexpr int FOLD_BIAS_HALF = 2 * CHUNK_ROWS * 16;              // B block of one half [2 k-blocks][192 rows][8 bf16]
-constexpr int SMEM_BYTES_FOLD = SM_FOLD + FOLD_ONES_BYTES + 2 * FOLD_BIAS_HALF;
-static_assert(SMEM_BYTES_FOLD <= 227 * 1024, "shared memory budget (bias-fold variant)");
-
-//
-// PACKED (mode 4): U arrives pre-split in the operand layout (ctgcn_cumspmm_fwd_packed) and is fetched by bulk copies — one lane
-// of warp 2 instead of the four loader warps (which idle at 24 registers) — and the registers they give up let the 16 gate
-// warps keep Σh in registers again (104 each) instead of the L2 scratch.  Stepping stone to two tiles in flight
-// (profiles/r02_gru_design.md step 3), where a bulk-copy ring is the only way to feed U.
-// PK2 (mode 5): the gate math on packed fp32 pairs (helpers above) — bit-identical arithmetic, about half the issue slots.
-// REORD (mode 6): both input parts of step i+1 are issued BEFORE h_i is awaited — the gate warps release an accumulator set right
-// after the last TMEM load of its last pass (the values are in registers by then), not after the math — so that only the two
-// recurrent parts (2 × 2.3 K cycles) stand between "h ready" and the last accumulator set; weight chunks are consumed in packed
-// order (X half0, X half1, H half0, H half1).  Model with 16 gate warps: period ≈ 10.3 K cycles instead of 12.2 K (design note).
-template <int NW, bool FOLD = false, bool PACKED = false, bool PK2 = false, bool REORD = false>   // gate-math warps: 8 (co-resident build, 96 registers per thread) or 16 (faster gate math)
-__device__ __forceinline__ void gru_tc_sumh_body(const Params& p) {
-    static_assert(!PACKED || NW == 16, "the bulk-copy-fed variant is built for 16 gate warps");
-    // setmaxnreg budgets per warpgroup: warps 0-3 | loaders 4-7 | gate warps (0 = keep the launch value)
-    //   NW = 8  (launch 96): 56 | 112 | 104      NW = 16 (launch 80): 48 | 112 | 80      PACKED (launch 80): 40 | 24 | 104
-    constexpr int WG0_REGS = PACKED ? 40 : (NW == 8 ? 56 : 48);
-    constexpr int THREADS_V = 32 * (FIRST_WORKER_WARP + NW);
-    constexpr int CHW = NW / 4;     // warps sharing one TMEM lane quarter = feature groups of a half
-    constexpr int FPT = 64 / CHW;   // features per thread and half: 32 | 16
-    constexpr int SUBS = FPT / 8;   // 8-feature passes per half: 4 | 2
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t sbase = smem_u32(smem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar0 = sbase + SM_BAR;
-    auto bar = [&](int i) { return bar0 + 8u * i; };
-    const int cpx = chunks_per_part(p.d_in);   // weight chunks of one half of the input part
-    constexpr int cph = chunks_per_part(H);    // … of the recurrent part
-    const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar(BAR_W_FULL + s), 1);
-            mbar_init(bar(BAR_W_EMPTY + s), 1);
-        }
-        mbar_init(bar(BAR_U_READY), PACKED ? 1 : NUM_LOADER_WARPS);
-        mbar_init(bar(BAR_U_FREE), 1);
-        mbar_init(bar(BAR_H_READY), NW);
-        mbar_init(bar(BAR_ACC_FULL0), 1);
-        mbar_init(bar(BAR_ACC_FULL1), 1);
-        mbar_init(bar(BAR_ACC_FREE0), NW);
-        mbar_init(bar(BAR_ACC_FREE1), NW);
-        fence_barrier_init();
-    }
-    for (int i = threadIdx.x; i < 4 * H; i += THREADS_V) reinterpret_cast<float*>(smem + SM_BIAS)[i] = p.bias4[i];
-    for (int i = threadIdx.x; i < H; i += THREADS_V) {
-        reinterpret_cast<float*>(smem + SM_LN)[i] = p.ln_w[i];
-        reinterpret_cast<float*>(smem + SM_LN)[H + i] = p.ln_b[i];
-    }
-    if constexpr (FOLD) {
-        // 16-byte units: the ones block (k-block 0 of every row = [1, 1, 0 …]), then per half 192 bias rows [hi, lo, 0 …];
-        // every k-block 1 is zero
-        constexpr int ONES_UNITS = FOLD_ONES_BYTES / 16, BIAS_UNITS = 2 * FOLD_BIAS_HALF / 16;
-        for (int u = threadIdx.x; u < ONES_UNITS + BIAS_UNITS; u += THREADS_V) {
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (u < TILE_M) {
-                v.x = 0x3f803f80u;                                   // bf16 1.0 | 1.0
-            } else if (u >= ONES_UNITS) {
-                const int b = u - ONES_UNITS, half = b / (2 * CHUNK_ROWS), r = b % (2 * CHUNK_ROWS);
-                if (r < CHUNK_ROWS) {                                // k-block 0
-                    const int blk = r / 64, f = half * 64 + r % 64;  // rows [n | r | z] like an X weight chunk
-                    const float bv = p.bias4[(blk == 0 ? 2 : blk - 1) * H + f];
-                    const __nv_bfloat16 bh = __float2bfloat16_rn(bv);
-                    const __nv_bfloat16 bl = __float2bfloat16_rn(bv - __bfloat162float(bh));
-                    v.x = (uint32_t)__bfloat16_as_ushort(bh) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
-                }
-            }
-            *reinterpret_cast<uint4*>(smem + SM_FOLD + 16 * u) = v;
-        }
-        fence_proxy_async();     // read by the tensor core (async proxy)
-    }
-    if (warp == 1) tmem_alloc(sbase + SM_TMEM_PTR, TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM_PTR);
-
-    // 512 threads start with 96 registers each: every role branch starts with its warpgroup's setmaxnreg
-    // (warps 0-3: 56, loaders 4-7: 112, workers 8-15: 104)
-    if (warp == 0) {
-        // ===================================================== weight producer
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WG0_REGS));
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            const int nx = 2 * cpx;
-            for (int t = 0; t < my_tiles; ++t) {
-                for (int i = 0; i < p.steps; ++i) {
-                    // consumption order of the MMA issuer: X half0, [H half0], X half1, [H half1]
-                    // (packed order is X half0, X half1, H half0, H half1)
-                    for (int seg = 0; seg < 4; ++seg) {
-                        const bool rec = REORD ? seg >= 2 : (seg & 1);
-                        if (rec && i == 0) continue;
-                        const int half = REORD ? (seg & 1) : (seg >> 1);
-                        const int first = rec ? nx + half * cph : half * cpx;
-                        const int count = rec ? cph : cpx;
-                        for (int c = first; c < first + count; ++c) {
-                            mbar_wait(bar(BAR_W_EMPTY + stage), phase ^ 1);
-                            mbar_expect_tx(bar(BAR_W_FULL + stage), CHUNK_BYTES);
-                            bulk_g2s(sbase + SM_W + stage * CHUNK_BYTES, p.packed + (size_t)c * CHUNK_BYTES, CHUNK_BYTES,
-                                     bar(BAR_W_FULL + stage));
-                            if (++stage == STAGES) {
-                                stage = 0;
-                                phase ^= 1;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================================================== MMA issuer
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WG0_REGS));
-        // All 32 lanes run the (warp-uniform) control flow and the barrier waits; one elected lane issues.
-        {
-            uint32_t stage = 0, phase = 0, gs = 0;
-            const uint32_t u_desc = desc_lo(sbase + SM_U, TILE_M * 16), h_desc = desc_lo(sbase + SM_H, TILE_M * 16);
-            // one part = one half (64 hidden features) of the input (A = U) or recurrent (A = h) contribution
-            auto run_part = [&](uint32_t a_desc, int ktot, int half, bool recurrent) {
-                const uint32_t d = tmem + half * 256 + (recurrent ? COL_R : COL_IN);
-                if (FOLD && !recurrent) {   // biases open the accumulation of [W_in·x | r | z]
-                    if (elect_one())
-                        umma_bf16(d, desc64(desc_lo(sbase + SM_FOLD, TILE_M * 16)),
-                                  desc64(desc_lo(sbase + SM_FOLD + FOLD_ONES_BYTES + half * FOLD_BIAS_HALF, CHUNK_ROWS * 16)),
-                                  umma_idesc_bf16(TILE_M, 192), 0u);
-                    __syncwarp();
-                }
-                for (int kc = 0; kc < ktot / CHUNK_K; ++kc) {
-                    mbar_wait(bar(BAR_W_FULL + stage), phase);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        issue_chunk(a_desc + kc * (CHUNK_K / 8) * ((TILE_M * 16) >> 4),
-                                    desc_lo(sbase + SM_W + stage * CHUNK_BYTES, CHUNK_ROWS * 16), d, !FOLD && !recurrent && kc == 0,
-                                    recurrent && kc == 0);
-                        umma_commit(bar(BAR_W_EMPTY + stage));
-                    }
-                    __syncwarp();
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-            };
-            auto commit = [&](int b) {
-                if (elect_one()) umma_commit(bar(b));
-                __syncwarp();
-            };
-            for (int t = 0; t < my_tiles; ++t) {
-                for (int i = 0; i < p.steps; ++i, ++gs) {
-                    const uint32_t par = gs & 1;
-                    if (lane == 0) GRU_TRACE(0, gs);
-                    mbar_wait(bar(BAR_U_READY), par);
-                    mbar_wait(bar(BAR_ACC_FREE0), par ^ 1);
-                    tc_fence_after();
-                    if (lane == 0) GRU_TRACE(1, gs);
-                    run_part(u_desc, p.d_in, 0, false);
-                    if (lane == 0) GRU_TRACE(2, gs);
-                    if constexpr (REORD) {
-                        mbar_wait(bar(BAR_ACC_FREE1), par ^ 1);
-                        tc_fence_after();
-                        if (lane == 0) GRU_TRACE(5, gs);
-                        run_part(u_desc, p.d_in, 1, false);
-                        commit(BAR_U_FREE);
-                        if (lane == 0) GRU_TRACE(6, gs);
-                        if (i > 0) {
-                            mbar_wait(bar(BAR_H_READY), par ^ 1);
-                            tc_fence_after();
-                            if (lane == 0) GRU_TRACE(3, gs);
-                            run_part(h_desc, H, 0, true);
-                        }
-                        commit(BAR_ACC_FULL0);
-                        if (lane == 0) GRU_TRACE(4, gs);
-                        if (i > 0) run_part(h_desc, H, 1, true);
-                        commit(BAR_ACC_FULL1);
-                        if (lane == 0) GRU_TRACE(7, gs);
-                        continue;
-                    }
-                    if (i == 0) {
-                        commit(BAR_ACC_FULL0);
-                    } else {
-                        // the recurrence h_{i-1} → gates → h_i is the critical chain: the first half's recurrent part
-                        // goes ahead of the second half's input part (same chunk order in the producer)
-                        mbar_wait(bar(BAR_H_READY), par ^ 1);
-                        tc_fence_after();
-                        if (lane == 0) GRU_TRACE(3, gs);
-                        run_part(h_desc, H, 0, true);
-                        commit(BAR_ACC_FULL0);
-                        if (lane == 0) GRU_TRACE(4, gs);
-                    }
-                    mbar_wait(bar(BAR_ACC_FREE1), par ^ 1);
-                    tc_fence_after();
-                    if (lane == 0) GRU_TRACE(5, gs);
-                    run_part(u_desc, p.d_in, 1, false);
-                    commit(BAR_U_FREE);
-                    if (lane == 0) GRU_TRACE(6, gs);
-                    if (i > 0) run_part(h_desc, H, 1, true);
-                    commit(BAR_ACC_FULL1);
-                    if (lane == 0) GRU_TRACE(7, gs);
-                }
-            }
-        }
-    } else if (warp < FIRST_WORKER_WARP) {
-        // ===================================================== input loaders (warps 4-7; warps 2-3 idle)
-        if (warp < FIRST_LOADER_WARP) {
-            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WG0_REGS));
-            if constexpr (PACKED) {
-                // ===================================================== U producer (warp 2, one lane): the SpMM stored this tile-step's
-                // operand image contiguously — four 16 KB bulk copies straight into the U buffer, no conversion, no registers
-                if (warp == 2 && lane == 0) {
-                    uint32_t gs = 0;
-                    for (int t = 0; t < my_tiles; ++t) {
-                        const size_t tile = (size_t)blockIdx.x + (size_t)t * gridDim.x;
-                        for (int i = 0; i < p.steps; ++i, ++gs) {
-                            mbar_wait(bar(BAR_U_FREE), (gs & 1) ^ 1);       // the previous step's input MMAs released the buffer
-                            mbar_expect_tx(bar(BAR_U_READY), 2 * A_PLANE);
-                            const uint8_t* src = p.packed_u + (tile * p.steps + i) * (size_t)(2 * A_PLANE);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                bulk_g2s(sbase + SM_U + q * (A_PLANE / 2), src + q * (A_PLANE / 2), A_PLANE / 2, bar(BAR_U_READY));
-                        }
-                    }
-                }
-            }
-        } else if constexpr (PACKED) {
-            asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");          // warps 4-7 have nothing to do in this variant
-        } else {
-            asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-            // A warp owns 32 tile rows.  Per load instruction its lanes cover 8 rows × 4 k-blocks (r = lane%8, c = lane/8):
-            // 128 contiguous bytes per row (8 L1 wavefronts instead of 32 for a row-per-lane mapping) and the 16-byte
-            // shared-memory stores of one 8-lane phase hit 8 consecutive rows of one k-block (conflict-free).
-            const int r8 = lane & 7, c4 = lane >> 3;
-            const int row_base = 32 * (warp - FIRST_LOADER_WARP);
-            uint8_t* u_hi = smem + SM_U;
-            const int nkg = p.d_in / 32;             // k-groups of 4 k-blocks
-            const int nit = 4 * nkg;                 // (row-group, k-group) iterations per step: 16 for d_in = 128
-            uint32_t gs = 0;
-            for (int t = 0; t < my_tiles; ++t) {
-                const int64_t tile_row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M;
-                for (int i = 0; i < p.steps; ++i, ++gs) {
-                    const float* base = p.seq + (int64_t)i * p.sss;
-                    float4 v[16];
-                    auto load_batch = [&](int it0) {   // 8 iterations = 16 LDG.128 in flight per lane
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int it = it0 + u, rg = it & 3, kg = it >> 2;
-                            const int64_t srow = tile_row0 + row_base + 8 * rg + r8;
-                            if (srow < p.n) {
-                                const float* src = base + srow * p.srs + (4 * kg + c4) * 8;
-                                v[2 * u] = __ldg(reinterpret_cast<const float4*>(src));
-                                v[2 * u + 1] = __ldg(reinterpret_cast<const float4*>(src + 4));
-                            } else {
-                                v[2 * u] = v[2 * u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            }
-                        }
-                    };
-                    auto store_batch = [&](int it0) {  // fp32 → bf16 hi/lo planes, 8 k-elements (16 B) per store
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int it = it0 + u, rg = it & 3, kg = it >> 2;
-                            const int m = row_base + 8 * rg + r8, kb = 4 * kg + c4;
-                            const float f8[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w,
-                                                 v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
-                            uint4 hi, lo;
-                            split8(f8, hi, lo);
-#ifdef GRU_EXP_NO_U_STORE
-                            if (f8[0] != 12345.678f) continue;   // timing experiment
-#endif
-                            *reinterpret_cast<uint4*>(u_hi + kb * (TILE_M * 16) + m * 16) = hi;
-                            *reinterpret_cast<uint4*>(u_hi + A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
-                        }
-                    };
-                    load_batch(0);   // global loads are issued BEFORE the buffer is free: their latency is off the loop
-                    // the input part of the previous step's MMAs must have released the single U buffer
-                    mbar_wait(bar(BAR_U_FREE), (gs & 1) ^ 1);
-                    if (threadIdx.x == FIRST_LOADER_WARP * 32) GRU_TRACE(13, gs);
-                    store_batch(0);
-                    for (int it0 = 8; it0 < nit; it0 += 8) {
-                        load_batch(it0);
-                        store_batch(it0);
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(BAR_U_READY));
-                    if (threadIdx.x == FIRST_LOADER_WARP * 32) GRU_TRACE(14, gs);
-                }
-            }
-        }
-    } else {
-        // ===================================================== workers (warps 8-15): gate math, h, Σh, LayerNorm
-        // register pools: NW = 8: 512 × 96 = 49 152 ≥ 128·56 + 128·112 + 256·104 = 48 128;
-        //                 NW = 16: 768 × 80 = 61 440 = 128·48 + 128·112 + 512·80
-        if constexpr (NW == 8 || PACKED) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-        // Σh scratch of this CTA: [16 feature blocks of 8][128 rows][8 floats] → a warp's 32 rows are 1 KB contiguous
-        float* const sumh = p.sumh_scratch + (size_t)blockIdx.x * (TILE_M * H);
-        const int ww = warp - FIRST_WORKER_WARP;
-        const int q = warp & 3;          // TMEM lane quarter this warp may access
-        const int ch = ww >> 2;          // which FPT of a half's 64 features this thread owns
-        const int m = 32 * q + lane;     // row inside the tile
-        const uint32_t tmem_lane = tmem + ((uint32_t)(32 * q) << 16);
-        const float* bias = reinterpret_cast<const float*>(smem + SM_BIAS);
-        const float* lnw = reinterpret_cast<const float*>(smem + SM_LN);
-        float* red = reinterpret_cast<float*>(smem + SMEM_BYTES);   // [2][CHW][128] fp32, appended to the common map
-        uint8_t* h_hi = smem + SM_H;
-        uint32_t gs = 0;
-
-        // SUM_LN result of a tile: normalised rows are staged in the (now idle) h buffer with a 16-byte XOR swizzle and
-        // written out one whole 512-byte row per warp instruction — to y, or straight into the owning node slice's
-        // (peer) buffer: NVLink wants full-line stores, not 32 scattered 16-byte pieces per instruction.
-        auto layer_norm_store_rows = [&](const float (&v)[2 * FPT], int64_t tile_row0) {
-            float s = 0.f;
-#pragma unroll
-            for (int j = 0; j < 2 * FPT; ++j) s += v[j];
-            red[ch * TILE_M + m] = s;
-            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
-            float tot = 0.f;
-#pragma unroll
-            for (int c = 0; c < CHW; ++c) tot += red[c * TILE_M + m];     // same order in every thread of the row
-            const float mean = tot * (1.f / H);
-            float sq = 0.f;
-#pragma unroll
-            for (int j = 0; j < 2 * FPT; ++j) {
-                const float dlt = v[j] - mean;
-                sq = fmaf(dlt, dlt, sq);
-            }
-            red[(CHW + ch) * TILE_M + m] = sq;
-            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
-            float totq = 0.f;
-#pragma unroll
-            for (int c = 0; c < CHW; ++c) totq += red[(CHW + c) * TILE_M + m];
-            const float rstd = rsqrtf(totq * (1.f / H) + p.eps);
-            float* stage = reinterpret_cast<float*>(smem + SM_H);     // [128 rows][32 chunks of 4 floats], chunk c of row r at c ^ (r & 31)
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll
-                for (int j4 = 0; j4 < FPT; j4 += 4) {
-                    const int f = hf * 64 + ch * FPT + j4;
-                    float4 o;
-                    o.x = (v[hf * FPT + j4 + 0] - mean) * rstd * lnw[f + 0] + lnw[H + f + 0];
-                    o.y = (v[hf * FPT + j4 + 1] - mean) * rstd * lnw[f + 1] + lnw[H + f + 1];
-                    o.z = (v[hf * FPT + j4 + 2] - mean) * rstd * lnw[f + 2] + lnw[H + f + 2];
-                    o.w = (v[hf * FPT + j4 + 3] - mean) * rstd * lnw[f + 3] + lnw[H + f + 3];
-                    *reinterpret_cast<float4*>(stage + m * H + (((f >> 2) ^ (m & 31)) << 2)) = o;
-                }
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
-            for (int rr = 0; rr < TILE_M / NW; ++rr) {
-                const int r = ww * (TILE_M / NW) + rr;
-                const int64_t grow = tile_row0 + r;
-                if (grow >= p.n) break;   // warp-uniform
-                const float4 o = *reinterpret_cast<const float4*>(stage + r * H + ((lane ^ (r & 31)) << 2));
-                float* dst = p.sc.slices ? p.sc.row_ptr(grow) : p.y + grow * p.yrs;
-                *reinterpret_cast<float4*>(dst + 4 * lane) = o;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");   // the staging area is h again from the next tile's first step on
-        };
-
-        for (int t = 0; t < my_tiles; ++t) {
-            const int64_t row = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + m;
-            float sum_regs[PACKED ? 2 * FPT : 1];   // PACKED: Σ_s h_s of this thread's features stays in registers
-#pragma unroll
-            for (int j = 0; j < (PACKED ? 2 * FPT : 1); ++j) sum_regs[j] = 0.f;
-
-            for (int i = 0; i < p.steps; ++i, ++gs) {
-                const uint32_t par = gs & 1;
-                // gates, one half (64 hidden features) at a time; this thread owns FPT of them, 8 per pass
-                float h0[FPT];  // first half of h_i, published only when no MMA reads h_{i-1} any more
-                auto put_h8 = [&](const float (&f8)[8], int f) {
-#ifdef GRU_EXP_NO_H_STORE
-                    if (f8[0] != 12345.678f) return;   // timing experiment: never true in practice
-#endif
-                    uint4 hi, lo;
-                    if constexpr (PK2) split8_pk(f8, hi, lo);
-                    else split8(f8, hi, lo);
-                    const int kb = f >> 3;
-                    *reinterpret_cast<uint4*>(h_hi + kb * (TILE_M * 16) + m * 16) = hi;
-                    *reinterpret_cast<uint4*>(h_hi + A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
-                };
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    if (threadIdx.x == FIRST_WORKER_WARP * 32) GRU_TRACE(8 + 2 * hf, gs);
-                    mbar_wait(bar(BAR_ACC_FULL0 + hf), par);
-                    tc_fence_after();
-                    if (threadIdx.x == FIRST_WORKER_WARP * 32) GRU_TRACE(9 + 2 * hf, gs);
-#pragma unroll
-                    for (int sub = 0; sub < SUBS; ++sub) {
-                        const int f0 = hf * 64 + ch * FPT + sub * 8;            // first of 8 features
-                        const uint32_t col = hf * 256 + ch * FPT + sub * 8;     // + gate block
-                        float gr[8], gz[8], gi[8], gh[8], hold[8];
-                        float* const sp = sumh + ((size_t)(f0 >> 3) * TILE_M + m) * 8;
-                        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-                        if (!PACKED && i > 0) {   // issued first: the L2 round trip hides under the TMEM loads and the gate math
-                            s0 = __ldcg(reinterpret_cast<const float4*>(sp));
-                            s1 = __ldcg(reinterpret_cast<const float4*>(sp) + 1);
-                        }
-                        tmem_ld8(tmem_lane + col + COL_R, gr);
-                        tmem_ld8(tmem_lane + col + COL_Z, gz);
-                        tmem_ld8(tmem_lane + col + COL_IN, gi);
-                        if (i > 0) {
-                            tmem_ld8(tmem_lane + col + COL_HN, gh);
-                            const int kb = f0 >> 3;
-                            const uint4 hi = *reinterpret_cast<const uint4*>(h_hi + kb * (TILE_M * 16) + m * 16);
-                            const uint4 lo = *reinterpret_cast<const uint4*>(h_hi + A_PLANE + kb * (TILE_M * 16) + m * 16);
-                            if constexpr (PK2) join8_pk(hi, lo, hold);
-                            else join8(hi, lo, hold);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) gh[j] = hold[j] = 0.f;
-                        }
-                        tmem_ld_wait();
-                        if constexpr (REORD) {
-                            if (sub == SUBS - 1) {   // every accumulator value of this half is in registers: hand the set back now
-                                tc_fence_before();
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive(bar(BAR_ACC_FREE0 + hf));
-                            }
-                        }
-                        // Gate math written stage by stage over the 8 features so that the 8 dependent chains
-                        // (ex2 → rcp → ex2 → rcp) are interleaved.  Pre-activations are pre-scaled (pack_weights_kernel):
-                        // sigmoid(a) = 1/(1 + 2^a'), tanh(s) = 1 − 2/(1 + 2^s'); one reciprocal serves r and z.
-                        float hn8[8], ea[8], eb[8], zz[8];
-                        if constexpr (PK2) {
-                            // the same operations in the same order on pairs (j, j+1): FADD2 / FMUL2 / FFMA2, MUFU and min stay scalar
-                            const float2 one = make_float2(1.f, 1.f), mtwo = make_float2(-2.f, -2.f), mone = make_float2(-1.f, -1.f);
-                            float2 a2[4], b2[4], i2[4], h2[4], z2[4], o2[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                a2[q] = make_float2(gr[2 * q], gr[2 * q + 1]);
-                                b2[q] = make_float2(gz[2 * q], gz[2 * q + 1]);
-                                i2[q] = make_float2(gi[2 * q], gi[2 * q + 1]);
-                                h2[q] = make_float2(gh[2 * q], gh[2 * q + 1]);
-                                if constexpr (!FOLD) {
-                                    a2[q] = add2(a2[q], *reinterpret_cast<const float2*>(bias + f0 + 2 * q));
-                                    b2[q] = add2(b2[q], *reinterpret_cast<const float2*>(bias + H + f0 + 2 * q));
-                                    i2[q] = add2(i2[q], *reinterpret_cast<const float2*>(bias + 2 * H + f0 + 2 * q));
-                                }
-                                h2[q] = add2(h2[q], *reinterpret_cast<const float2*>(bias + 3 * H + f0 + 2 * q));
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                a2[q] = make_float2(ex2_approx(a2[q].x), ex2_approx(a2[q].y));
-                                b2[q] = make_float2(ex2_approx(b2[q].x), ex2_approx(b2[q].y));
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                a2[q] = add2(one, make_float2(fminf(a2[q].x, 1e18f), fminf(a2[q].y, 1e18f)));
-                                b2[q] = add2(one, make_float2(fminf(b2[q].x, 1e18f), fminf(b2[q].y, 1e18f)));
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float2 pr = mul2(a2[q], b2[q]);
-                                o2[q] = make_float2(rcp_approx(pr.x), rcp_approx(pr.y));
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                z2[q] = mul2(o2[q], a2[q]);                                   // z
-                                i2[q] = fma2(mul2(o2[q], b2[q]), h2[q], i2[q]);               // W_in x + b_in + r ⊙ (W_hn h + b_hn)
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) i2[q] = make_float2(ex2_approx(i2[q].x), ex2_approx(i2[q].y));
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float2 dn = add2(one, i2[q]);
-                                i2[q] = make_float2(rcp_approx(dn.x), rcp_approx(dn.y));
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float2 nn = fma2(mtwo, i2[q], one);                     // tanh
-                                const float2 dl = fma2(nn, mone, make_float2(hold[2 * q], hold[2 * q + 1]));   // h − n (one rounding, as hold − nn)
-                                const float2 hv = fma2(z2[q], dl, nn);                        // (1 − z) n + z h
-                                hn8[2 * q] = hv.x;
-                                hn8[2 * q + 1] = hv.y;
-                            }
-                        } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if constexpr (FOLD) {          // b_r, b_z, b_in are already in the accumulators
-                                ea[j] = gr[j];
-                                eb[j] = gz[j];
-                            } else {
-                                ea[j] = gr[j] + bias[f0 + j];
-                                eb[j] = gz[j] + bias[H + f0 + j];
-                                gi[j] += bias[2 * H + f0 + j];
-                            }
-                            gh[j] += bias[3 * H + f0 + j];
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            ea[j] = ex2_approx(ea[j]);
-                            eb[j] = ex2_approx(eb[j]);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            ea[j] = 1.f + fminf(ea[j], 1e18f);     // clamped so that the product below stays finite
-                            eb[j] = 1.f + fminf(eb[j], 1e18f);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) hn8[j] = rcp_approx(ea[j] * eb[j]);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            zz[j] = hn8[j] * ea[j];                                          // z
-                            gi[j] = fmaf(hn8[j] * eb[j], gh[j], gi[j]);                      // W_in x + b_in + r ⊙ (W_hn h + b_hn)
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) gi[j] = ex2_approx(gi[j]);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) gi[j] = rcp_approx(1.f + gi[j]);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float nn = fmaf(-2.f, gi[j], 1.f);                         // tanh
-                            hn8[j] = fmaf(zz[j], hold[j] - nn, nn);                          // (1 − z) n + z h
-                        }
-                        }   // !PK2
-                        if (hf == 0) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) h0[sub * 8 + j] = hn8[j];
-                        } else {
-                            // every MMA that reads h_{i-1} has completed (acc1 full): h may be overwritten in place.
-                            // The held-back first half is published piecewise here so that its ALU work hides
-                            // under the MUFU latency of this pass.
-                            const float f8[8] = {h0[sub * 8], h0[sub * 8 + 1], h0[sub * 8 + 2], h0[sub * 8 + 3],
-                                                 h0[sub * 8 + 4], h0[sub * 8 + 5], h0[sub * 8 + 6], h0[sub * 8 + 7]};
-                            put_h8(f8, ch * FPT + sub * 8);
-                            put_h8(hn8, f0);
-                        }
-                        if constexpr (PACKED) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) sum_regs[hf * FPT + sub * 8 + j] += hn8[j];
-                        } else if constexpr (PK2) {
-                            const float2 t0 = add2(make_float2(s0.x, s0.y), make_float2(hn8[0], hn8[1]));
-                            const float2 t1 = add2(make_float2(s0.z, s0.w), make_float2(hn8[2], hn8[3]));
-                            const float2 t2 = add2(make_float2(s1.x, s1.y), make_float2(hn8[4], hn8[5]));
-                            const float2 t3 = add2(make_float2(s1.z, s1.w), make_float2(hn8[6], hn8[7]));
-                            __stcg(reinterpret_cast<float4*>(sp), make_float4(t0.x, t0.y, t1.x, t1.y));
-                            __stcg(reinterpret_cast<float4*>(sp) + 1, make_float4(t2.x, t2.y, t3.x, t3.y));
-                        } else {
-                            s0.x += hn8[0];
-                            s0.y += hn8[1];
-                            s0.z += hn8[2];
-                            s0.w += hn8[3];
-                            s1.x += hn8[4];
-                            s1.y += hn8[5];
-                            s1.z += hn8[6];
-                            s1.w += hn8[7];
-                            __stcg(reinterpret_cast<float4*>(sp), s0);
-                            __stcg(reinterpret_cast<float4*>(sp) + 1, s1);
-                        }
-                        if (threadIdx.x == FIRST_WORKER_WARP * 32) GRU_TRACE(16 + hf * 4 + sub, gs);
-                    }
-                    if constexpr (!REORD) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar(BAR_ACC_FREE0 + hf));
-                    }
-                }
-                // h_i is complete in shared memory: the next step's recurrent MMAs may read it
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(BAR_H_READY));
-                if (threadIdx.x == FIRST_WORKER_WARP * 32) GRU_TRACE(12, gs);
-            }
-            {
-                float acc_out[2 * FPT];   // Σ_s h_s of this thread's features, read back once per tile (own writes: program order)
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf)
-#pragma unroll
-                    for (int sub = 0; sub < SUBS; ++sub) {
-                        if constexpr (PACKED) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) acc_out[hf * FPT + sub * 8 + j] = sum_regs[hf * FPT + sub * 8 + j];
-                            continue;
-                        }
-                        const float* sp = sumh + ((size_t)((hf * 64 + ch * FPT + sub * 8) >> 3) * TILE_M + m) * 8;
-                        const float4 a0 = __ldcg(reinterpret_cast<const float4*>(sp)), a1 = __ldcg(reinterpret_cast<const float4*>(sp) + 1);
-                        float* o = acc_out + hf * FPT + sub * 8;
-                        o[0] = a0.x, o[1] = a0.y, o[2] = a0.z, o[3] = a0.w, o[4] = a1.x, o[5] = a1.y, o[6] = a1.z, o[7] = a1.w;
-                    }
-                layer_norm_store_rows(acc_out, row - m);
-            }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
-}
-
-// co-resident build: 8 gate warps, 96 registers per thread at launch (leaves 16 384 registers per SM to a 64-register SpMM block)
-__global__ void __maxnreg__(96) gru_tc_coop_kernel(const Params p) { gru_tc_sumh_body<8>(p); }
-// fast-gate build: 16 gate warps (each thread 16 features of a half instead of 32), the whole register file: 768 × 80
-__global__ void __maxnreg__(80) gru_tc_w16_kernel(const Params p) { gru_tc_sumh_body<16>(p); }
-// the same with the input-side biases folded into the MMAs (mode 3)
-__global__ void __maxnreg__(80) gru_tc_w16f_kernel(const Params p) { gru_tc_sumh_body<16, true>(p); }
-// bulk-copy-fed U, Σh in registers, 16 gate warps (mode 4 building block; launched by launch_gru_tc_packed only)
-__global__ void __maxnreg__(80) gru_tc_packed_kernel(const Params p) { gru_tc_sumh_body<16, false, true>(p); }
-// mode 5: mode 3 with the gate math on packed fp32 pairs
-__global__ void __maxnreg__(80) gru_tc_w16fp_kernel(const Params p) { gru_tc_sumh_body<16, true, false, true>(p); }
-// mode 6: mode 5 with the reordered MMA schedule and the early accumulator release
-__global__ void __maxnreg__(80) gru_tc_w16r_kernel(const Params p) { gru_tc_sumh_body<16, true, false, true, true>(p); }
-
 // ------------------------------------------------------------------------------------------------ self test
 // One half-step of a GRU cell's pre-activations for d_in = 64 through exactly the packer, chunk images, bulk copies,
 // descriptors, split-bf16 MMAs (incl. the split-first recurrent MMA) and TMEM loads of the GRU kernel:
@@ -1341,15 +671,6 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
 
 static long long* g_gru_trace = nullptr;
 void set_gru_trace(long long* buf) { g_gru_trace = buf; }
-// 0 default kernels | 1 co-resident builds (gru_tc_coop_kernel, 64-register SpMM) | 2 gru_tc_w16_kernel | 3 gru_tc_w16f_kernel
-static std::atomic<int> g_coop{0};
-void set_coop_mode(int mode) { g_coop.store((mode >= 1 && mode <= 3) || mode == 5 || mode == 6 ? mode : 0); }   // 4: separate entry point
-int coop_mode() { return g_coop.load(); }
-constexpr int SMEM_BYTES_SUMH = SMEM_BYTES + 4096;   // + the LayerNorm exchange area [2][NW/4][128] fp32 of gru_tc_sumh_body
-static_assert(SMEM_BYTES_SUMH <= 227 * 1024, "shared memory budget");
-// Σh scratch of the co-resident variant: one [TILE_M, H] fp32 tile per CTA of the persistent grid (≤ 256 SMs)
-size_t gru_tc_coop_scratch_bytes() { return (size_t)256 * TILE_M * H * sizeof(float); }
-
 // returns 0 = done, <0 = error, 1 = shape not supported by this path
 int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* w_ih,
                   const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
@@ -1363,31 +684,18 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
     CTGCN_REQUIRE(ws && ws_bytes >= packed_bytes + 4 * H * sizeof(float), "gru_tc: workspace too small");
     uint8_t* packed = (uint8_t*)ws;
     float* bias4 = (float*)(packed + packed_bytes);
-    const size_t scratch_off = align_up(packed_bytes + 4 * H * sizeof(float), 256);
-    const int coop = (mode == CTGCN_GRU_SUM_LN && ws_bytes >= scratch_off + gru_tc_coop_scratch_bytes()) ? g_coop.load() : 0;
     {
         ProfScope prof(PROF_PACK, st);
         const int threads = nchunks * UNITS_PER_PLANE;
         pack_weights_kernel<<<(threads + 255) / 256, 256, 0, st>>>(w_ih, w_hh, b_ih, b_hh, d_in, packed, bias4, 1);
         CTGCN_LAUNCH_OK("pack_weights_kernel");
     }
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        CTGCN_CUDA_OK(cudaGetDevice(&dev));
-        CTGCN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_kernel<CTGCN_GRU_SUM_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_kernel<CTGCN_GRU_EACH_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    }
-    static bool coop_ready = false;      // set up lazily: nothing about the experimental variant can affect the default path
-    if (coop && !coop_ready) {
-        CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SUMH));
-        CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_w16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SUMH));
-        CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_w16f_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_FOLD));
-        CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_w16fp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_FOLD));
-        CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_w16r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_FOLD));
-        coop_ready = true;
-    }
+    // per device (the attribute belongs to the device's context; a process may drive several GPUs) and cheap: set on every call
+    int dev = 0, sm_count = 0;
+    CTGCN_CUDA_OK(cudaGetDevice(&dev));
+    CTGCN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_kernel<CTGCN_GRU_SUM_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_kernel<CTGCN_GRU_EACH_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     Params p;
     p.seq = seq;
     p.srs = srs;
@@ -1406,71 +714,13 @@ int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int ste
     p.sc = sc ? *sc : RowScatter();
     p.num_tiles = (int)((n + TILE_M - 1) / TILE_M);
     p.trace = g_gru_trace;
-    p.sumh_scratch = coop ? (float*)((char*)ws + scratch_off) : nullptr;
-    p.packed_u = nullptr;
     const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
-    CTGCN_REQUIRE(!coop || grid <= 256, "gru_tc: co-resident variant supports at most 256 SMs");
     ProfScope prof(PROF_GRU, st);
-    if (coop == 1)
-        gru_tc_coop_kernel<<<grid, THREADS, SMEM_BYTES_SUMH, st>>>(p);
-    else if (coop == 2)
-        gru_tc_w16_kernel<<<grid, 32 * (FIRST_WORKER_WARP + 16), SMEM_BYTES_SUMH, st>>>(p);
-    else if (coop == 3)
-        gru_tc_w16f_kernel<<<grid, 32 * (FIRST_WORKER_WARP + 16), SMEM_BYTES_FOLD, st>>>(p);
-    else if (coop == 5)
-        gru_tc_w16fp_kernel<<<grid, 32 * (FIRST_WORKER_WARP + 16), SMEM_BYTES_FOLD, st>>>(p);
-    else if (coop == 6)
-        gru_tc_w16r_kernel<<<grid, 32 * (FIRST_WORKER_WARP + 16), SMEM_BYTES_FOLD, st>>>(p);
-    else if (mode == CTGCN_GRU_SUM_LN)
+    if (mode == CTGCN_GRU_SUM_LN)
         gru_tc_kernel<CTGCN_GRU_SUM_LN><<<grid, THREADS, SMEM_BYTES, st>>>(p);
     else
         gru_tc_kernel<CTGCN_GRU_EACH_LN><<<grid, THREADS, SMEM_BYTES, st>>>(p);
     CTGCN_LAUNCH_OK("gru_tc_kernel");
-    return CTGCN_OK;
-}
-
-// EXPERIMENTAL (never run): the SUM_LN core GRU (128 → 128) fed by the pre-split U of ctgcn_cumspmm_fwd_packed.
-// ws: packed weights + biases as for launch_gru_tc (no Σh scratch).
-int launch_gru_tc_packed(const uint8_t* packed_u, int64_t n, int steps, const float* w_ih, const float* w_hh, const float* b_ih,
-                         const float* b_hh, const float* ln_w, const float* ln_b, float eps, float* y, int64_t yrs, void* ws,
-                         size_t ws_bytes, cudaStream_t st) {
-    constexpr int d_in = 128;
-    const int nchunks = 2 * chunks_per_part(d_in) + 2 * chunks_per_part(H);
-    const size_t packed_bytes = (size_t)nchunks * CHUNK_BYTES;
-    CTGCN_REQUIRE(ws && ws_bytes >= packed_bytes + 4 * H * sizeof(float), "gru_tc_packed: workspace too small");
-    CTGCN_REQUIRE((reinterpret_cast<uintptr_t>(packed_u) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (yrs & 3) == 0,
-                  "gru_tc_packed: unaligned buffers");
-    uint8_t* packed = (uint8_t*)ws;
-    float* bias4 = (float*)(packed + packed_bytes);
-    pack_weights_kernel<<<(nchunks * UNITS_PER_PLANE + 255) / 256, 256, 0, st>>>(w_ih, w_hh, b_ih, b_hh, d_in, packed, bias4, 1);
-    CTGCN_LAUNCH_OK("pack_weights_kernel");
-    int dev = 0, sms = 0;
-    CTGCN_CUDA_OK(cudaGetDevice(&dev));
-    CTGCN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_tc_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SUMH));
-    Params p;
-    p.seq = nullptr;
-    p.srs = p.sss = 0;
-    p.n = n;
-    p.steps = steps;
-    p.d_in = d_in;
-    p.packed = packed;
-    p.bias4 = bias4;
-    p.ln_w = ln_w;
-    p.ln_b = ln_b;
-    p.eps = eps;
-    p.y = y;
-    p.yrs = yrs;
-    p.yss = 0;
-    p.sc = RowScatter();
-    p.num_tiles = (int)((n + TILE_M - 1) / TILE_M);
-    p.trace = g_gru_trace;
-    p.sumh_scratch = nullptr;
-    p.packed_u = packed_u;
-    const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-    ProfScope prof(PROF_GRU, st);
-    gru_tc_packed_kernel<<<grid, 32 * (FIRST_WORKER_WARP + 16), SMEM_BYTES_SUMH, st>>>(p);
-    CTGCN_LAUNCH_OK("gru_tc_packed_kernel");
     return CTGCN_OK;
 }
 

@@ -13,7 +13,6 @@
 #include "common.cuh"
 
 namespace ctgcn {
-int coop_mode();   // gru_tc.cu
 namespace {
 
 constexpr int WARPS_PER_BLOCK = 8;
@@ -35,95 +34,12 @@ __device__ __forceinline__ void fma4(float4& a, float w, const float4& x) {
 }
 
 // D % 4 == 0.  NV = float4 slots per lane: lane owns float4 indices lane + 32*v (< D/4).
-template <int NV, int UNROLL, bool RELU>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+// MINB = minimum resident blocks per SM the register allocation is held to: the 128-d build (NV = 1, 8 rows in flight per lane)
+// compiled for 4 blocks (64 registers, 84 bytes of spills) measured 6 % FASTER than the unconstrained 80-register build at
+// cfg 4 (2.96 vs 3.16 ms, bit-identical; profiles/r02_experiments.md) — more warps in flight hide the gather latency.
+template <int NV, int UNROLL, bool RELU, int MINB>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB)
     cumspmm_vec_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                       const float* __restrict__ val, const uint8_t* __restrict__ lvl, const float* __restrict__ x,
-                       int64_t ldx, int d, int k, int64_t n_rows, float* __restrict__ u) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = blockIdx.x * (int64_t)WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    if (row >= n_rows) return;
-    const int d4 = d >> 2;
-    const int start = rowptr[row], end = rowptr[row + 1];
-
-    float4 P[NV], S[NV];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) P[v] = S[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    int cur = 0;
-    float* urow = u + row * (int64_t)k * d;
-
-    auto emit_until = [&](int lev) {
-        while (cur < lev) {
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                S[v].x += P[v].x;
-                S[v].y += P[v].y;
-                S[v].z += P[v].z;
-                S[v].w += P[v].w;
-                const int i4 = lane + 32 * v;
-                if (i4 < d4) {
-                    float4 o = S[v];
-                    if (RELU) {
-                        o.x = fmaxf(o.x, 0.f);
-                        o.y = fmaxf(o.y, 0.f);
-                        o.z = fmaxf(o.z, 0.f);
-                        o.w = fmaxf(o.w, 0.f);
-                    }
-                    st_f4_stream(urow + (int64_t)cur * d + 4 * i4, o);
-                }
-            }
-            ++cur;
-        }
-    };
-
-    for (int base = start; base < end; base += 32) {
-        const int cnt = min(32, end - base);
-        int c = 0;
-        float w = 0.f;
-        int l = 0;
-        if (lane < cnt) {
-            c = __ldg(col + base + lane);
-            w = __ldg(val + base + lane);
-            l = __ldg(lvl + base + lane);
-        }
-        for (int j = 0; j < cnt; j += UNROLL) {
-            float4 xv[UNROLL][NV];
-#pragma unroll
-            for (int q = 0; q < UNROLL; ++q) {
-                const int cj = __shfl_sync(0xffffffffu, c, (j + q) & 31);
-                const float* xr = x + (int64_t)cj * ldx;
-#pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    const int i4 = lane + 32 * v;
-                    xv[q][v] = (j + q < cnt && i4 < d4) ? ldg_f4(xr + 4 * i4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < UNROLL; ++q) {
-                const float wj = __shfl_sync(0xffffffffu, w, (j + q) & 31);
-                const int lj = __shfl_sync(0xffffffffu, l, (j + q) & 31);
-                if (j + q < cnt) {  // warp-uniform
-                    emit_until(lj & 127);
-                    if (lj & 128) {
-#pragma unroll
-                        for (int v = 0; v < NV; ++v) fma4(S[v], wj, xv[q][v]);
-                    } else {
-#pragma unroll
-                        for (int v = 0; v < NV; ++v) fma4(P[v], wj, xv[q][v]);
-                    }
-                }
-            }
-        }
-    }
-    emit_until(k);
-}
-
-// EXPERIMENTAL co-resident variant (ctgcn_set_coop_mode(1); see gru_tc_coop_kernel): the same kernel compiled for at most
-// 64 registers per thread, so that one 256-thread block fits into the 16 384 registers the co-resident GRU kernel leaves free
-// on every SM and the next snapshot's aggregation streams from HBM while the current snapshot's GRU occupies the tensor cores.
-template <int NV, int UNROLL, bool RELU>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4)
-    cumspmm_vec_coop_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                        const float* __restrict__ val, const uint8_t* __restrict__ lvl, const float* __restrict__ x,
                        int64_t ldx, int d, int k, int64_t n_rows, float* __restrict__ u) {
     const int lane = threadIdx.x & 31;
@@ -391,18 +307,13 @@ template <int NV, int UNROLL>
 int launch_vec(const ctgcn_plan* p, const float* x, int64_t ldx, int d, float* u, bool relu, cudaStream_t st, int64_t row0,
                int64_t rows) {
     const unsigned blocks = (unsigned)((rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    if (NV == 1 && relu && coop_mode() == 1) {   // experimental: 64-register build of the 128-d kernel (co-residency with the GRU)
-        cumspmm_vec_coop_kernel<1, 8, true><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p->rowptr + row0, p->col, p->val, p->lvl, x,
-                                                                                     ldx, d, p->k, rows, u);
-        CTGCN_LAUNCH_OK("cumspmm_vec_coop_kernel");
-        return CTGCN_OK;
-    }
+    constexpr int MINB = NV == 1 ? 4 : 1;
     if (relu)
-        cumspmm_vec_kernel<NV, UNROLL, true><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p->rowptr + row0, p->col, p->val, p->lvl, x,
-                                                                                      ldx, d, p->k, rows, u);
+        cumspmm_vec_kernel<NV, UNROLL, true, MINB><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p->rowptr + row0, p->col, p->val, p->lvl,
+                                                                                            x, ldx, d, p->k, rows, u);
     else
-        cumspmm_vec_kernel<NV, UNROLL, false><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p->rowptr + row0, p->col, p->val, p->lvl,
-                                                                                       x, ldx, d, p->k, rows, u);
+        cumspmm_vec_kernel<NV, UNROLL, false, MINB><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p->rowptr + row0, p->col, p->val, p->lvl,
+                                                                                             x, ldx, d, p->k, rows, u);
     CTGCN_LAUNCH_OK("cumspmm_vec_kernel");
     return CTGCN_OK;
 }

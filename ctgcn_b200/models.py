@@ -2,8 +2,9 @@
 top of the sm_100a kernels, with the reference's constructor / forward signatures, attribute names
 (``mlp_list``, ``duffision_list`` [sic], ``rnn``, ``norm``, ``method_name``) and ``state_dict`` keys.
 
-Snapshot-parallel mode: when ``torch.distributed`` is initialised with world size G > 1,
-``CTGCN.forward`` computes only the snapshots t ≡ rank (mod G) — their MLP_t / CDN_t weights, features and
+Snapshot-parallel mode is an explicit opt-in (``model.snapshot_parallel = True``; the reference has no such
+mode, so an initialised ``torch.distributed`` alone never changes behaviour — DDP-style use keeps the ordinary autograd path):
+with world size G > 1 ``CTGCN.forward`` then computes only the snapshots t ≡ rank (mod G) — their MLP_t / CDN_t weights, features and
 graph plans are disjoint (models.py:225-231) — exchanges the per-snapshot embeddings once, runs the
 temporal GRU on this rank's node slice, and (optionally) gathers the result.
 """
@@ -19,7 +20,6 @@ from . import dist as _dist
 
 
 _copy_streams = {}
-_coop_streams = {}
 
 
 class _HostFeatureStager:
@@ -153,7 +153,9 @@ class CTGCN(nn.Module):
         self.rnn = rnn_cls(output_dim, output_dim, num_layers=1, bias=bias, batch_first=True)
         self.norm = nn.LayerNorm(output_dim)
         self._cell = _lib.CELLS[rnn_type]
-        # snapshot-parallel options (only read when torch.distributed is initialised with world size > 1)
+        # snapshot-parallel execution is opt-in: every rank must then pass the same x_list / adj_list structure, the forward is
+        # inference-only, and for model_type 'S' trans_list holds None for snapshots owned by other ranks
+        self.snapshot_parallel = False
         self.gather_output = True
 
     def _temporal(self, hx, out=None):
@@ -166,64 +168,9 @@ class CTGCN(nn.Module):
         return ops.rnn_seq(hx, r.weight_ih_l0, r.weight_hh_l0, b_ih, b_hh, self.norm.weight, self.norm.bias, self.norm.eps,
                            _lib.GRU_EACH_LN, out=out, cell=self._cell)
 
-    def _forward_coop(self, x_list, adj_list):
-        """EXPERIMENTAL (self.coop = True; round-2 groundwork, not measured yet): the cumulative SpMM of snapshot t+1 (HBM-bound)
-        runs on the current stream while the core GRU of snapshot t (tensor-bound) runs on a high-priority stream, co-resident
-        on the same SMs (reduced-register kernel variants, ctgcn_set_coop_mode).  Needs one CoreDiffusion layer per snapshot.
-        Same arithmetic as forward(): results are bit-identical.  Timeline on the device:
-            cur:  SpMM(0) lin(1) | SpMM(1) ........ lin(2) | SpMM(2) ........ lin(3) | ...
-            hi :                 | GRU(0) ......          | GRU(1) ......          | ...                       """
-        from .plan import plan_for
-        T = len(x_list)
-        dev = self.norm.weight.device
-        cur = torch.cuda.current_stream(dev)
-        if str(dev) not in _coop_streams:
-            _coop_streams[str(dev)] = torch.cuda.Stream(device=dev, priority=-1)
-        hi = _coop_streams[str(dev)]
-        stager = _HostFeatureStager(x_list, range(T), dev)
-        layers = [cdn.diffusion_list[0] for cdn in self.duffision_list]
-        plans = [plan_for(adj_list[t], dev) for t in range(T)]
-        trans_list = [None] * T
-        trans_list[0] = self.mlp_list[0](stager.get(0))
-        n = trans_list[0].shape[0]
-        d_mid = trans_list[0].shape[1]
-        hx = torch.empty(n, T, self.output_dim, dtype=torch.float32, device=dev)
-        ubuf = [torch.empty(n * max(p.k for p in plans) * d_mid, dtype=torch.float32, device=dev) for _ in range(2)]
-        for b in ubuf:
-            b.record_stream(hi)
-        hx.record_stream(hi)
-        gru_done = [None, None]                     # event after the GRU that last read ubuf[b]
-        u = ops.cumspmm(plans[0], trans_list[0], out=ubuf[0])
-        for t in range(T):
-            if t + 1 < T:                           # the next snapshot's MLP goes BEFORE this snapshot's GRU: its CTAs need the
-                trans_list[t + 1] = self.mlp_list[t + 1](stager.get(t + 1))   # whole shared memory and cannot be co-resident
-            ready = torch.cuda.Event()
-            ready.record(cur)                       # U(t) and lin(t+1) are done
-            hi.wait_event(ready)
-            lay = layers[t]
-            w_ih, w_hh, b_ih, b_hh = lay._gru_params()
-            with torch.cuda.stream(hi):
-                ops.rnn_seq(u, w_ih, w_hh, b_ih, b_hh, lay.norm.weight, lay.norm.bias, lay.norm.eps, _lib.GRU_SUM_LN,
-                            out=hx[:, t, :], cell=lay._cell)
-                done = torch.cuda.Event()
-                done.record(hi)
-            gru_done[t & 1] = done
-            if t + 1 < T:
-                b = (t + 1) & 1
-                if gru_done[b] is not None:
-                    cur.wait_event(gru_done[b])     # the GRU that read this buffer two snapshots ago has finished
-                u = ops.cumspmm(plans[t + 1], trans_list[t + 1], out=ubuf[b])          # overlaps GRU(t)
-        cur.wait_event(gru_done[(T - 1) & 1])
-        if T > 1:
-            cur.wait_event(gru_done[(T - 2) & 1])
-        out = self._temporal(hx).transpose(0, 1)
-        return out if self.model_type == 'C' else (out, trans_list)
-
     def forward(self, x_list, adj_list):
-        if _dist.world_size() > 1:
+        if self.snapshot_parallel and _dist.world_size() > 1:
             return _dist.ctgcn_forward_sharded(self, x_list, adj_list)
-        if getattr(self, "coop", False) and self.diffusion_num == 1 and not torch.is_grad_enabled():
-            return self._forward_coop(x_list, adj_list)
         T = len(x_list)
         dev = self.norm.weight.device
         hx, trans_list, emb_list = None, [], []

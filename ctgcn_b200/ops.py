@@ -63,38 +63,6 @@ def cumspmm(plan: GraphPlan, x: torch.Tensor, relu: bool = True, out: torch.Tens
     return u
 
 
-def cumspmm_packed(plan: GraphPlan, x: torch.Tensor) -> torch.Tensor:
-    """EXPERIMENTAL (unmeasured): cumspmm for 128-wide x with the output pre-split into the GRU's tensor-core operand layout —
-    uint8 [tiles, K, 2 planes, 16 k-blocks, 128 rows, 16 bytes] (csrc/spmm_packed.cu).  Rows beyond N in the last tile stay zero."""
-    x = _f32_rows(x, "x")
-    if x.shape[0] != plan.n_cols or x.shape[1] != 128:
-        raise _lib.CtgcnError("cumspmm_packed needs x of shape [plan.n_cols, 128]")
-    tiles = (plan.n_rows + 127) // 128
-    u = torch.zeros(tiles, plan.k, 2, 16, 128, 16, dtype=torch.uint8, device=x.device)
-    assert u.numel() == _lib.lib.ctgcn_cumspmm_packed_bytes(plan.handle)
-    with torch.cuda.device(x.device):
-        _lib.check(_lib.lib.ctgcn_cumspmm_fwd_packed(plan.handle, _ptr(x), x.stride(0), 128, _ptr(u), _stream()),
-                   "ctgcn_cumspmm_fwd_packed")
-    return u
-
-
-def core_diffusion_packed(plan: GraphPlan, x, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps: float) -> torch.Tensor:
-    """EXPERIMENTAL (unmeasured): core_diffusion for 128 → 128 GRU layers through the pre-split U and the bulk-copy-fed GRU
-    kernel (csrc/core_diffusion_packed.cu).  Same result as core_diffusion up to the summation order inside the LayerNorm."""
-    x = _f32_rows(x, "x")
-    if x.shape != (plan.n_cols, 128) or tuple(w_ih.shape) != (384, 128) or tuple(w_hh.shape) != (384, 128):
-        raise _lib.CtgcnError("core_diffusion_packed handles 128 -> 128 GRU layers only")
-    w_ih, w_hh, b_ih, b_hh, ln_w, ln_b = (_vec(t, "parameter") for t in (w_ih, w_hh, b_ih, b_hh, ln_w, ln_b))
-    ws_bytes = _lib.lib.ctgcn_core_diffusion_packed_workspace_bytes(plan.handle)
-    ws = _workspace(ws_bytes, x.device)
-    y = torch.empty(plan.n_rows, 128, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
-        _lib.check(_lib.lib.ctgcn_core_diffusion_fwd_packed(plan.handle, _ptr(x), x.stride(0), _ptr(w_ih), _ptr(w_hh), _ptr(b_ih),
-                                                            _ptr(b_hh), _ptr(ln_w), _ptr(ln_b), float(eps), _ptr(y), y.stride(0),
-                                                            _ptr(ws), ws_bytes, _stream()), "ctgcn_core_diffusion_fwd_packed")
-    return y
-
-
 def cumspmm_hubsplit(plan: GraphPlan, x: torch.Tensor, threshold: int = 4096) -> torch.Tensor:
     """EXPERIMENTAL (unmeasured): cumspmm with hub rows (> threshold entries) cut into segments that run as rows of their own
     (GraphPlan.hub_split).  Non-hub rows: the usual pass.  Hub rows: S_i of every segment without the relu, summed over the

@@ -8,6 +8,7 @@ their index tensors.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from collections import OrderedDict
 
 import numpy as np
@@ -64,7 +65,9 @@ class GraphPlan:
                 n_seg = parts["seg_row"].numel()
                 parts = dict(parts, main=build_plan_csr(self.n_rows, self.n_cols, self.k, *parts["main"], self.nnz_raw_sum, self.device),
                              hub=build_plan_csr(n_seg, self.n_cols, self.k, *parts["hub"], 0, self.device))
-            self._hub_cache = dict(getattr(self, "_hub_cache", {}), **{key: parts})
+            cache = dict(getattr(self, "_hub_cache", {}))
+            cache[key] = parts
+            self._hub_cache = cache
         return self._hub_cache[key]
 
     def arrays(self):
@@ -190,6 +193,31 @@ def build_plan_csr(n_rows, n_cols, k, rowptr, col, val, level, nnz_raw_sum, devi
 
 
 _cache: "OrderedDict[tuple, tuple]" = OrderedDict()
+_cache_limits = {"entries": _CACHE_SIZE, "bytes": 16 << 30}
+
+
+def set_cache_limits(entries: int = None, device_bytes: int = None):
+    """Bounds of the plan cache: number of cached adj_lists and total cudaMalloc'd plan bytes (least recently used plans go
+    first).  Plans live outside torch's caching allocator, so ``torch.cuda.empty_cache()`` never reclaims them."""
+    if entries is not None:
+        _cache_limits["entries"] = max(int(entries), 1)
+    if device_bytes is not None:
+        _cache_limits["bytes"] = max(int(device_bytes), 0)
+    _trim()
+
+
+def _plan_bytes(plan):
+    t = getattr(plan, "_t", None)
+    return plan.device_bytes + (t.device_bytes if t is not None else 0)
+
+
+def _trim(keep=None):
+    while len(_cache) > 1 and (len(_cache) > _cache_limits["entries"] or
+                               sum(_plan_bytes(v[1]) for v in _cache.values()) > _cache_limits["bytes"]):
+        key = next(iter(_cache))
+        if key == keep:
+            break
+        _cache.pop(key)
 
 
 def _signature(mats):
@@ -202,8 +230,16 @@ def _signature(mats):
     return tuple(sig)
 
 
+def _evict(key):
+    _cache.pop(key, None)
+
+
 def plan_for(adj_list, device) -> GraphPlan:
-    """Cached plan of one snapshot's adj_list (or of a single sparse feature matrix wrapped in a list)."""
+    """Cached plan of one snapshot's adj_list (or of a single sparse feature matrix wrapped in a list).
+
+    The cache never keeps the caller's matrices alive: it holds weak references only, and the entry (with its device plan) is
+    dropped as soon as one of the matrices is garbage-collected — the reference trainer frees a time window's graphs with
+    ``del adj_list, x_list`` (embedding.py:287, 365; window loop at train.py:269) and expects the memory back."""
     if isinstance(adj_list, GraphPlan):
         return adj_list
     key = (id(adj_list), str(device))
@@ -213,15 +249,19 @@ def plan_for(adj_list, device) -> GraphPlan:
         mats = list(adj_list)
     sig = _signature(mats)
     hit = _cache.get(key)
-    if hit is not None and hit[0] == sig:
+    if hit is not None and hit[0] == sig and all(r() is m for r, m in zip(hit[2], mats)):
         _cache.move_to_end(key)
         return hit[1]
     plan = build_plan_coo(mats, device)
-    _cache[key] = (sig, plan, adj_list)  # keep the list alive so that id() stays unique while cached
-    while len(_cache) > _CACHE_SIZE:
-        _cache.popitem(last=False)
+    refs = []
+    for m in mats:
+        refs.append(weakref.ref(m))
+        weakref.finalize(m, _evict, key)      # any matrix of the list dying invalidates the entry
+    _cache[key] = (sig, plan, refs)
+    _trim(keep=key)
     return plan
 
 
 def clear_cache():
+    """Destroy every cached plan now (window-based training: call between windows to return the device memory at once)."""
     _cache.clear()

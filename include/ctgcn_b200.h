@@ -129,16 +129,6 @@ int ctgcn_gru_seq_fwd(const float* seq, int64_t seq_row_stride, int64_t seq_step
                       const float* ln_w, const float* ln_b, float eps, int mode, float* y, int64_t y_row_stride,
                       int64_t y_step_stride, void* workspace, size_t workspace_bytes, void* stream);
 int ctgcn_set_gru_impl(int impl);
-/* EXPERIMENTAL (not measured yet, default 0).  mode 1: kernel variants with a reduced register footprint so that a
- * cumulative-SpMM block (HBM-bound) can be co-resident on every SM with the tcgen05 GRU kernel (tensor-bound) of another
- * snapshot / row chunk launched on a second stream.  mode 2: the tcgen05 SUM_LN GRU kernel with 16 instead of 8 gate-math
- * warps.  mode 3: mode 2 with the input-side biases added by one extra MMA per input part instead of by the gate warps (the
- * bias enters as bf16 hi+lo: results agree with the default kernels to ~1e-6, not bit for bit).  mode 5: mode 3 with the gate math
- * on packed fp32 pairs (FADD2 / FMUL2 / FFMA2: same arithmetic as mode 3, fewer issue slots).  mode 6: mode 5 with both input
- * parts of the next step issued before h is awaited (accumulator sets released right after their last TMEM load).  All keep the running sum of h in an
- * L2-resident scratch instead of registers; modes 1 and 2 give the same results as the default kernels.  (4 is not a mode: the
- * bulk-copy-fed variant has an entry point of its own, ctgcn_core_diffusion_fwd_packed.) */
-int ctgcn_set_coop_mode(int mode);
 /* debug: when non-NULL, block 0 of every following tcgen05 GRU launch writes clock64() stamps of its pipeline events
  * into device_buf[24 events][64 steps] (int64); NULL switches it off. */
 int ctgcn_debug_gru_trace(int64_t* device_buf);
@@ -207,21 +197,8 @@ int ctgcn_linear_fwd(const float* x, int64_t ldx, int64_t n, int64_t d_in, const
 int ctgcn_spmm_linear_fwd(const ctgcn_plan* x_plan, const float* w, const float* b, int64_t d_out, int act,
                           float* y, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
 
-/* EXPERIMENTAL (never run yet; csrc/spmm_packed.cu, profiles/r02_gru_design.md step 3): ctgcn_cumspmm_fwd for d = 128 whose output
- * is pre-split into the tensor-core operand layout instead of fp32 rows: per 128-row tile and level one 64 KB image
- * [plane hi|lo][k-block 16][row 128][8 bf16], hi = bf16_rn(u), lo = bf16_rn(u - hi); u: ctgcn_cumspmm_packed_bytes(plan) bytes. */
-size_t ctgcn_cumspmm_packed_bytes(const ctgcn_plan* plan);
-int ctgcn_cumspmm_fwd_packed(const ctgcn_plan* plan, const float* x, int64_t ldx, int d, void* u, void* stream);
-
-/* EXPERIMENTAL (never run yet): CoreDiffusion.forward for 128 -> 128 GRU layers through the pre-split U (the SpMM above, then a GRU
- * kernel that fetches its U tiles with bulk copies; csrc/core_diffusion_packed.cu).  Arguments as ctgcn_core_diffusion_fwd. */
-size_t ctgcn_core_diffusion_packed_workspace_bytes(const ctgcn_plan* plan);
-int ctgcn_core_diffusion_fwd_packed(const ctgcn_plan* plan, const float* x, int64_t ldx, const float* w_ih, const float* w_hh,
-                                    const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps, float* y,
-                                    int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
-
-/* EXPERIMENTAL test hook (never run yet): one GRU half-step through tcgen05.mma.cta_group::2 on a CTA pair (csrc/umma2_selftest.cu,
- * profiles/r02_gru_design.md step 2).  out[256,256] = [x W_in^T | x W_ir^T + h W_hr^T | x W_iz^T + h W_hz^T | h W_hn^T] for hidden
+/* test hook: one GRU half-step through tcgen05.mma.cta_group::2 on a CTA pair (csrc/umma2_selftest.cu) — the mechanisms of
+ * csrc/gru_tc2.cu in isolation (cluster launch, 2-CTA TMEM allocation, half weight chunks + remote-arrive relay, multicast commit).  out[256,256] = [x W_in^T | x W_ir^T + h W_hr^T | x W_iz^T + h W_hz^T | h W_hn^T] for hidden
  * features 0..63 from x[256,64], h[256,128], w_ih[384,64], w_hh[384,128]; workspace >= 512 KB of device memory. */
 int ctgcn_selftest_umma_pair(const float* x, const float* h, const float* w_ih, const float* w_hh, float* out, void* workspace,
                              size_t workspace_bytes, void* stream);

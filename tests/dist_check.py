@@ -43,6 +43,7 @@ def main():
         model = pkg.CTGCN(d, d, d, 1, 1, T, model_type="S").to(dev)
         model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
         model.exchange = exchange
+        model.snapshot_parallel = True
         xs = [synth.features(n, d, 1000 + t).to(dev) for t in range(T)]
         plans = [s.plan(dev) for s in snaps]
         with torch.no_grad():
@@ -57,14 +58,9 @@ def main():
         owned = dist.owned_snapshots(T, world, rank)
         ok &= all((trans[t] is not None) == (t in owned) for t in range(T))
         if rank == 0:
-            import ctgcn_b200.dist as D
-            real = D.world_size
-            D.world_size = lambda: 1                          # single-process reference path
-            try:
-                with torch.no_grad():
-                    ref, ref_trans = model(xs, plans)
-            finally:
-                D.world_size = real
+            model.snapshot_parallel = False                   # single-process reference path
+            with torch.no_grad():
+                ref, ref_trans = model(xs, plans)
             maxdiff = (ref - out).abs().max().item()
             print(f"[{exchange}] sharded vs single-GPU: equal={torch.equal(ref, out)} max|diff|={maxdiff:.3e}", flush=True)
             ok &= maxdiff <= 1e-6

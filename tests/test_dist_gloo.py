@@ -53,7 +53,7 @@ def test_exchange_world2(mode, T, n):
         assert ok2, f"rank {rank}: gathered output differs"
 
 
-def _model_worker(rank, world, port, name, mode, q):
+def _model_worker(rank, world, port, name, mode, q, opt_in=True):
     """The whole snapshot-parallel CTGCN.forward (ownership t mod G, exchange, node-sliced temporal GRU, output gather) on
     CPU/gloo, with the CUDA entry points replaced by the oracle-backed stand-in (tests/fake_backend.py)."""
     sys.path.insert(0, ROOT)
@@ -75,8 +75,9 @@ def _model_worker(rank, world, port, name, mode, q):
         model = grad_checks.build_model(pkg, m, "cpu")
         model.load_state_dict(grad_checks.tsd(c["sd"]), strict=True)
         model.exchange = mode
+        model.snapshot_parallel = opt_in
         xs, adj = grad_checks.model_inputs(c, "cpu")
-        owned = set(range(rank, m["T"], world))
+        owned = set(range(rank, m["T"], world)) if opt_in else set(range(m["T"]))
         xs = [x if t in owned else None for t, x in enumerate(xs)]          # other ranks' snapshots are never touched
         adj = [a if t in owned else None for t, a in enumerate(adj)]
         model.node_num = m["n"]
@@ -89,6 +90,8 @@ def _model_worker(rank, world, port, name, mode, q):
             out.sum().backward()
         except NotImplementedError:
             raised = True                                                    # sharded forward is inference-only, loudly
+        if not opt_in:                                                       # ordinary path: gradients must exist
+            raised = (not raised) and all(p.grad is not None for nm, p in model.named_parameters() if ".linear." not in nm or "mlp" in nm)
         q.put((rank, err, tuple(out.shape), ok_trans, raised))
     except Exception as exc:
         import traceback
@@ -115,3 +118,24 @@ def test_sharded_forward_world2(name, mode, lib):
         assert shape == (m["T"], m["n"], m["d_out"]), shape
         assert err < 5e-6, (rank, err)
         assert ok_trans and raised
+
+
+def test_initialised_process_group_alone_does_not_shard(lib):
+    """sharding is an explicit opt-in.  With torch.distributed initialised (world 2) but snapshot_parallel unset, every
+    rank runs the ordinary full forward with autograd (what a DDP-style caller of the drop-in modules expects)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29930 + os.getpid() % 20
+    procs = [ctx.Process(target=_model_worker, args=(r, 2, port, "ctgcn_C_T3", "all_to_all", q, False)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    from oracle import cases
+    m = cases.load_meta("ctgcn_C_T3")
+    for rank, err, shape, ok_trans, grads_ok in res:
+        assert shape is not None, f"rank {rank}: {err}"
+        assert shape == (m["T"], m["n"], m["d_out"]), shape
+        assert err < 5e-6, (rank, err)
+        assert grads_ok

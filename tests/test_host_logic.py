@@ -205,3 +205,54 @@ def test_hostmem_best_effort(lib, tmp_path, monkeypatch):
         assert rec["cpus"] is None and "outside" in rec["note"]
     finally:
         os.sched_setaffinity(0, before)
+
+
+def test_plan_cache_holds_no_strong_references(lib, monkeypatch):
+    """the plan cache must not keep a window's graphs (or their cudaMalloc'd plans) alive after the trainer's
+    `del adj_list` (embedding.py:287, 365), and it is bounded by device bytes.  No GPU: the builder is replaced by a stub."""
+    import gc
+    from ctgcn_b200 import plan as P
+
+    destroyed = []
+
+    class Stub:
+        def __init__(self, tag, nbytes):
+            self.tag, self.device_bytes = tag, nbytes
+
+        def __del__(self):
+            destroyed.append(self.tag)
+
+    built = []
+
+    def fake_build(mats, device):
+        built.append(len(mats))
+        return Stub(len(built), 100)
+
+    monkeypatch.setattr(P, "build_plan_coo", fake_build)
+    P.clear_cache()
+
+    def coo(seed):
+        i = torch.tensor([[0, 1, 2], [1, 2, seed % 3]])
+        return torch.sparse_coo_tensor(i, torch.ones(3), (3, 3))
+
+    adj = [coo(0), coo(1)]
+    p1 = P.plan_for(adj, "cuda:0")
+    assert P.plan_for(adj, "cuda:0") is p1 and len(built) == 1          # same list, same tensors: cached
+    tag = p1.tag
+    del p1, adj
+    gc.collect()
+    assert len(P._cache) == 0 and tag in destroyed                       # freed with the graphs, without clear_cache()
+
+    # byte bound: three 100-byte plans under a 250-byte cap → the least recently used one goes
+    keep = [[coo(s)] for s in range(3)]
+    P.set_cache_limits(device_bytes=250)
+    try:
+        plans = [P.plan_for(a, "cuda:0") for a in keep]
+        assert len(P._cache) == 2
+        assert P.plan_for(keep[2], "cuda:0") is plans[2]
+        n_built = len(built)
+        P.plan_for(keep[0], "cuda:0")                                    # evicted: rebuilt
+        assert len(built) == n_built + 1
+    finally:
+        P.set_cache_limits(device_bytes=16 << 30)
+        P.clear_cache()
