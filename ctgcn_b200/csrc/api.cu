@@ -50,6 +50,11 @@ void set_error(const char* fmt, ...) {
 int launch_gru_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* w_ih,
                   const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
                   int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* sc, void* ws, size_t ws_bytes, cudaStream_t st);
+// CTA-pair tcgen05 path (gru_tc2.cu), cg = 2, or the same kernel without pairing, cg = 1; returns 1 when the shape is not supported
+int launch_gru_tc2(int cg, const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* w_ih,
+                   const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
+                   int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* sc, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t gru_tc2_workspace_bytes(int d_in);
 // tcgen05 dense layer (linear_tc.cu); returns 1 when the shape is not supported by it
 int launch_linear_tc(const float* x, int64_t ldx, int64_t n, int64_t d_in, const float* w, const float* b, int64_t d_out,
                      int act, float* y, int64_t ldy, void* ws, cudaStream_t st);
@@ -108,14 +113,16 @@ extern "C" int ctgcn_prof_collect(double* ms, int64_t* counts, int reset) {
 
 namespace ctgcn {
 void set_gru_trace(long long* buf);
+void set_gru2_trace(long long* buf);
 }
 extern "C" int ctgcn_debug_gru_trace(int64_t* device_buf) {
     set_gru_trace(reinterpret_cast<long long*>(device_buf));
+    set_gru2_trace(reinterpret_cast<long long*>(device_buf));
     return CTGCN_OK;
 }
 
 extern "C" int ctgcn_set_gru_impl(int impl) {
-    CTGCN_REQUIRE(impl >= CTGCN_IMPL_AUTO && impl <= CTGCN_IMPL_TCGEN05, "set_gru_impl: unknown implementation %d", impl);
+    CTGCN_REQUIRE(impl >= CTGCN_IMPL_AUTO && impl <= CTGCN_IMPL_TC_UNPAIRED, "set_gru_impl: unknown implementation %d", impl);
     g_gru_impl.store(impl);
     return CTGCN_OK;
 }
@@ -159,8 +166,10 @@ static int cell_gates(int cell) { return cell == CTGCN_CELL_LSTM ? 4 : 3; }
 static size_t rnn_ws_simt(int cell, int d_in, int h) {
     return align_up((size_t)cell_gates(cell) * h * (d_in + h) * sizeof(float), 256);
 }
-static size_t gru_ws_tc(int d_in, int h) {   // packed bf16 hi|lo weights + biases
-    return align_up((size_t)3 * h * (d_in + h) * 2 * sizeof(uint16_t), 256) + 4096;
+static size_t gru_ws_tc(int d_in, int h) {   // packed bf16 hi|lo weights + biases (one-CTA kernel) or + bias-fold images (pair kernel)
+    const size_t r1 = align_up((size_t)3 * h * (d_in + h) * 2 * sizeof(uint16_t), 256) + 4096;
+    const size_t r2 = (h == 128 && d_in >= 32 && d_in <= 128) ? gru_tc2_workspace_bytes(d_in) : 0;
+    return r1 > r2 ? r1 : r2;
 }
 
 extern "C" size_t ctgcn_rnn_workspace_bytes(int cell, int d_in, int h) {
@@ -189,10 +198,15 @@ static int rnn_seq_impl(int cell, const float* seq, int64_t srs, int64_t sss, in
     const int impl = g_gru_impl.load();
     if (cell == CTGCN_CELL_GRU && impl != CTGCN_IMPL_SIMT) {
         char* tc_ws = (char*)workspace + rnn_ws_simt(cell, d_in, h);
-        int rc = launch_gru_tc(seq, srs, sss, n, steps, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, sc,
+        int rc = 1;
+        if (impl != CTGCN_IMPL_TC_ONE_CTA_R1)
+            rc = launch_gru_tc2(impl == CTGCN_IMPL_TC_UNPAIRED ? 1 : 2, seq, srs, sss, n, steps, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w,
+                                ln_b, eps, mode, y, yrs, yss, sc, tc_ws, gru_ws_tc(d_in, h), st);
+        if (rc == 1 && (impl == CTGCN_IMPL_TC_ONE_CTA_R1 || impl == CTGCN_IMPL_AUTO || impl == CTGCN_IMPL_TCGEN05))
+            rc = launch_gru_tc(seq, srs, sss, n, steps, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, sc,
                                tc_ws, gru_ws_tc(d_in, h), st);
         if (rc <= 0) return rc;  // done or failed
-        CTGCN_REQUIRE(impl == CTGCN_IMPL_AUTO, "gru_seq_fwd: tcgen05 path does not support d_in=%d h=%d", d_in, h);
+        CTGCN_REQUIRE(impl != CTGCN_IMPL_TCGEN05, "gru_seq_fwd: no tensor-core kernel for d_in=%d h=%d", d_in, h);
     }
     const int g = cell_gates(cell);
     float* wt_ih = (float*)workspace;

@@ -1,0 +1,788 @@
+// tcgen05 GRU over a short sequence + Σ/LayerNorm epilogue on CTA PAIRS (cta_group::2) — the compute-bound half of
+// CoreDiffusion.forward (layers.py:59-62) and the temporal GRU of CTGCN.forward (models.py:249-250).
+//
+// Why pairs (profiles/r02_experiments.md): the one-CTA kernel (gru_tc.cu) is bound by the SM's shared-memory / L1 data path
+// (128 B/cycle), not by its recurrence chain: per 128-row tile-step the tensor core fetches 960 KB of operands and the weight
+// ring is re-written with the full 393 KB packed weight set — ≈ 1.65 MB ≈ 12.9 K cycles of that pipe against 9.2 K cycles of
+// MMA work.  With cta_group::2 the two CTAs of a cluster share every weight chunk: each CTA holds HALF of the chunk's B rows,
+// the leader issues M = 256 MMAs over both CTAs' 128-row A tiles (accumulators stay per CTA: 128 TMEM lanes each), so per SM
+// the B-operand fetch and the ring writes halve (≈ 1.17 MB ≈ 9.1 K cycles per tile-step).
+//
+// Numerics as in gru_tc.cu: every fp32 operand is split a = hi + lo (two bf16 planes) and each product is three MMAs
+// hi·hi + lo·hi + hi·lo accumulated in fp32 in TMEM.  New here: the biases are added by the tensor core — ONE extra K = 16 MMA
+// per 64-feature block and step, A = a resident block of ones (k = 0, 1), B = the block's [b_in | b_ir+b_hr | b_iz+b_hz | b_hn]
+// as bf16 hi (k = 0) and lo (k = 1), N = 256, opens the accumulation of the whole accumulator set.  Every other MMA is then a
+// plain N = 192 accumulate (no "fresh"/"split-first" special cases, which would split B differently across the pair), step 0
+// needs no special gate code (W_hn·h + b_hn = b_hn is already in the accumulator), and the gate warps lose their 32 bias adds and
+// 8 broadcast shared-memory loads per 8-feature pass (measured harmless to the result: relL2 3.4e-7, r02_experiments.md).
+//
+// Per CTA (512 threads, one 128-row tile for the WHOLE sequence; both CTAs of a pair run in lock step):
+//   warp 0      weight producer: this CTA's half chunks (96 rows × 32 k, hi|lo = 12 KB) through a 6-stage ring (cp.async.bulk)
+//   warp 1      leader: MMA issuer.  follower: relays "my half chunk has landed" to the leader (a plain bulk copy can only
+//               complete_tx on a barrier of its own CTA)
+//   warps 4-7   input loaders: fp32 rows → bf16 hi/lo planes in UMMA core-matrix order
+//   warps 8-15  gate math (tcgen05.ld, ex2/rcp sigmoid & tanh), h written back as the next step's A operand, Σh / LayerNorm
+// Barriers the leader's MMA warp waits on (U_READY, H_READY, ACC_FREE*, W_PEER*) live in the LEADER's shared memory and count the
+// arrivals of both CTAs (the follower's warps arrive remotely: mapa + mbarrier.arrive, CTA-scope release — see tc_common.cuh for
+// why not cluster scope); everything the MMAs signal (W_EMPTY*, U_FREE, ACC_FULL*) is committed to both CTAs at once
+// (tcgen05.commit … multicast::cluster).  The input loaders pull the NEXT step's rows into the L2 one step ahead (prefetch.global.L2).
+// The same code compiles for CG = 1 (no cluster, whole chunks, local barriers): the A/B check of the pairing itself.
+//
+// Measured (B200, 1 M rows, profiles/r02_experiments.md): core GRU (10 steps, SUM_LN) 4.74 ms, temporal (8 steps, EACH_LN) 4.46-4.70 ms
+// against 5.27-5.33 / 5.60 ms for the one-CTA kernel of round 1 and 4.79-5.10 / 5.08-5.26 ms for this kernel without pairing.
+// Variants that were built, measured and removed: 16 gate warps (4.73 ms: the gate math of a block is MUFU-paced, ≈ 3.9 K cycles
+// with 8 or 16 warps against a floor of 2.56 K), a double-buffered h block 0 (4.77 ms: costs two ring stages), two concurrent
+// gate groups + both input parts ahead of "h ready" + early accumulator release (5.08 ms: the sets are only free at the very end
+// of a group's gate phase, so the input parts land ON the chain).
+//
+// Shapes: H = 128, d_in ∈ {32, 64, 96, 128}.  Other shapes: gru_simt.cu.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace ctgcn {
+namespace {
+
+using namespace tc;
+
+constexpr int H = 128, TILE_M = 128, BLK = 64, NB = H / BLK;   // NB blocks of 64 hidden features, one accumulator set each
+constexpr int CHUNK_K = 32, GATE_ROWS = 192;
+constexpr int A_PLANE = TILE_M * H * 2;                        // 32 KB: one bf16 plane of a 128 × 128 operand tile
+constexpr int NUM_LOADER_WARPS = 4;
+constexpr int FIRST_LOADER_WARP = 4, FIRST_WORKER_WARP = 8;    // warp 0 producer, warp 1 MMA / relay, warps 2-3 idle
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t COL_IN = 0, COL_R = 64, COL_Z = 128, COL_HN = 192;   // inside a 256-column accumulator set
+
+constexpr int NW = 8;                                           // gate-math warps
+template <int CG>
+struct Lay {   // per-CTA shared-memory map (identical in both CTAs of a pair: the MMA descriptors are CTA-relative)
+    static constexpr int ROWS = GATE_ROWS / CG;                  // weight rows of a chunk held by one CTA
+    static constexpr int W_PLANE = ROWS * CHUNK_K * 2;
+    static constexpr int W_CHUNK = 2 * W_PLANE;                  // hi | lo
+    static constexpr int STAGES = CG == 2 ? 6 : 3;               // 72 KB of weights in flight either way
+    static constexpr int FOLD_ROWS = 256 / CG;                   // bias rows [in | r | z | hn] of a block held by one CTA
+    static constexpr int FOLD_ONES = 2 * TILE_M * 16;            // A block [2 k-blocks][128 rows][8 bf16]
+    static constexpr int FOLD_BIAS = 2 * FOLD_ROWS * 16;         // B block of one feature block
+    static constexpr int FOLD_BYTES = FOLD_ONES + NB * FOLD_BIAS;
+    static constexpr int SM_U = 0;                               // U hi | lo (planes of A_PLANE bytes)
+    static constexpr int SM_H = SM_U + 2 * A_PLANE;              // h hi | lo
+    static constexpr int SM_W = SM_H + 2 * A_PLANE;              // weight ring
+    static constexpr int SM_FOLD = SM_W + STAGES * W_CHUNK;
+    static constexpr int SM_LN = SM_FOLD + FOLD_BYTES;           // ln_w | ln_b
+    static constexpr int SM_RED = SM_LN + 2 * H * 4;             // [2 buffers][2 feature groups][128 rows] fp32
+    static constexpr int SM_BAR = SM_RED + 2 * 2 * TILE_M * 4;
+    enum { W_FULL = 0, W_EMPTY = STAGES, W_PEER = 2 * STAGES, U_READY = 3 * STAGES, U_FREE, H_READY, ACC_FULL0, ACC_FULL1,
+           ACC_FREE0, ACC_FREE1, NUM_BARS };
+    static constexpr int SM_TMEM_PTR = SM_BAR + NUM_BARS * 8;
+    static constexpr int SMEM_BYTES = SM_TMEM_PTR + 16;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static constexpr int THREADS = 32 * (FIRST_WORKER_WARP + NW);
+    // setmaxnreg budgets (warps 0-3 | loaders 4-7 | gate warps) out of the 512 × 128 registers the CTA starts with
+    static constexpr int REG_WG0 = 56, REG_LOAD = 112, REG_GATE = 168;
+    static_assert(128 * REG_WG0 + 128 * REG_LOAD + 32 * NW * REG_GATE <= THREADS * 128, "register pool");
+    // byte offset (from the CTA's shared-memory base) of the hi 16-byte unit holding features f..f+7 (f % 8 == 0) of row m
+    static __device__ __forceinline__ uint32_t h_unit(int f, int m) { return SM_H + (f >> 3) * (TILE_M * 16) + m * 16; }
+    static constexpr int H_LO = A_PLANE;                         // byte distance hi plane → lo plane
+};
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// Chunk order: part ∈ {X block0, X block1, H block0, H block1}, then k-chunk of 32.  An X chunk holds the rows [n | r | z] of W_ih
+// for the block's 64 hidden features, an H chunk the rows [r | z | n] of W_hh.  Per chunk: rank 0's ROWS rows (hi plane, lo
+// plane), then rank 1's; element (row, k) of a plane at (k/8)·ROWS·16 + row·16 + (k%8)·2 (no-swizzle K-major core matrices,
+// LBO = ROWS·16, SBO = 128).  r/z rows and biases are multiplied by −log2(e), n rows by 2·log2(e): sigmoid/tanh need a bare ex2.
+// Then per rank the bias-fold image: ones block | NB bias blocks (see the header comment).
+__host__ __device__ constexpr int chunks_of(int k) { return k / CHUNK_K; }
+
+template <int CG>
+__global__ void pack2_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b_ih,
+                             const float* __restrict__ b_hh, int d_in, uint8_t* __restrict__ packed, uint8_t* __restrict__ fold) {
+    using LY = Lay<CG>;
+    constexpr float kLog2e = 1.4426950408889634f;
+    constexpr int UNITS = GATE_ROWS * (CHUNK_K / 8);             // 16-byte units of one plane of a whole chunk (all ranks)
+    const int cx = chunks_of(d_in), chh = chunks_of(H);
+    const int nchunks = NB * cx + NB * chh;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    // ---- bias-fold images: CG × (256 ones units + NB × 2·FOLD_ROWS bias units)
+    constexpr int FOLD_UNITS = LY::FOLD_BYTES / 16;
+    if (t < CG * FOLD_UNITS) {
+        const int rank = t / FOLD_UNITS, u = t % FOLD_UNITS;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (u < TILE_M) {
+            v.x = 0x3f803f80u;                                   // k = 0, 1: bf16 1.0 | 1.0 (k-block 0 of every row)
+        } else if (u >= LY::FOLD_ONES / 16) {
+            const int b = u - LY::FOLD_ONES / 16, blk = b / (2 * LY::FOLD_ROWS), r = b % (2 * LY::FOLD_ROWS);
+            if (r < LY::FOLD_ROWS && b_ih) {                     // k-block 0; k-block 1 stays zero
+                const int n = rank * LY::FOLD_ROWS + r, g4 = n / BLK, f = blk * BLK + n % BLK;   // accumulator column order
+                float bv;
+                if (g4 == 0) bv = b_ih[2 * H + f] * (2.f * kLog2e);                              // b_in
+                else if (g4 == 1) bv = (b_ih[f] + b_hh[f]) * -kLog2e;                            // b_ir + b_hr
+                else if (g4 == 2) bv = (b_ih[H + f] + b_hh[H + f]) * -kLog2e;                    // b_iz + b_hz
+                else bv = b_hh[2 * H + f] * (2.f * kLog2e);                                      // b_hn
+                const __nv_bfloat16 bh = __float2bfloat16_rn(bv);
+                const __nv_bfloat16 bl = __float2bfloat16_rn(bv - __bfloat162float(bh));
+                v.x = (uint32_t)__bfloat16_as_ushort(bh) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+            }
+        }
+        *reinterpret_cast<uint4*>(fold + (size_t)rank * LY::FOLD_BYTES + 16 * (size_t)u) = v;
+    }
+    if (t >= nchunks * UNITS) return;
+    const int c = t / UNITS, unit = t % UNITS;
+    const bool is_x = c < NB * cx;
+    const int cc = is_x ? c : c - NB * cx;
+    const int per = is_x ? cx : chh;
+    const int ktot = is_x ? d_in : H;
+    const int blk = cc / per, kc = cc % per;
+    const int kb = unit / GATE_ROWS, row = unit % GATE_ROWS;
+    const int g3 = row / BLK, f = row % BLK;
+    const int gate = is_x ? (g3 == 0 ? 2 : g3 - 1) : g3;        // X: [n, r, z]   H: [r, z, n]
+    const float* src = (is_x ? w_ih : w_hh) + (int64_t)(gate * H + blk * BLK + f) * ktot + kc * CHUNK_K + kb * 8;
+    const float scale = gate < 2 ? -kLog2e : 2.f * kLog2e;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = src[i] * scale;
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    const int rank = row / LY::ROWS, rr = row % LY::ROWS;
+    uint8_t* dst = packed + (size_t)c * (CG * LY::W_CHUNK) + (size_t)rank * LY::W_CHUNK + kb * (LY::ROWS * 16) + rr * 16;
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + LY::W_PLANE) = lo;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+struct Params2 {
+    const float* seq;
+    int64_t srs, sss, n;
+    int steps, d_in;
+    const uint8_t* packed;
+    const uint8_t* fold;
+    const float* ln_w;
+    const float* ln_b;
+    float eps;
+    float* y;
+    int64_t yrs, yss;
+    RowScatter sc;      // SUM_LN only: rows go to their node slice's buffer (fused snapshot exchange)
+    int num_tiles;
+    long long* trace;   // optional [24 events][64 steps] clock64 stamps of block 0 (ctgcn_debug_gru_trace), else NULL
+};
+
+#define GRU2_TRACE(e, gs)                                                                   \
+    do {                                                                                    \
+        if (p.trace && blockIdx.x == 0 && (gs) < 64u) p.trace[(e) * 64 + (gs)] = clock64(); \
+    } while (0)
+
+__device__ __forceinline__ float ex2_approx(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+template <int CG>
+__device__ __forceinline__ void umma_cg(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CG == 2) umma2_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
+    else umma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+template <int CG>
+__device__ __forceinline__ void commit_cg(uint32_t bar) {
+    if constexpr (CG == 2) umma2_commit(bar);
+    else umma_commit(bar);
+}
+// arrive on a barrier that lives in the pair's LEADER (rank 0)
+template <int CG>
+__device__ __forceinline__ void arrive_leader(uint32_t bar, uint32_t rank) {
+    if (CG == 2 && rank != 0) mbar_arrive_remote(bar, 0);
+    else mbar_arrive(bar);
+}
+// leader-side wait on a barrier with arrivals from both CTAs
+template <int CG>
+__device__ __forceinline__ void wait_pair(uint32_t bar, uint32_t parity) {
+    if constexpr (CG == 2) mbar_wait_cluster(bar, parity);
+    else mbar_wait(bar, parity);
+}
+
+// fp32 gate math of W pre-activation columns (complete: weights and biases, pre-scaled) → h_new.  Written stage by stage over
+// the W features so that the dependent chains (ex2 → rcp → ex2 → rcp) are interleaved.
+// sigmoid(a) = 1/(1 + 2^a'), tanh(s) = 1 − 2/(1 + 2^s'); one reciprocal serves r and z.
+template <int W>
+__device__ __forceinline__ void gate_math(float (&ea)[W], float (&eb)[W], float (&gi)[W], const float (&gh)[W], const float (&hold)[W],
+                                          float (&hn)[W]) {
+    float zz[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        ea[j] = ex2_approx(ea[j]);
+        eb[j] = ex2_approx(eb[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        ea[j] = 1.f + fminf(ea[j], 1e18f);     // clamped so that the product below stays finite
+        eb[j] = 1.f + fminf(eb[j], 1e18f);
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) hn[j] = rcp_approx(ea[j] * eb[j]);
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        zz[j] = hn[j] * ea[j];                                          // z
+        gi[j] = fmaf(hn[j] * eb[j], gh[j], gi[j]);                      // W_in x + b_in + r ⊙ (W_hn h + b_hn)
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) gi[j] = ex2_approx(gi[j]);
+#pragma unroll
+    for (int j = 0; j < W; ++j) gi[j] = rcp_approx(1.f + gi[j]);
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        const float nn = fmaf(-2.f, gi[j], 1.f);                        // tanh
+        hn[j] = fmaf(zz[j], hold[j] - nn, nn);                          // (1 − z) n + z h
+    }
+}
+
+template <int CG, int MODE>
+__global__ void __launch_bounds__(Lay<CG>::THREADS, 1) gru2_kernel(const Params2 p) {
+    using LY = Lay<CG>;
+    constexpr int THREADS = LY::THREADS;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = sbase + LY::SM_BAR;
+    auto bar = [&](int i) { return bar0 + 8u * i; };
+    const uint32_t rank = CG == 2 ? cluster_rank() : 0u;
+    const int cluster_id = (int)blockIdx.x / CG, nclusters = (int)gridDim.x / CG;
+    const int num_groups = (p.num_tiles + CG - 1) / CG;          // tile pairs
+    const int my_iters = (num_groups - cluster_id + nclusters - 1) / nclusters;
+    const int cpx = chunks_of(p.d_in);
+    constexpr int cph = chunks_of(H);
+    auto tile_of = [&](int t) { return (int64_t)(cluster_id + t * nclusters) * CG + rank; };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < LY::STAGES; ++s) {
+            mbar_init(bar(LY::W_FULL + s), 1);
+            mbar_init(bar(LY::W_EMPTY + s), 1);
+            mbar_init(bar(LY::W_PEER + s), 1);
+        }
+        mbar_init(bar(LY::U_READY), CG * NUM_LOADER_WARPS);
+        mbar_init(bar(LY::U_FREE), 1);
+        mbar_init(bar(LY::H_READY), CG * NW);
+        mbar_init(bar(LY::ACC_FULL0), 1);
+        mbar_init(bar(LY::ACC_FULL1), 1);
+        mbar_init(bar(LY::ACC_FREE0), CG * NW);
+        mbar_init(bar(LY::ACC_FREE1), CG * NW);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < H; i += THREADS) {
+        reinterpret_cast<float*>(smem + LY::SM_LN)[i] = p.ln_w[i];
+        reinterpret_cast<float*>(smem + LY::SM_LN)[H + i] = p.ln_b[i];
+    }
+    {   // this rank's bias-fold image (read by the tensor core: async proxy)
+        const uint4* src = reinterpret_cast<const uint4*>(p.fold + (size_t)rank * LY::FOLD_BYTES);
+        uint4* dst = reinterpret_cast<uint4*>(smem + LY::SM_FOLD);
+        for (int i = threadIdx.x; i < LY::FOLD_BYTES / 16; i += THREADS) dst[i] = src[i];
+        fence_proxy_async();
+    }
+    if constexpr (CG == 2) {
+        cluster_sync_all();                                     // barriers initialised in BOTH CTAs before anyone arrives remotely
+        if (warp == 1) tmem_alloc2(sbase + LY::SM_TMEM_PTR, TMEM_COLS);
+        tc_fence_before();
+        cluster_sync_all();
+    } else {
+        if (warp == 1) tmem_alloc(sbase + LY::SM_TMEM_PTR, TMEM_COLS);
+        tc_fence_before();
+        __syncthreads();
+    }
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + LY::SM_TMEM_PTR);
+
+    // every role branch starts with its warpgroup's setmaxnreg (Lay::REG_*)
+    if (warp == 0) {
+        // ===================================================== weight producer (this CTA's half of every chunk)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(LY::REG_WG0));
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            const int nx = NB * cpx;
+            const uint8_t* mine = p.packed + (size_t)rank * LY::W_CHUNK;
+            for (int t = 0; t < my_iters; ++t) {
+                for (int i = 0; i < p.steps; ++i) {
+                    // consumption order of the MMA issuer: X block0, [H block0], X block1, [H block1]
+                    for (int seg = 0; seg < 2 * NB; ++seg) {
+                        const bool rec = seg & 1;
+                        if (rec && i == 0) continue;
+                        const int blk = seg >> 1;
+                        const int first = rec ? nx + blk * cph : blk * cpx;
+                        const int count = rec ? cph : cpx;
+                        for (int c = first; c < first + count; ++c) {
+                            mbar_wait(bar(LY::W_EMPTY + stage), phase ^ 1);
+                            mbar_expect_tx(bar(LY::W_FULL + stage), LY::W_CHUNK);
+                            bulk_g2s(sbase + LY::SM_W + stage * LY::W_CHUNK, mine + (size_t)c * (CG * LY::W_CHUNK), LY::W_CHUNK,
+                                     bar(LY::W_FULL + stage));
+                            if (++stage == LY::STAGES) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(LY::REG_WG0));
+        if (CG == 2 && rank != 0) {
+            // ===================================================== follower: relay "my half of the chunk has landed"
+            uint32_t stage = 0, phase = 0;
+            for (int t = 0; t < my_iters; ++t) {
+                for (int i = 0; i < p.steps; ++i) {
+                    const int nch = NB * cpx + (i > 0 ? NB * cph : 0);
+                    for (int c = 0; c < nch; ++c) {
+                        mbar_wait(bar(LY::W_FULL + stage), phase);
+                        if (lane == 0) mbar_arrive_remote(bar(LY::W_PEER + stage), 0);
+                        __syncwarp();
+                        if (++stage == LY::STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        } else {
+            // ===================================================== MMA issuer (all 32 lanes run the control flow, one lane issues)
+            constexpr uint32_t idesc192 = umma_idesc_bf16(TILE_M * CG, 192), idesc256 = umma_idesc_bf16(TILE_M * CG, 256);
+            constexpr uint32_t A_STEP = (2 * TILE_M * 16) >> 4, B_STEP = (2 * LY::ROWS * 16) >> 4;
+            constexpr uint32_t U_LO_PLANE = A_PLANE >> 4, H_LO_PLANE = LY::H_LO >> 4, B_LO_PLANE = LY::W_PLANE >> 4;
+            uint32_t stage = 0, phase = 0, gs = 0;
+            long long w_wait = 0;                                   // trace: cycles spent waiting for weight chunks in this step
+            const uint64_t ones_desc = desc64(desc_lo(sbase + LY::SM_FOLD, TILE_M * 16));
+            // biases open the accumulation of the block's whole accumulator set [W_in·x | r | z | W_hn·h]
+            auto fold = [&](int blk) {
+                if (elect_one())
+                    umma_cg<CG>(tmem + (blk & 1) * 256, ones_desc,
+                                desc64(desc_lo(sbase + LY::SM_FOLD + LY::FOLD_ONES + blk * LY::FOLD_BIAS, LY::FOLD_ROWS * 16)),
+                                idesc256, 0u);
+                __syncwarp();
+            };
+            // one part = one block (64 hidden features) of the input (A = U) or recurrent (A = h_{i-1}) contribution
+            auto run_part = [&](int nchunks, int blk, bool recurrent) {
+                const uint32_t d = tmem + (blk & 1) * 256 + (recurrent ? COL_R : COL_IN);
+                for (int kc = 0; kc < nchunks; ++kc) {
+                    const long long t0 = p.trace ? clock64() : 0;
+                    mbar_wait(bar(LY::W_FULL + stage), phase);
+                    if constexpr (CG == 2) mbar_wait_cluster(bar(LY::W_PEER + stage), phase);
+                    if (p.trace) w_wait += clock64() - t0;
+                    tc_fence_after();
+                    if (elect_one()) {
+                        // descriptor (hi plane) of this chunk's 4 k-blocks of A, and the distance to the lo plane
+                        uint32_t a0, a_lo;
+                        if (!recurrent) {
+                            a0 = desc_lo(sbase + LY::SM_U + kc * (CHUNK_K / 8) * (TILE_M * 16), TILE_M * 16);
+                            a_lo = U_LO_PLANE;
+                        } else {
+                            a0 = desc_lo(sbase + LY::h_unit(kc * CHUNK_K, 0), TILE_M * 16);
+                            a_lo = H_LO_PLANE;
+                        }
+                        const uint32_t b0 = desc_lo(sbase + LY::SM_W + stage * LY::W_CHUNK, LY::ROWS * 16);
+#pragma unroll
+                        for (int ks = 0; ks < CHUNK_K / 16; ++ks) {
+                            const uint64_t ah = desc64(a0 + ks * A_STEP), al = desc64(a0 + a_lo + ks * A_STEP);
+                            const uint64_t bh = desc64(b0 + ks * B_STEP), bl = desc64(b0 + B_LO_PLANE + ks * B_STEP);
+                            umma_cg<CG>(d, ah, bh, idesc192, 1u);
+                            umma_cg<CG>(d, al, bh, idesc192, 1u);
+                            umma_cg<CG>(d, ah, bl, idesc192, 1u);
+                        }
+                        commit_cg<CG>(bar(LY::W_EMPTY + stage));
+                    }
+                    __syncwarp();
+                    if (++stage == LY::STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            };
+            auto commit = [&](int b) {
+                if (elect_one()) commit_cg<CG>(bar(b));
+                __syncwarp();
+            };
+            for (int t = 0; t < my_iters; ++t) {
+                for (int i = 0; i < p.steps; ++i, ++gs) {
+                    const uint32_t par = gs & 1;
+                    if (lane == 0) GRU2_TRACE(0, gs);
+                    wait_pair<CG>(bar(LY::U_READY), par);
+                    wait_pair<CG>(bar(LY::ACC_FREE0), par ^ 1);
+                    tc_fence_after();
+                    if (lane == 0) GRU2_TRACE(1, gs);
+                    fold(0);
+                    run_part(cpx, 0, false);
+                    if (lane == 0) GRU2_TRACE(2, gs);
+                    if (i > 0) {
+                        // the recurrence h_{i-1} → gates → h_i is the critical chain: block 0's recurrent part goes ahead of
+                        // block 1's input part (same chunk order in the producers)
+                        wait_pair<CG>(bar(LY::H_READY), par ^ 1);
+                        tc_fence_after();
+                        if (lane == 0) GRU2_TRACE(3, gs);
+                        run_part(cph, 0, true);
+                    }
+                    commit(LY::ACC_FULL0);
+                    if (lane == 0) GRU2_TRACE(4, gs);
+                    wait_pair<CG>(bar(LY::ACC_FREE1), par ^ 1);
+                    tc_fence_after();
+                    if (lane == 0) GRU2_TRACE(5, gs);
+                    fold(1);
+                    run_part(cpx, 1, false);
+                    commit(LY::U_FREE);
+                    if (lane == 0) GRU2_TRACE(6, gs);
+                    if (i > 0) run_part(cph, 1, true);
+                    commit(LY::ACC_FULL1);
+                    if (lane == 0) GRU2_TRACE(7, gs);
+                    if (lane == 0 && p.trace && blockIdx.x == 0 && gs < 64u) p.trace[15 * 64 + gs] = w_wait;
+                    w_wait = 0;
+                }
+            }
+        }
+    } else if (warp < FIRST_WORKER_WARP) {
+        // ===================================================== input loaders (warps 4-7; warps 2-3 idle)
+        if (warp < FIRST_LOADER_WARP) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(LY::REG_WG0));
+        } else {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(LY::REG_LOAD));
+            // A warp owns 32 tile rows.  Per load instruction its lanes cover 8 rows × 4 k-blocks (r = lane%8, c = lane/8):
+            // 128 contiguous bytes per row (8 L1 wavefronts instead of 32 for a row-per-lane mapping) and the 16-byte
+            // shared-memory stores of one 8-lane phase hit 8 consecutive rows of one k-block (conflict-free).
+            const int r8 = lane & 7, c4 = lane >> 3;
+            const int row_base = 32 * (warp - FIRST_LOADER_WARP);
+            uint8_t* u_hi = smem + LY::SM_U;
+            const int nkg = p.d_in / 32;             // k-groups of 4 k-blocks
+            const int nit = 4 * nkg;                 // (row-group, k-group) iterations per step: 16 for d_in = 128
+            uint32_t gs = 0;
+            // U comes from HBM (written by the SpMM, far larger than the L2): the rows of the NEXT step are pulled into the L2 one
+            // whole step ahead, so that the loads issued around "U buffer free" see L2 latency instead of DRAM latency
+            auto prefetch_step = [&](int t, int i) {
+                if (i >= p.steps) {
+                    i = 0;
+                    if (++t >= my_iters) return;
+                }
+                const int64_t tile_row0 = tile_of(t) * TILE_M;
+                const float* base = p.seq + (int64_t)i * p.sss;
+                const int lines_per_row = p.d_in / 32;                      // 128-byte lines
+                for (int l = lane; l < 32 * lines_per_row; l += 32) {       // this warp's 32 rows
+                    const int64_t srow = tile_row0 + row_base + l / lines_per_row;
+                    if (srow < p.n) prefetch_l2(base + srow * p.srs + (l % lines_per_row) * 32);
+                }
+            };
+            prefetch_step(0, 0);
+            for (int t = 0; t < my_iters; ++t) {
+                const int64_t tile_row0 = tile_of(t) * TILE_M;
+                for (int i = 0; i < p.steps; ++i, ++gs) {
+                    const float* base = p.seq + (int64_t)i * p.sss;
+                    float4 v[16];
+                    auto load_batch = [&](int it0, int cnt) {   // up to 8 iterations = 16 LDG.128 in flight per lane
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int it = it0 + u, rg = it & 3, kg = it >> 2;
+                            const int64_t srow = tile_row0 + row_base + 8 * rg + r8;
+                            if (u < cnt && srow < p.n) {
+                                const float* src = base + srow * p.srs + (4 * kg + c4) * 8;
+                                v[2 * u] = __ldg(reinterpret_cast<const float4*>(src));
+                                v[2 * u + 1] = __ldg(reinterpret_cast<const float4*>(src + 4));
+                            } else {
+                                v[2 * u] = v[2 * u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                        }
+                    };
+                    auto store_batch = [&](int it0, int cnt) {  // fp32 → bf16 hi/lo planes, 8 k-elements (16 B) per store
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (u < cnt) {
+                                const int it = it0 + u, rg = it & 3, kg = it >> 2;
+                                const int m = row_base + 8 * rg + r8, kb = 4 * kg + c4;
+                                const float f8[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w,
+                                                     v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
+                                uint4 hi, lo;
+                                split8(f8, hi, lo);
+                                *reinterpret_cast<uint4*>(u_hi + kb * (TILE_M * 16) + m * 16) = hi;
+                                *reinterpret_cast<uint4*>(u_hi + A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
+                            }
+                        }
+                    };
+                    const int first = nit < 8 ? nit : 8;
+                    load_batch(0, first);   // global loads are issued BEFORE the buffer is free: their latency is off the loop
+                    prefetch_step(t, i + 1);
+                    // the input parts of the previous step's MMAs must have released the single U buffer
+                    mbar_wait(bar(LY::U_FREE), (gs & 1) ^ 1);
+                    if (threadIdx.x == FIRST_LOADER_WARP * 32) GRU2_TRACE(13, gs);
+                    store_batch(0, first);
+                    for (int it0 = 8; it0 < nit; it0 += 8) {
+                        const int cnt = nit - it0 < 8 ? nit - it0 : 8;
+                        load_batch(it0, cnt);
+                        store_batch(it0, cnt);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) arrive_leader<CG>(bar(LY::U_READY), rank);
+                    if (threadIdx.x == FIRST_LOADER_WARP * 32) GRU2_TRACE(14, gs);
+                }
+            }
+        }
+    } else {
+        // ===================================================== gate warps: gate math, h, Σh, LayerNorm
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(LY::REG_GATE));
+        constexpr int CHW = NW / 4;          // warps sharing one TMEM lane quarter: partial row sums to exchange
+        constexpr int FPT = BLK / CHW;       // features per thread and block: 32
+        constexpr int NACC = 2 * FPT;        // features per thread
+        const int ww = warp - FIRST_WORKER_WARP;
+        const int q = warp & 3;              // TMEM lane quarter this warp may access
+        const int ch = ww >> 2;              // which FPT of a block's 64 features this thread owns
+        const int m = 32 * q + lane;         // row inside the tile
+        const uint32_t tmem_lane = tmem + ((uint32_t)(32 * q) << 16);
+        const float* lnw = reinterpret_cast<const float*>(smem + LY::SM_LN);
+        float* red = reinterpret_cast<float*>(smem + LY::SM_RED);
+        uint32_t gs = 0;
+        // feature of this thread's value j (0 ≤ j < NACC)
+        auto feat = [&](int j) { return (j / FPT) * BLK + ch * FPT + j % FPT; };
+
+        // row statistics over 128 values: this thread holds NACC of them, CHW−1 other warps of its lane quarter the rest
+        auto row_stats = [&](const float (&v)[NACC], float& mean, float& rstd) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < NACC; ++j) s += v[j];
+            red[ch * TILE_M + m] = s;
+            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+            float tot = 0.f;
+#pragma unroll
+            for (int c = 0; c < CHW; ++c) tot += red[c * TILE_M + m];     // same order in every thread of the row
+            mean = tot * (1.f / H);
+            float sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < NACC; ++j) {
+                const float dlt = v[j] - mean;
+                sq = fmaf(dlt, dlt, sq);
+            }
+            red[(CHW + ch) * TILE_M + m] = sq;
+            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+            float totq = 0.f;
+#pragma unroll
+            for (int c = 0; c < CHW; ++c) totq += red[(CHW + c) * TILE_M + m];
+            rstd = rsqrtf(totq * (1.f / H) + p.eps);
+        };
+        // EACH_LN: LayerNorm(h_s) of this step straight to y (row-per-thread 16-byte stores)
+        auto layer_norm_store = [&](const float (&v)[NACC], float* dst_row, bool valid) {
+            float mean, rstd;
+            row_stats(v, mean, rstd);
+            if (valid) {
+#pragma unroll
+                for (int j4 = 0; j4 < NACC; j4 += 4) {
+                    const int f = feat(j4);
+                    float4 o;
+                    o.x = (v[j4 + 0] - mean) * rstd * lnw[f + 0] + lnw[H + f + 0];
+                    o.y = (v[j4 + 1] - mean) * rstd * lnw[f + 1] + lnw[H + f + 1];
+                    o.z = (v[j4 + 2] - mean) * rstd * lnw[f + 2] + lnw[H + f + 2];
+                    o.w = (v[j4 + 3] - mean) * rstd * lnw[f + 3] + lnw[H + f + 3];
+                    *reinterpret_cast<float4*>(dst_row + f) = o;
+                }
+            }
+        };
+        // SUM_LN result of a tile: normalised rows are staged in the (now idle) h buffer with a 16-byte XOR swizzle and
+        // written out one whole 512-byte row per warp instruction — to y, or straight into the owning node slice's
+        // (peer) buffer: NVLink wants full-line stores, not 32 scattered 16-byte pieces per instruction.
+        auto layer_norm_store_rows = [&](const float (&v)[NACC], int64_t tile_row0) {
+            float mean, rstd;
+            row_stats(v, mean, rstd);
+            float* stage = reinterpret_cast<float*>(smem + LY::SM_H);   // 64 KB: [128 rows][32 chunks of 4 floats], chunk c of row r at c ^ (r & 31)
+#pragma unroll
+            for (int j4 = 0; j4 < NACC; j4 += 4) {
+                const int f = feat(j4);
+                float4 o;
+                o.x = (v[j4 + 0] - mean) * rstd * lnw[f + 0] + lnw[H + f + 0];
+                o.y = (v[j4 + 1] - mean) * rstd * lnw[f + 1] + lnw[H + f + 1];
+                o.z = (v[j4 + 2] - mean) * rstd * lnw[f + 2] + lnw[H + f + 2];
+                o.w = (v[j4 + 3] - mean) * rstd * lnw[f + 3] + lnw[H + f + 3];
+                *reinterpret_cast<float4*>(stage + m * H + (((f >> 2) ^ (m & 31)) << 2)) = o;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+            for (int rr = 0; rr < TILE_M / NW; ++rr) {
+                const int r = ww * (TILE_M / NW) + rr;
+                const int64_t grow = tile_row0 + r;
+                if (grow >= p.n) break;   // warp-uniform
+                const float4 o = *reinterpret_cast<const float4*>(stage + r * H + ((lane ^ (r & 31)) << 2));
+                float* dst = p.sc.slices ? p.sc.row_ptr(grow) : p.y + grow * p.yrs;
+                *reinterpret_cast<float4*>(dst + 4 * lane) = o;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");   // the staging area is h again from the next tile's first step on
+        };
+        auto put_h8 = [&](const float (&f8)[8], int f) {
+            uint4 hi, lo;
+            split8(f8, hi, lo);
+            uint8_t* dst = smem + LY::h_unit(f, m);
+            *reinterpret_cast<uint4*>(dst) = hi;
+            *reinterpret_cast<uint4*>(dst + LY::H_LO) = lo;
+        };
+
+        for (int t = 0; t < my_iters; ++t) {
+            const int64_t row = tile_of(t) * TILE_M + m;
+            const bool valid = row < p.n;
+            float acc_out[NACC];   // Σ_s h_s (SUM_LN) / h_s of the current step (EACH_LN) for this thread's features
+#pragma unroll
+            for (int j = 0; j < NACC; ++j) acc_out[j] = 0.f;
+
+            for (int i = 0; i < p.steps; ++i, ++gs) {
+                const uint32_t par = gs & 1;
+                float h0[FPT];   // block 0 of h_i, published only when no MMA reads h_{i-1} any more
+#pragma unroll
+                for (int hf = 0; hf < NB; ++hf) {
+                    if (lane == 0 && q == 0 && ch == 0) GRU2_TRACE(8 + 2 * hf, gs);
+                    mbar_wait(bar(LY::ACC_FULL0 + hf), par);
+                    tc_fence_after();
+                    if (lane == 0 && q == 0 && ch == 0) GRU2_TRACE(9 + 2 * hf, gs);
+#pragma unroll
+                    for (int sub = 0; sub < FPT / 8; ++sub) {
+                        const int f0 = hf * BLK + ch * FPT + sub * 8;           // first of 8 features (one 16-byte operand unit)
+                        const uint32_t col = hf * 256 + ch * FPT + sub * 8;     // + gate block
+                        float hold[8], hn8[8];
+                        if (i > 0) {
+                            const uint8_t* src = smem + LY::h_unit(f0, m);
+                            const uint4 hi = *reinterpret_cast<const uint4*>(src);
+                            const uint4 lo = *reinterpret_cast<const uint4*>(src + LY::H_LO);
+                            join8(hi, lo, hold);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) hold[j] = 0.f;
+                        }
+                        float ea[8], eb[8], gi[8], gh[8];
+                        tmem_ld8(tmem_lane + col + COL_R, ea);
+                        tmem_ld8(tmem_lane + col + COL_Z, eb);
+                        tmem_ld8(tmem_lane + col + COL_IN, gi);
+                        tmem_ld8(tmem_lane + col + COL_HN, gh);                 // step 0: b_hn alone (bias fold, no recurrent part)
+                        tmem_ld_wait();
+                        gate_math<8>(ea, eb, gi, gh, hold, hn8);
+                        if (hf == 0) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) h0[sub * 8 + j] = hn8[j];
+                        } else {
+                            // every MMA that reads h_{i-1} has completed (acc1 full): h may be overwritten in place.  The held-back
+                            // block 0 is published piecewise here so that its ALU work hides under the MUFU latency of this pass.
+                            const float f8[8] = {h0[sub * 8], h0[sub * 8 + 1], h0[sub * 8 + 2], h0[sub * 8 + 3],
+                                                 h0[sub * 8 + 4], h0[sub * 8 + 5], h0[sub * 8 + 6], h0[sub * 8 + 7]};
+                            put_h8(f8, ch * FPT + sub * 8);
+                            put_h8(hn8, f0);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int a = hf * FPT + sub * 8 + j;
+                            if (MODE == CTGCN_GRU_SUM_LN) acc_out[a] += hn8[j];
+                            else acc_out[a] = hn8[j];
+                        }
+                        if (lane == 0 && q == 0 && ch == 0 && sub < 4) GRU2_TRACE(16 + hf * 4 + sub, gs);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) arrive_leader<CG>(bar(LY::ACC_FREE0 + hf), rank);
+                }
+                // this warp's share of h_i is complete in shared memory (all shares: the next step's recurrent MMAs may read it)
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) arrive_leader<CG>(bar(LY::H_READY), rank);
+                if (lane == 0 && q == 0 && ch == 0) GRU2_TRACE(12, gs);
+                if (MODE == CTGCN_GRU_EACH_LN) layer_norm_store(acc_out, p.y + row * p.yrs + (int64_t)i * p.yss, valid);
+            }
+            if (MODE == CTGCN_GRU_SUM_LN) layer_norm_store_rows(acc_out, row - m);
+        }
+    }
+
+    tc_fence_before();
+    if constexpr (CG == 2) {
+        cluster_sync_all();      // neither CTA may exit (or free TMEM) while the pair's MMAs can still touch its memory
+        if (warp == 1) tmem_dealloc2(tmem, TMEM_COLS);
+    } else {
+        __syncthreads();
+        if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+    }
+}
+
+template <int CG>
+size_t packed_bytes(int d_in) {
+    return (size_t)(NB * chunks_of(d_in) + NB * chunks_of(H)) * CG * Lay<CG>::W_CHUNK;
+}
+
+template <int CG>
+int launch_variant(const Params2& p0, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int mode, void* ws,
+                   size_t ws_bytes, cudaStream_t st) {
+    using LY = Lay<CG>;
+    Params2 p = p0;
+    const size_t pb = packed_bytes<CG>(p.d_in), fb = (size_t)CG * LY::FOLD_BYTES;
+    CTGCN_REQUIRE(ws && ws_bytes >= pb + fb, "gru_tc2: workspace too small (%zu < %zu)", ws_bytes, pb + fb);
+    uint8_t* packed = (uint8_t*)ws;
+    uint8_t* fold = packed + pb;
+    {
+        ProfScope prof(PROF_PACK, st);
+        const int nchunks = NB * chunks_of(p.d_in) + NB * chunks_of(H);
+        int threads = nchunks * GATE_ROWS * (CHUNK_K / 8);
+        const int fold_threads = CG * LY::FOLD_BYTES / 16;
+        if (fold_threads > threads) threads = fold_threads;
+        pack2_kernel<CG><<<(threads + 255) / 256, 256, 0, st>>>(w_ih, w_hh, b_ih, b_hh, p.d_in, packed, fold);
+        CTGCN_LAUNCH_OK("pack2_kernel");
+    }
+    p.packed = packed;
+    p.fold = fold;
+    int dev = 0, sm_count = 0;
+    CTGCN_CUDA_OK(cudaGetDevice(&dev));
+    CTGCN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    auto kern = mode == CTGCN_GRU_SUM_LN ? gru2_kernel<CG, CTGCN_GRU_SUM_LN> : gru2_kernel<CG, CTGCN_GRU_EACH_LN>;
+    CTGCN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LY::SMEM_BYTES));
+    const int groups = (p.num_tiles + CG - 1) / CG, max_clusters = sm_count / CG;
+    const int clusters = groups < max_clusters ? groups : max_clusters;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * CG));
+    cfg.blockDim = dim3(LY::THREADS);
+    cfg.dynamicSmemBytes = LY::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ProfScope prof(PROF_GRU, st);
+    CTGCN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
+    CTGCN_LAUNCH_OK("gru2_kernel");
+    return CTGCN_OK;
+}
+
+}  // namespace
+
+static long long* g_gru2_trace = nullptr;
+void set_gru2_trace(long long* buf) { g_gru2_trace = buf; }
+
+size_t gru_tc2_workspace_bytes(int d_in) {
+    // the larger of the two builds (whole chunks: same weight bytes; fold images: 2 × 12 KB vs 20 KB)
+    return align_up(packed_bytes<2>(d_in) + 2 * (size_t)Lay<2>::FOLD_BYTES + (size_t)Lay<1>::FOLD_BYTES, 256);
+}
+
+// returns 0 = done, <0 = error, 1 = shape not supported by this path.  cg: CTAs per MMA (2 = CTA pairs, 1 = the A/B build without pairing)
+int launch_gru_tc2(int cg, const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* w_ih,
+                   const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
+                   int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* sc, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (h != H || d_in < 32 || d_in > 128 || (d_in % 32)) return 1;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (!al16(seq) || (srs & 3) || (sss & 3)) return 1;
+    if (sc ? ((sc->row_stride & 3) || (sc->col_offset & 3)) : (!al16(y) || (yrs & 3) || (yss & 3))) return 1;
+    Params2 p;
+    p.seq = seq;
+    p.srs = srs;
+    p.sss = sss;
+    p.n = n;
+    p.steps = steps;
+    p.d_in = d_in;
+    p.packed = nullptr;
+    p.fold = nullptr;
+    p.ln_w = ln_w;
+    p.ln_b = ln_b;
+    p.eps = eps;
+    p.y = y;
+    p.yrs = yrs;
+    p.yss = yss;
+    p.sc = sc ? *sc : RowScatter();
+    p.num_tiles = (int)((n + TILE_M - 1) / TILE_M);
+    p.trace = g_gru2_trace;
+    if (cg == 2) return launch_variant<2>(p, w_ih, w_hh, b_ih, b_hh, mode, ws, ws_bytes, st);
+    return launch_variant<1>(p, w_ih, w_hh, b_ih, b_hh, mode, ws, ws_bytes, st);
+}
+
+}  // namespace ctgcn

@@ -226,13 +226,11 @@ int launch_linear_tc(const float* x, int64_t ldx, int64_t n, int64_t d_in, const
         pack_linear_weights_kernel<<<(units + 255) / 256, 256, 0, st>>>(w, (int)d_in, (int)d_out, packed);
         CTGCN_LAUNCH_OK("pack_linear_weights_kernel");
     }
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        CTGCN_CUDA_OK(cudaGetDevice(&dev));
-        CTGCN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        CTGCN_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    }
+    // per device (a process may drive several GPUs; the attribute belongs to the device's context): set on every call
+    int dev = 0, sm_count = 0;
+    CTGCN_CUDA_OK(cudaGetDevice(&dev));
+    CTGCN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    CTGCN_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     Params p;
     p.x = x;
     p.ldx = ldx;

@@ -1,4 +1,4 @@
-// EXPERIMENTAL building block (round-2 groundwork, never run): one GRU half-step through `tcgen05.mma.cta_group::2`.
+// Building-block self test (green on a B200 since round 2): one GRU half-step through `tcgen05.mma.cta_group::2`.
 //
 // profiles/r02_gru_design.md, step 2: a CTA pair shares every weight chunk — each CTA holds HALF of the B rows, the leader issues
 // M = 256 MMAs over both CTAs' 128-row A tiles, accumulators stay per CTA (128 TMEM lanes each).  This kernel exercises exactly
@@ -71,55 +71,6 @@ __global__ void pack_pair_kernel(const float* __restrict__ w_ih, const float* __
     uint8_t* dst = packed + (size_t)c * PAIR_CHUNK + (size_t)rank * HALF_BYTES + off;
     *reinterpret_cast<uint4*>(dst) = hi;
     *reinterpret_cast<uint4*>(dst + HALF_PLANE) = lo;
-}
-
-__device__ __forceinline__ uint32_t cluster_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t cta) {
-    uint32_t remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(cta));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-}
-// wait on a LOCAL barrier whose arrivals come from the peer CTA: cluster-scope acquire
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0, ok = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity), "r"(20000u)
-            : "memory");
-        if (!ok && ++spins > (1u << 24)) __trap();
-    }
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    const uint32_t z = 0;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(z)
-        : "memory");
-}
-__device__ __forceinline__ void umma2_commit(uint32_t bar) {   // arrives on `bar` (same offset) in both CTAs of the pair
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"((uint16_t)3)
-                 : "memory");
 }
 
 // split products hi·hi + lo·hi + hi·lo of one K = 16 step; a_lo32 / b_lo32: descriptor low words of the hi planes

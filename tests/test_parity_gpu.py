@@ -37,9 +37,10 @@ def xin(x, dev):
     return torch.from_numpy(x).to(dev) if isinstance(x, np.ndarray) else oracle_torch.to_torch_coo(x).to(dev)
 
 
-@pytest.fixture(scope="module", params=["simt", "auto"])
+@pytest.fixture(scope="module", params=["simt", "auto", "unpaired", "one_cta_r1"])
 def impl(request, lib, cuda_device):
-    lib.set_gru_impl(lib.IMPL_SIMT if request.param == "simt" else lib.IMPL_AUTO)
+    lib.set_gru_impl({"simt": lib.IMPL_SIMT, "auto": lib.IMPL_AUTO, "unpaired": lib.IMPL_TC_UNPAIRED,
+                      "one_cta_r1": lib.IMPL_TC_ONE_CTA_R1}[request.param])
     yield request.param
     lib.set_gru_impl(lib.IMPL_AUTO)
 
