@@ -103,95 +103,117 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------ CPU baseline
+# ------------------------------------------------------------------------------------------ CPU baseline / reference arm
 class CpuReference:
-    """The torch-CPU port of the reference path (oracle/oracle_torch.py: torch.sparse.mm ×K, nn.GRU, LayerNorm, nn.Linear —
-    the same library calls the reference makes) on ONE snapshot's MLP + CoreDiffusion: a bounded sample of the workload
-    (same density and K, node count capped at 100 K)."""
+    """The torch-CPU port of the reference path (oracle/oracle_torch.py: torch.sparse.mm ×K, nn.GRU, LayerNorm, nn.Linear — the
+    same library calls the reference makes; kind "port": the reference is Python and cannot travel to the GPU box).  Nothing
+    here imports the product package: the graph comes from oracle/synth_np.py (numpy / scipy; same seeds → same graphs as the
+    GPU arm).  One pass = 1/T of the workload's forward: ONE snapshot's MLP + CoreDiffusion at `n` nodes plus the temporal
+    GRU + LayerNorm over n/T rows × T steps; edges-aggregated/s of that sample is the metric of the whole workload (both scale by T)."""
 
-    def __init__(self, cfg):
+    def __init__(self, cfg, n):
         import numpy as np
         import torch
-        from ctgcn_b200 import synth
-        from oracle import cases, oracle_torch
+        from oracle import cases, oracle_torch, synth_np
 
         self.torch = torch
-        n = min(cfg["n"], 100_000)
         m = int(cfg["m"] * (n / cfg["n"]))
-        self.snap = snap = synth.make_snapshot(cfg["kind"], n, m, cfg["K"], seed=0, levels=cfg.get("levels", "top"))
-        adj = snap.coo_list("cpu")
-        d = cfg["D"]
-        x = synth.features(n, d, 1000)
+        d, T = cfg["D"], cfg["T"]
+        t0 = time.perf_counter()
+        adj, st = synth_np.make_adj_list(cfg["kind"], n, m, cfg["K"], seed=0, levels=cfg.get("levels", "top"))
+        self.setup_s = time.perf_counter() - t0
+        self.e_agg = st["edges_aggregated"]
+        x = synth_np.features(n, d, 1000)
         sd = {k: torch.from_numpy(v) for k, v in cases.ctgcn_params(np.random.default_rng(0), d, d, d, 1, 1, 1, "C").items()}
+        rows_t = max(n // T, 1)
+        seq = torch.randn(rows_t, T, d, generator=torch.Generator().manual_seed(7))
 
         def run():
             with torch.no_grad():
                 h = oracle_torch.mlp(x, sd, "mlp_list.0.", 1, "L")
-                return oracle_torch.cdn(h, adj, sd, "duffision_list.0.", 1)
+                y = oracle_torch.cdn(h, adj, sd, "duffision_list.0.", 1)
+                o = oracle_torch._gru_all_outputs(seq, sd, "")
+                o = torch.nn.functional.layer_norm(o, (d,), sd["norm.weight"], sd["norm.bias"], 1e-5)
+                return y, o
 
         self.run = run
         self.host_cores = os.cpu_count() or 1
-        self.what = (f"1 snapshot MLP+CoreDiffusion fwd, {cfg['kind'].upper()} N={n} m={m} K={snap.k} D={d} "
-                     f"(E_agg={snap.edges_aggregated})")
-        self.reduced = "" if n == cfg["n"] else f", node count reduced from {cfg['n']}"
-        self.threads, self.tried = None, []
+        self.what = (f"1/{T} of the step: snapshot 0 of {T} (MLP + CoreDiffusion fwd, {cfg['kind'].upper()} N={n} m={m} K={st['k']} "
+                     f"D={d}, E_agg={self.e_agg}) + temporal GRU + LayerNorm on N/{T} rows x {T} steps")
+        self.reduced = "" if n == cfg["n"] else f"; node count reduced from {cfg['n']} (same density, K, width)"
+        self.threads, self.tried = None, {}
 
     def time_once(self):
         t0 = time.perf_counter()
         self.run()
         return time.perf_counter() - t0
 
-    def sweep(self, seconds_budget=25.0):
-        """Pick the thread count (mirrors main.py:51-52 `torch.set_num_threads`): one warm-up + one timed run each."""
-        cand = sorted({c for c in (1, 2, 4, 8, 16, 32, 64, 128, self.host_cores) if c <= self.host_cores})
-        best, spent = None, 0.0
+    def sweep(self):
+        """Thread count (mirrors main.py:51-52 `torch.set_num_threads`): every power of two up to the host's core count (and the
+        count itself), one timed pass each after one warm-up — no time cut-off: the best count is never 'the last one tried'
+        by accident."""
+        cand = sorted({c for c in (1, 2, 4, 8, 16, 32, 64, 128, 256, self.host_cores) if c <= self.host_cores})
+        self.torch.set_num_threads(cand[-1])
+        self.time_once()                                    # warm-up (allocator, first-touch)
+        best = None
         for thr in cand:
-            self.tried.append(thr)
             self.torch.set_num_threads(thr)
-            warm = self.time_once()
             dt = self.time_once()
-            spent += warm + dt
+            self.tried[thr] = round(dt, 3)
             if best is None or dt < best:
                 best, self.threads = dt, thr
-            if spent > seconds_budget:
-                break
         self.torch.set_num_threads(self.threads)
         return best
 
-    def record(self, seconds):
-        sample = (f"{self.what}; best of thread counts {self.tried} = {self.threads} threads on {self.host_cores} cores; "
-                  f"same density/K as the workload{self.reduced}")
-        return dict(value=self.snap.edges_aggregated / seconds, unit="edges-aggregated/s", cores=self.threads, kind="port",
-                    sample=sample, seconds=seconds, host_cores=self.host_cores)
+    def record(self, seconds, swept_on=None):
+        sweep = f"thread sweep {self.tried} s -> {self.threads} threads of {self.host_cores} cores"
+        if swept_on is not None:
+            sweep = f"thread count from a sweep on a {swept_on}-node proxy: {sweep}"
+        return dict(value=self.e_agg / seconds, unit="edges-aggregated/s", cores=self.threads, kind="port",
+                    sample=f"{self.what}{self.reduced}; {sweep}", seconds=seconds, host_cores=self.host_cores)
 
 
-def cpu_reference_sample(cfg, seconds_budget=25.0):
-    ref = CpuReference(cfg)
-    return ref.record(ref.sweep(seconds_budget))
+def _proxy_nodes(cfg, cap_bytes):
+    """Largest node count ≤ the workload's whose per-core-sums tensor [N, K, D] fp32 stays under cap_bytes."""
+    n = int(cap_bytes // (cfg["K"] * cfg["D"] * 4))
+    return min(cfg["n"], max(n // 1000 * 1000, 1000))
+
+
+def cpu_reference_sample(cfg):
+    """cpu_baseline of the GPU arm's line: a bounded sample (≈ 100 K nodes: 10-30 s of CPU work including the thread sweep)."""
+    ref = CpuReference(cfg, min(_proxy_nodes(cfg, 512 << 20), 100_000))
+    return ref.record(ref.sweep())
 
 
 def run_reference_arm(args, cfg):
-    """`--impl reference`: the reference's CPU path (kind "port", see CpuReference) on the host cores.  One step = one timed
-    pass over the bounded sample at the thread count the initial sweep picked; under torchrun rank 0 alone runs it."""
+    """`--impl reference`: the reference's CPU path (kind "port", see CpuReference) on the host cores at the workload's FULL node
+    count when its [N, K, D] tensors fit comfortably in host memory (cfg4: 1 M nodes, 5.1 GB each), thread count picked by a sweep
+    on a 100 K-node proxy.  One step = one timed pass; under torchrun rank 0 alone runs it.  Bounded: stops after ≈ 150 s."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ref = CpuReference(cfg)
-    ref.sweep(25.0)                                 # also the first warm-up
-    for _ in range(max(args.warmup - 1, 0)):
-        ref.time_once()
-    times = []
-    for _ in range(max(args.steps, 1)):
-        times.append(ref.time_once())
-        if sum(times) > 150:                        # bounded: a slow host stops early and reports the steps it did
+    proxy = CpuReference(cfg, min(_proxy_nodes(cfg, 512 << 20), 100_000))
+    proxy.sweep()
+    ref = CpuReference(cfg, _proxy_nodes(cfg, 6 << 30))
+    ref.threads, ref.tried = proxy.threads, proxy.tried
+    ref.torch.set_num_threads(ref.threads)
+    n_proxy = proxy.what.split("N=")[1].split(" ")[0]
+    del proxy
+    times, spent = [], 0.0
+    for it in range(max(args.warmup, 1) + max(args.steps, 1)):
+        dt = ref.time_once()
+        spent += dt
+        if it >= max(args.warmup, 1) or spent > 150:       # a slow host: the warm-up passes count as steps rather than nothing
+            times.append(dt)
+        if spent > 150 and times:
             break
     t = sum(times) / len(times)
-    base = ref.record(t)
+    base = ref.record(t, swept_on=n_proxy)
     val = base["value"]
     line = {"metric": "edges-aggregated/s, CTGCN CoreDiffusion forward", "value": val, "unit": "edges-aggregated/s",
             "impl": "reference", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": t * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["name"]},
+            "config": {"workload": cfg["name"], "config": args.config, "graph_setup_s": round(ref.setup_s, 1)},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": val, "unit": "edges-aggregated/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -373,23 +395,50 @@ def main():
     rows = dist.node_slices(n, world)[rank]
     assert tuple(out.shape) == (T, rows[1] - rows[0], d) and bool(torch.isfinite(out).all())
 
+    # ---- driver-visible multi-GPU parity: rank 0 rebuilds ONE snapshot that another rank owns, recomputes it alone on its own
+    # GPU and compares its node slice bit for bit with what arrived through the exchange (peer stores / NCCL); the temporal GRU
+    # on the slice is the same kernel on the same rows as in the single-GPU forward
+    sharded_parity = None
+    if world > 1:
+        model.keep_exchanged = True
+        step_resident()
+        torch.cuda.synchronize()
+        td.barrier()
+        if rank == 0:
+            tq = 1                                                  # owned by rank 1
+            snap = synth.make_snapshot(cfg["kind"], n, cfg["m"], K, seed=tq, levels=cfg.get("levels", "top"))
+            with torch.no_grad():
+                trans = model.mlp_list[tq](synth.features(n, d, 1000 + tq).to(dev))
+                emb = model.duffision_list[tq].forward_into(trans, snap.plan(dev))
+                got = model._exchanged[:, tq, :]
+                same = bool(torch.equal(emb[rows[0]:rows[1]], got))
+                maxdiff = float((emb[rows[0]:rows[1]] - got).abs().max())
+                again = model._temporal(model._exchanged).transpose(0, 1)
+                same_t = bool(torch.equal(again, out))
+            sharded_parity = ("bit-identical" if same and same_t else f"MISMATCH (max |diff| {maxdiff:.3e}, temporal equal {same_t})") + \
+                f" (snapshot {tq} of rank 1: rows [{rows[0]}, {rows[1]}) recomputed on rank 0 vs the exchanged buffer; temporal GRU re-run)"
+            del snap, trans, emb
+        model.keep_exchanged = False
+
     if rank != 0:
         if world > 1:
             td.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel class (this rank's launches; every rank runs the same kernels)
-    L = len(owned)
-    spmm_bytes = sum(s["entries"] * (9 + 4 * d) + n * 4 + s["k"] * n * 4 * d for s in stats.values()) / max(L, 1)
+    # SpMM: algorithmic bytes of everything launched in the timed region ÷ total kernel time (a row-chunked CoreDiffusion issues
+    # several launches per snapshot: per-LAUNCH averages would credit each chunk with the whole snapshot's bytes)
+    spmm_bytes_step = sum(s["entries"] * (9 + 4 * d) + n * 4 + s["k"] * n * 4 * d for s in stats.values())
     gru_core_flops = sum(n * s["k"] * 6 * d * (d + d) for s in stats.values())
     rows_n = rows[1] - rows[0]
     gru_temporal_flops = rows_n * T * 6 * d * (d + d)
     by_kernel = {}
     if kern["spmm"]["launches"]:
+        per_launch = spmm_bytes_step * args.steps / kern["spmm"]["launches"]
         avg = kern["spmm"]["ms"] / kern["spmm"]["launches"]
-        by_kernel["cumspmm"] = {"bound": "hbm", "achieved": spmm_bytes / (avg * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                                "avg_ms": avg, "launches": kern["spmm"]["launches"], "share_of_step": kern["spmm"]["ms"] / ms,
-                                "algorithmic_bytes_per_launch": spmm_bytes}
+        by_kernel["cumspmm"] = {"bound": "hbm", "achieved": spmm_bytes_step * args.steps / (kern["spmm"]["ms"] * 1e-3) / 1e9,
+                                "peak": peaks["hbm"], "unit": "GB/s", "avg_ms": avg, "launches": kern["spmm"]["launches"],
+                                "share_of_step": kern["spmm"]["ms"] / ms, "algorithmic_bytes_per_launch": per_launch}
     if kern["gru"]["launches"]:
         flops = (gru_core_flops + gru_temporal_flops) * args.steps
         by_kernel["gru_seq"] = {"bound": "tensor", "achieved": flops / (kern["gru"]["ms"] * 1e-3) / 1e12, "peak": peaks["tf_sustained"],
@@ -428,6 +477,7 @@ def main():
         "e2e": {"value": e_agg / (ms_e2e / args.steps * 1e-3), "unit": "edges-aggregated/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": launches_total,
+        "sharded_parity": sharded_parity,
         "clocks": clocks,
         "roofline": roofline,
         "roofline_by_kernel": by_kernel,

@@ -204,6 +204,8 @@ def ctgcn_forward_sharded(model, x_list, adj_list):
                 n = int(getattr(model, "node_num", 0)) or _infer_rows(x_list, adj_list)
                 hx_local = torch.zeros(n, tl, model.output_dim, dtype=torch.float32, device=dev)
             seq = exchange_to_node_slices(hx_local, T, mode=mode)
+        if getattr(model, "keep_exchanged", False):     # bench / tests: the [rows, T, D] sequence this rank received (a view)
+            model._exchanged = seq
         out = model._temporal(seq)
         if getattr(model, "gather_output", True):
             out = gather_node_slices(out, n)

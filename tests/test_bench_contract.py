@@ -28,3 +28,15 @@ def test_reference_arm_non_zero_rank_is_silent(lib):
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "tiny", "--gpus", "2"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+def test_reference_arm_never_loads_the_product_library():
+    """Round-1 verdict: the reference process must not map libctgcn_b200.so (its graph comes from oracle/synth_np.py)."""
+    code = (
+        "import sys, types; sys.argv=['bench.py','--impl','reference','--config','tiny','--steps','1','--warmup','0'];"
+        f"sys.path.insert(0, {ROOT!r}); import bench; bench.main();"
+        "maps=open('/proc/self/maps').read();"
+        "assert 'libctgcn_b200' not in maps, 'product library mapped';"
+        "assert not any(m == 'ctgcn_b200' or m.startswith('ctgcn_b200.') for m in sys.modules), 'product package imported'")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]

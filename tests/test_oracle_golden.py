@@ -87,3 +87,33 @@ def test_build_core_adj_list_semantics():
     assert (adj[1].toarray() == a1.toarray()).all()
     adj2, mc2 = oracle_np.build_core_adj_list([a1, a2, a3], max_core=2)  # sticky max_core keeps files [:2]
     assert mc2 == 2 and len(adj2) == 2 and (adj2[0].toarray() == a2.toarray() + np.eye(3)).all()
+
+
+def test_synth_np_matches_networkx_and_the_loader_contract():
+    """oracle/synth_np.py (the reference arm's graph generator): exact core numbers (vs networkx) and the list of
+    helper.py:51-82 (densest core first, +I on the first matrix, nested, identical levels dropped)."""
+    import networkx as nx
+    from oracle import synth_np
+    for kind in ("er", "powerlaw"):
+        n, m = 1500, 9000
+        u, v = (synth_np.er_edges if kind == "er" else synth_np.powerlaw_edges)(n, m, np.random.default_rng(5))
+        g = nx.Graph()
+        g.add_nodes_from(range(n))
+        g.add_edges_from(zip(u.tolist(), v.tolist()))
+        cn = nx.core_number(g)
+        assert (synth_np.core_numbers(n, u, v) == np.array([cn[i] for i in range(n)])).all()
+        for levels, k in (("top", 3), ("loader", 5)):
+            adj, st = synth_np.make_adj_list(kind, n, m, k, seed=5, levels=levels)
+            dense = [a.to_dense().numpy() for a in adj]
+            assert st["k"] == len(adj) <= k and st["edges_aggregated"] == sum(int(a._nnz()) for a in adj)
+            first = dense[0] - np.eye(n, dtype=np.float32)
+            assert (np.diag(first) == 0).all() and (first == first.T).all()
+            prev = first
+            for lvl, d in zip(st["core_levels"][1:], dense[1:]):
+                assert (d - prev >= 0).all() and (d != prev).any()          # nested, and never a duplicate of the previous entry
+                sub = nx.k_core(g, k=lvl, core_number=cn)
+                a = np.zeros((n, n), dtype=np.float32)
+                for x, y in sub.edges():
+                    a[x, y] = a[y, x] = 1.0
+                assert (a == d).all()
+                prev = d
