@@ -57,6 +57,7 @@ SIGNATURES = {
     "ctgcn_rnn_seq_fwd": (C.c_int, [_i32, _p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _f32, _i32, _p, _i64,
                                     _i64, _p, _sz, _p]),
     "ctgcn_set_gru_impl": (C.c_int, [_i32]),
+    "ctgcn_set_fusion": (C.c_int, [_i32]),
     "ctgcn_debug_gru_trace": (C.c_int, [_p]),
     "ctgcn_selftest_umma": (C.c_int, [_p, _p, _p, _p, _p, _p, _sz, _p]),
     "ctgcn_selftest_umma_pair": (C.c_int, [_p, _p, _p, _p, _p, _p, _sz, _p]),
@@ -115,6 +116,11 @@ def set_workspace_cap(nbytes: int) -> None:
     """Bound on the per-core-sums buffer of one CoreDiffusion call (0 = default 8 GiB); larger layers run in row chunks."""
     check(lib.ctgcn_set_workspace_cap(int(nbytes)), "ctgcn_set_workspace_cap")
 
+
+
+def set_fusion(on: bool) -> None:
+    """CoreDiffusion as one launch (default) or as the two-kernel path SpMM → U → GRU."""
+    check(lib.ctgcn_set_fusion(1 if on else 0), "ctgcn_set_fusion")
 
 
 def set_gru_impl(impl: int) -> None:

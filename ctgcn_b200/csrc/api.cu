@@ -12,6 +12,7 @@ namespace ctgcn {
 static thread_local char g_err[1024] = "";
 std::atomic<int64_t> g_launches{0};
 static std::atomic<int> g_gru_impl{CTGCN_IMPL_AUTO};
+static std::atomic<int> g_fusion{0};         // ctgcn_set_fusion: CoreDiffusion as one launch when the shapes allow (off until it beats two launches)
 static constexpr size_t kDefaultChunkCap = (size_t)8 << 30;
 static std::atomic<size_t> g_chunk_cap{kDefaultChunkCap};   // bound on the per-core-sums buffer of a CoreDiffusion call
 
@@ -55,6 +56,13 @@ int launch_gru_tc2(int cg, const float* seq, int64_t srs, int64_t sss, int64_t n
                    const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
                    int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* sc, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t gru_tc2_workspace_bytes(int d_in);
+bool gru_tc2_takes(int d_in, int h);
+// CoreDiffusion in ONE launch (gru_tc2.cu, fused build: the cumulative SpMM runs in gather warps of the GRU kernel)
+size_t core_diffusion_fused_workspace_bytes(int64_t n, int k, int d_in);
+int launch_core_diffusion_fused(const ctgcn_plan* plan, int64_t row0, int64_t rows, const float* x, int64_t ldx, int d_in, int h,
+                                const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w,
+                                const float* ln_b, float eps, float* y, int64_t yrs, const RowScatter* sc, void* ws, size_t ws_bytes,
+                                cudaStream_t st);
 // tcgen05 dense layer (linear_tc.cu); returns 1 when the shape is not supported by it
 int launch_linear_tc(const float* x, int64_t ldx, int64_t n, int64_t d_in, const float* w, const float* b, int64_t d_out,
                      int act, float* y, int64_t ldy, void* ws, cudaStream_t st);
@@ -121,6 +129,11 @@ extern "C" int ctgcn_debug_gru_trace(int64_t* device_buf) {
     return CTGCN_OK;
 }
 
+extern "C" int ctgcn_set_fusion(int on) {
+    g_fusion.store(on ? 1 : 0);
+    return CTGCN_OK;
+}
+
 extern "C" int ctgcn_set_gru_impl(int impl) {
     CTGCN_REQUIRE(impl >= CTGCN_IMPL_AUTO && impl <= CTGCN_IMPL_TC_UNPAIRED, "set_gru_impl: unknown implementation %d", impl);
     g_gru_impl.store(impl);
@@ -168,7 +181,7 @@ static size_t rnn_ws_simt(int cell, int d_in, int h) {
 }
 static size_t gru_ws_tc(int d_in, int h) {   // packed bf16 hi|lo weights + biases (one-CTA kernel) or + bias-fold images (pair kernel)
     const size_t r1 = align_up((size_t)3 * h * (d_in + h) * 2 * sizeof(uint16_t), 256) + 4096;
-    const size_t r2 = (h == 128 && d_in >= 32 && d_in <= 128) ? gru_tc2_workspace_bytes(d_in) : 0;
+    const size_t r2 = gru_tc2_takes(d_in, h) ? gru_tc2_workspace_bytes(d_in) : 0;
     return r1 > r2 ? r1 : r2;
 }
 
@@ -253,6 +266,12 @@ static int64_t cd_chunk_rows(const ctgcn_plan* plan, int d_in) {
     return rows;
 }
 
+// shapes the one-launch CoreDiffusion takes (the launcher has the final say: alignment, row lengths)
+static bool cd_fused_eligible(const ctgcn_plan* plan, int cell, int d_in, int h) {
+    return cell == CTGCN_CELL_GRU && h == 128 && d_in >= 32 && d_in <= 128 && d_in % 32 == 0 && plan->k <= 64 &&
+           plan->n_rows == plan->n_cols;
+}
+
 extern "C" int ctgcn_set_workspace_cap(size_t bytes) {
     g_chunk_cap.store(bytes ? bytes : kDefaultChunkCap);
     return CTGCN_OK;
@@ -262,7 +281,10 @@ extern "C" size_t ctgcn_core_diffusion_rnn_workspace_bytes(const ctgcn_plan* pla
     if (!plan || d_in <= 0 || h <= 0) return 0;
     const size_t r = ctgcn_rnn_workspace_bytes(cell, d_in, h);
     if (!r) return 0;
-    return align_up((size_t)cd_chunk_rows(plan, d_in) * plan->k * d_in * sizeof(float), 256) + r;
+    const size_t two_kernel = align_up((size_t)cd_chunk_rows(plan, d_in) * plan->k * d_in * sizeof(float), 256) + r;
+    const size_t fused = cd_fused_eligible(plan, cell, d_in, h) && cd_chunk_rows(plan, d_in) == plan->n_rows
+                             ? core_diffusion_fused_workspace_bytes(plan->n_rows, plan->k, d_in) : 0;
+    return two_kernel > fused ? two_kernel : fused;
 }
 
 extern "C" size_t ctgcn_core_diffusion_workspace_bytes(const ctgcn_plan* plan, int d_in, int h) {
@@ -281,6 +303,15 @@ static int core_diffusion_impl(const ctgcn_plan* plan, int cell, const float* x,
     if (!workspace || workspace_bytes < need) {
         set_error("core_diffusion_fwd: workspace of %zu bytes, need %zu", workspace_bytes, need);
         return CTGCN_ENOMEM;
+    }
+    {
+        const int impl = g_gru_impl.load();
+        if (g_fusion.load() && (impl == CTGCN_IMPL_AUTO || impl == CTGCN_IMPL_TCGEN05) && cd_fused_eligible(plan, cell, d_in, h) &&
+            cd_chunk_rows(plan, d_in) == plan->n_rows) {
+            int rc = launch_core_diffusion_fused(plan, 0, plan->n_rows, x, ldx, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, y,
+                                                 ldy, sc, workspace, workspace_bytes, (cudaStream_t)stream);
+            if (rc <= 0) return rc;      // done or failed; 1 = not for this path (alignment, hub rows) → two kernels
+        }
     }
     float* u = (float*)workspace;
     const int64_t chunk = cd_chunk_rows(plan, d_in);

@@ -66,6 +66,7 @@ struct ctgcn_plan {
     int64_t nnz_raw_sum = 0;    // Σ_i stored nnz of the K input matrices ("aggregated edges")
     int64_t nnz_coalesced = 0;  // Σ_i nnz after summing duplicates
     int64_t n_oneshot = 0;
+    int64_t max_row_entries = 0;  // longest row of the union CSR (the fused CoreDiffusion kernel and the hub-row split look at it)
     int device = 0;
     int32_t* rowptr = nullptr;  // [n_rows + 1]
     int32_t* col = nullptr;     // [entries]

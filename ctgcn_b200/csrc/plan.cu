@@ -150,6 +150,37 @@ static int bits_for(uint64_t v) {  // number of bits needed to represent values 
     return b;
 }
 
+__global__ void max_row_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, int* __restrict__ out) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int v = r < n_rows ? rowptr[r + 1] - rowptr[r] : 0;
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
+}
+
+// longest row of the finished CSR → p->max_row_entries (synchronises the stream)
+static int measure_rows(ctgcn_plan* p, cudaStream_t st) {
+    p->max_row_entries = 0;
+    if (p->n_rows == 0 || p->entries == 0) return CTGCN_OK;
+    int* d = nullptr;
+    int h = 0;
+    CTGCN_CUDA_OK(cudaMalloc(&d, sizeof(int)));
+    cudaError_t e = cudaMemsetAsync(d, 0, sizeof(int), st);
+    if (e == cudaSuccess) {
+        max_row_kernel<<<(unsigned)((p->n_rows + 255) / 256), 256, 0, st>>>(p->rowptr, p->n_rows, d);
+        e = cudaGetLastError();
+        count_launch();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        set_error("plan: CUDA error while measuring rows: %s", cudaGetErrorString(e));
+        return CTGCN_ECUDA;
+    }
+    p->max_row_entries = h;
+    return CTGCN_OK;
+}
+
 static int alloc_plan_arrays(ctgcn_plan* p) {
     const size_t e = (size_t)(p->entries > 0 ? p->entries : 1);
     // +16 entries of slack so that 128-bit vector loads of col/val/lvl never leave the allocation
@@ -334,6 +365,10 @@ extern "C" int ctgcn_plan_create_coo(int64_t n_rows, int64_t n_cols, int k, cons
     count_launch();
     PLAN_CUDA(cudaStreamSynchronize(st));
 #undef PLAN_CUDA
+    {
+        int rc = measure_rows(p, st);
+        if (rc) return fail(rc);
+    }
     *out = p;
     return CTGCN_OK;
 }
@@ -398,6 +433,13 @@ extern "C" int ctgcn_plan_create_csr(int64_t n_rows, int64_t n_cols, int k, cons
         return CTGCN_EINVAL;
     }
     p->n_oneshot = (int64_t)h_one;
+    {
+        int rc = measure_rows(p, st);
+        if (rc) {
+            ctgcn_plan_destroy(p);
+            return rc;
+        }
+    }
     *out = p;
     return CTGCN_OK;
 }

@@ -102,6 +102,13 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
+// Ampere-style asynchronous copy global → shared memory, 16 bytes per thread, cached at the L2 only (LDGSTS)
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

@@ -134,8 +134,12 @@ int ctgcn_gru_seq_fwd(const float* seq, int64_t seq_row_stride, int64_t seq_step
                       const float* ln_w, const float* ln_b, float eps, int mode, float* y, int64_t y_row_stride,
                       int64_t y_step_stride, void* workspace, size_t workspace_bytes, void* stream);
 int ctgcn_set_gru_impl(int impl);
+/* CoreDiffusion as ONE launch (default on): for 128-wide GRU layers ctgcn_core_diffusion_fwd* run the cumulative SpMM inside the
+ * tensor-core GRU kernel (gather warps fetch the next tile's feature rows with bulk copies while the tensor cores work on the
+ * current tile).  0 = always the two-kernel path (SpMM → U → GRU); used by tests and A/B measurements. */
+int ctgcn_set_fusion(int on);
 /* debug: when non-NULL, block 0 of every following tcgen05 GRU launch writes clock64() stamps of its pipeline events
- * into device_buf[24 events][64 steps] (int64); NULL switches it off. */
+ * into device_buf[32 events][64 steps] (int64); NULL switches it off. */
 int ctgcn_debug_gru_trace(int64_t* device_buf);
 /* test hook: one half-step of a GRU cell's pre-activations for d_in = 64 through the tcgen05 weight packer, chunk images,
  * descriptors, split-bf16 MMAs and TMEM loads of the GRU kernel:

@@ -36,7 +36,7 @@ def main():
     sd.update(cases.norm_params(rng, "norm.", d))
     sd = {k: torch.from_numpy(v).to(dev) for k, v in sd.items()}
     seq = torch.randn(n, args.steps, d, device=dev).abs()
-    buf = torch.zeros(24, 64, dtype=torch.int64, device=dev)
+    buf = torch.zeros(32, 64, dtype=torch.int64, device=dev)
     run = lambda: ops.gru_seq(seq, sd["rnn.weight_ih_l0"], sd["rnn.weight_hh_l0"], sd["rnn.bias_ih_l0"], sd["rnn.bias_hh_l0"],
                               sd["norm.weight"], sd["norm.bias"], 1e-5, args.mode)
     run()

@@ -225,7 +225,8 @@ def test_umma_selftest(lib, cuda_device):
 # ----------------------------------------------------------------------------- GRU kernel alone
 @pytest.mark.parametrize("n,steps,d_in,h,bias", [(300, 5, 128, 128, True), (77, 1, 128, 128, True), (130, 12, 128, 128, False),
                                                  (65, 3, 500, 128, True), (40, 4, 20, 24, True), (257, 7, 64, 32, True),
-                                                 (129, 2, 256, 256, True)])
+                                                 (129, 2, 256, 256, True), (300, 5, 192, 128, True), (129, 2, 260, 128, False),
+                                                 (200, 3, 512, 128, True), (140, 4, 96, 128, True)])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_gru_seq_kernel(n, steps, d_in, h, bias, mode, impl, lib, cuda_device):
     from ctgcn_b200 import ops
