@@ -4,3 +4,5 @@ out=gpurun_out/r02i
 step() { local name=$1 limit=$2; shift 2; local t0=$SECONDS; timeout "$limit" "$@" > "${out}_${name}.log" 2>&1; local rc=$?
   echo "[$name] rc=$rc $((SECONDS - t0))s" | tee -a "${out}_summary.log"; tail -n 14 "${out}_${name}.log" | grep -v Warning | sed "s/^/    /" | tee -a "${out}_summary.log"; }
 step tl_cfg4  200 python profiles/cd_timeline.py --config cfg4
+step sliced   300 python -m pytest tests/test_parity_gpu.py -m gpu -x -q -k "gru_seq_kernel and auto"
+step uci      300 python -m pytest tests/test_parity_gpu.py tests/test_uci_e2e.py -m gpu -x -q -k "auto or uci"
