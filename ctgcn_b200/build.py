@@ -29,8 +29,8 @@ def sources():
 
 def _digest(paths):
     h = hashlib.sha256()
-    for p in sorted(paths):
-        h.update(p.encode())
+    for p in sorted(paths, key=os.path.basename):
+        h.update(os.path.basename(p).encode())      # not the absolute path: the stamp must stay valid when the tree is copied
         with open(p, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(ARCH + CFLAGS).encode())

@@ -88,7 +88,7 @@ struct Lay {   // per-CTA shared-memory map (identical in both CTAs of a pair: t
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static constexpr int THREADS = 32 * (FIRST_WORKER_WARP + NW);
     // setmaxnreg budgets (warps 0-3 | loaders 4-7 | gate warps) out of the 512 × 128 registers the CTA starts with
-    static constexpr int REG_WG0 = FUSED ? 80 : 56, REG_LOAD = FUSED ? 80 : 112, REG_GATE = 168;   // FUSED: warps 2-7 run the gather
+    static constexpr int REG_WG0 = FUSED ? 88 : 56, REG_LOAD = FUSED ? 88 : 112, REG_GATE = 168;   // FUSED: warps 2-7 run the gather
     static_assert(128 * REG_WG0 + 128 * REG_LOAD + 32 * NW * REG_GATE <= THREADS * 128, "register pool");
     // byte offset (from the CTA's shared-memory base) of the hi 16-byte unit holding features f..f+7 (f % 8 == 0) of row m
     static __device__ __forceinline__ uint32_t h_unit(int f, int m) { return SM_H + (f >> 3) * (TILE_M * 16) + m * 16; }
@@ -570,6 +570,7 @@ __global__ void __launch_bounds__(Lay<CG, FUSED>::THREADS, 1) gru2_kernel(const 
             int32_t* rp_s = reinterpret_cast<int32_t*>(smem + LY::SM_ROWPTR) + gw * 24;
             const int d = p.d_in, K = p.steps;
             const bool lane_on = 4 * lane < d;                  // this lane's float4 of a feature row exists
+            const float* const xlane = p.x + 4 * lane;
             const int grp = lane < G_SLOTS ? lane / G_GROUP : -1;   // the group of this lane's slot (lanes ≥ 10 hold no entry)
             const int lrow0 = gw * TILE_M / NUM_GATHER_WARPS, lrow1 = (gw + 1) * TILE_M / NUM_GATHER_WARPS;   // rows of the tile
             for (int tg = 0; tg < my_iters; ++tg) {
@@ -593,13 +594,14 @@ __global__ void __launch_bounds__(Lay<CG, FUSED>::THREADS, 1) gru2_kernel(const 
                     // metadata of (batch, lane < 10): entry E0 + 10·batch + lane — column, weight, and level byte | row << 8.  The
                     // row of an entry (binary search in the warp's ≤ 23 row pointers) is found HERE, ten entries at a time, so that
                     // the serial consume loop below has one compare on its fast path.
-                    int c_nx = 0, m_nx = 0, m_cur = 0;
-                    float w_nx = 0.f, w_cur = 0.f;
-                    auto load_meta = [&](int b) {
+                    // Two batches of metadata are in flight (n2 → nx → cur): the arrays stream from HBM (≈ 2.4 K cycles measured), one
+                    // batch of lead is not enough.  The row search comes BEFORE the loads are issued so that its shared-memory reads
+                    // never share a scoreboard with (and wait for) the global loads.
+                    int c_nx = 0, l_nx = 0, r_nx = 0, m_cur = 0, c_n2 = 0, l_n2 = 0, r_n2 = 0;
+                    float w_nx = 0.f, w_cur = 0.f, w_n2 = 0.f;
+                    auto load_meta = [&](int b) {                   // → n2
                         const int e = E0 + G_SLOTS * b + lane;
                         if (b < nbatch && lane < G_SLOTS && e < E1) {
-                            c_nx = __ldg(p.col + e);
-                            w_nx = __ldg(p.val + e);
                             int lo = 0, hi = nrows - 1;
 #pragma unroll 1
                             while (lo < hi) {               // largest r with rowptr[r] ≤ e (rows without entries are skipped over)
@@ -607,30 +609,40 @@ __global__ void __launch_bounds__(Lay<CG, FUSED>::THREADS, 1) gru2_kernel(const 
                                 if (rp_s[mid] <= e) lo = mid;
                                 else hi = mid - 1;
                             }
-                            m_nx = (int)__ldg(p.lvl + e) | (lo << 8);
+                            r_n2 = lo << 8;
+                            c_n2 = __ldg(p.col + e);
+                            w_n2 = __ldg(p.val + e);
+                            l_n2 = __ldg(p.lvl + e);
                         }
+                    };
+                    auto shift_meta = [&]() {
+                        c_nx = c_n2;
+                        w_nx = w_n2;
+                        l_nx = l_n2;
+                        r_nx = r_n2;
                     };
                     // copy the feature rows of group g of batch b (column indices in *_nx of the group's lanes) into the group's
                     // slots: one cp.async group, possibly empty (the group count per batch stays uniform)
                     auto issue = [&](int b, int g) {
                         const int ebase = E0 + G_SLOTS * b + G_GROUP * g;
-#pragma unroll 1
-                        for (int i2 = 0; i2 < G_GROUP; ++i2) {
-                            const int cj = __shfl_sync(0xffffffffu, c_nx, G_GROUP * g + i2);
+                        int cj[G_GROUP];
+#pragma unroll
+                        for (int i2 = 0; i2 < G_GROUP; ++i2) cj[i2] = __shfl_sync(0xffffffffu, c_nx, G_GROUP * g + i2);
+#pragma unroll
+                        for (int i2 = 0; i2 < G_GROUP; ++i2)
                             if (ebase + i2 < E1 && lane_on)
-                                cp_async16(ring + (G_GROUP * g + i2) * G_SLOT + 16 * lane, p.x + (int64_t)cj * p.ldx + 4 * lane);
-                        }
+                                cp_async16(ring + (G_GROUP * g + i2) * G_SLOT + 16 * lane, xlane + (int64_t)cj[i2] * p.ldx);
                         cp_async_commit();
                         if (grp == g) {
                             w_cur = w_nx;
-                            m_cur = m_nx;
+                            m_cur = l_nx | r_nx;
                         }
                     };
                     float4 P = make_float4(0.f, 0.f, 0.f, 0.f), S = P;
                     int cur = 0, row = 0;
                     uint8_t* urow = img + (size_t)lrow0 * 16;
                     const bool tr = p.trace && blockIdx.x == 0 && gw == 0 && tg < 64;   // trace: where this warp's cycles go
-                    long long t_wait = 0, t_flush = 0, t_issue = 0, t_meta = 0;
+                    long long t_wait = 0, t_flush = 0, t_issue = 0, t_meta = 0, t_pf = 0;
                     // close levels (S += P; U_level = relu(S) → scratch, split into bf16 hi / lo) and rows until the cursor stands
                     // at (trow, tlev); rows in between (without entries) get K zero levels.  The ONE place that stores.
                     auto flush_to = [&](int trow, int tlev) {
@@ -693,10 +705,13 @@ __global__ void __launch_bounds__(Lay<CG, FUSED>::THREADS, 1) gru2_kernel(const 
                         }
                     };
                     load_meta(0);
+                    shift_meta();
+                    load_meta(1);
                     if (nbatch > 0) {
 #pragma unroll 1
                         for (int g = 0; g < G_GROUPS; ++g) issue(0, g);
-                        load_meta(1);
+                        shift_meta();
+                        load_meta(2);
                     }
 #pragma unroll 1
                     for (int b = 0; b < nbatch; ++b) {
@@ -708,54 +723,53 @@ __global__ void __launch_bounds__(Lay<CG, FUSED>::THREADS, 1) gru2_kernel(const 
                             if (tr) t_wait += clock64() - c0;
                             int cnt = E1 - ebase;
                             cnt = cnt > G_GROUP ? G_GROUP : cnt;
-                            // software pipeline over the group's entries: the next entry's weight / metadata / feature slice are
-                            // fetched before the current one is accumulated
-                            float wj = 0.f;
-                            int mj = 0;
-                            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-                            auto fetch = [&](int i2, float& w_o, int& m_o, float4& x_o) {
-                                w_o = __shfl_sync(0xffffffffu, w_cur, G_GROUP * g + i2);
-                                m_o = __shfl_sync(0xffffffffu, m_cur, G_GROUP * g + i2);
-                                if (lane_on) x_o = *reinterpret_cast<const float4*>(ring_p + (G_GROUP * g + i2) * G_SLOT + 16 * lane);
-                            };
-                            if (cnt > 0) fetch(0, wj, mj, xv);
-#pragma unroll 1
-                            for (int i2 = 0; i2 < cnt; ++i2) {  // warp-uniform trip count
-                                float wn = 0.f;
-                                int mn = 0;
-                                float4 xn = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (i2 + 1 < cnt) fetch(i2 + 1, wn, mn, xn);
-                                const int erow = mj >> 8, elev = mj & 127;
-                                if (erow != row || elev != cur) {                          // fast path: same row, same level
-                                    c0 = tr ? clock64() : 0;
-                                    flush_to(erow, elev);
-                                    if (tr) t_flush += clock64() - c0;
+                            // the group's five weights / metadata words / feature slices are fetched up front (independent shuffles
+                            // and shared-memory loads in flight together), then accumulated in order
+                            float wj[G_GROUP];
+                            int mj[G_GROUP];
+                            float4 xv[G_GROUP];
+#pragma unroll
+                            for (int i2 = 0; i2 < G_GROUP; ++i2) {
+                                wj[i2] = __shfl_sync(0xffffffffu, w_cur, G_GROUP * g + i2);
+                                mj[i2] = __shfl_sync(0xffffffffu, m_cur, G_GROUP * g + i2);
+                                xv[i2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (lane_on) xv[i2] = *reinterpret_cast<const float4*>(ring_p + (G_GROUP * g + i2) * G_SLOT + 16 * lane);
+                            }
+#pragma unroll
+                            for (int i2 = 0; i2 < G_GROUP; ++i2) {
+                                if (i2 < cnt) {                     // warp-uniform
+                                    const int erow = mj[i2] >> 8, elev = mj[i2] & 127;
+                                    if (erow != row || elev != cur) {                      // fast path: same row, same level
+                                        c0 = tr ? clock64() : 0;
+                                        flush_to(erow, elev);
+                                        if (tr) t_flush += clock64() - c0;
+                                    }
+                                    if (mj[i2] & 128) {             // one-shot entry (present in A_level only): straight into S
+                                        S.x = fmaf(wj[i2], xv[i2].x, S.x);
+                                        S.y = fmaf(wj[i2], xv[i2].y, S.y);
+                                        S.z = fmaf(wj[i2], xv[i2].z, S.z);
+                                        S.w = fmaf(wj[i2], xv[i2].w, S.w);
+                                    } else {
+                                        P.x = fmaf(wj[i2], xv[i2].x, P.x);
+                                        P.y = fmaf(wj[i2], xv[i2].y, P.y);
+                                        P.z = fmaf(wj[i2], xv[i2].z, P.z);
+                                        P.w = fmaf(wj[i2], xv[i2].w, P.w);
+                                    }
                                 }
-                                if (mj & 128) {                     // one-shot entry (present in A_level only): straight into S
-                                    S.x = fmaf(wj, xv.x, S.x);
-                                    S.y = fmaf(wj, xv.y, S.y);
-                                    S.z = fmaf(wj, xv.z, S.z);
-                                    S.w = fmaf(wj, xv.w, S.w);
-                                } else {
-                                    P.x = fmaf(wj, xv.x, P.x);
-                                    P.y = fmaf(wj, xv.y, P.y);
-                                    P.z = fmaf(wj, xv.z, P.z);
-                                    P.w = fmaf(wj, xv.w, P.w);
-                                }
-                                wj = wn;
-                                mj = mn;
-                                xv = xn;
                             }
                             // the group's slots are free (every lane has read its own 16 bytes): refill them with the same group
                             // of the next batch; past the end an empty group keeps "one group behind" true
                             c0 = tr ? clock64() : 0;
                             if (b + 1 < nbatch) issue(b + 1, g);
                             else cp_async_commit();
-                            pf_step(ebase + G_GROUP);
                             if (tr) t_issue += clock64() - c0;
+                            c0 = tr ? clock64() : 0;
+                            pf_step(ebase + G_GROUP);
+                            if (tr) t_pf += clock64() - c0;
                         }
                         const long long c1 = tr ? clock64() : 0;
-                        load_meta(b + 2);
+                        shift_meta();                           // batch b + 2 (loaded one iteration ago) becomes "next"
+                        load_meta(b + 3);
                         if (tr) t_meta += clock64() - c1;
                     }
                     flush_to(nrows - 1, K);                     // close the last rows (and rows without entries)
@@ -764,6 +778,7 @@ __global__ void __launch_bounds__(Lay<CG, FUSED>::THREADS, 1) gru2_kernel(const 
                         p.trace[28 * 64 + tg] = t_flush;
                         p.trace[29 * 64 + tg] = t_issue;
                         p.trace[30 * 64 + tg] = t_meta;
+                        p.trace[31 * 64 + tg] = t_pf;
                     }
                     cp_async_wait<0>();
                 }

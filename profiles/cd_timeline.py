@@ -32,6 +32,7 @@ def main():
     sd = {k: torch.from_numpy(v).to(dev) for k, v in sd.items()}
     w = (sd["rnn.weight_ih_l0"], sd["rnn.weight_hh_l0"], sd["rnn.bias_ih_l0"], sd["rnn.bias_hh_l0"], sd["norm.weight"], sd["norm.bias"], 1e-5)
     y = torch.empty(n, d, device=dev)
+    _lib.set_fusion(True)
     ops.core_diffusion(plan, x, *w, out=y)
     torch.cuda.synchronize()
     buf = torch.zeros(32, 64, dtype=torch.int64, device=dev)
@@ -46,7 +47,7 @@ def main():
     names = {24: "gather: tile begin", 25: "gather: slot free", 26: "gather: tile done"}
     for e in (24, 25, 26):
         print(f"{names[e]:24s}", " ".join(f"{int(t[e, s] - t0):8d}" if t[e, s] else "       -" for s in range(8)))
-    for e, nm in ((27, "gather w0: cp.async wait"), (28, "gather w0: flush (emit)"), (29, "gather w0: issue+prefetch"), (30, "gather w0: metadata")):
+    for e, nm in ((27, "gather w0: cp.async wait"), (28, "gather w0: flush (emit)"), (29, "gather w0: issue cp.async"), (30, "gather w0: metadata"), (31, "gather w0: L2 prefetch")):
         print(f"{nm:26s}", " ".join(f"{int(t[e, s]):8d}" for s in range(8)), " (cycles per tile)")
     for e, nm in ((0, "mma: step begin"), (3, "mma: h ready"), (7, "mma: last part issued"), (12, "wrk: h published"), (13, "ldr: U buffer free"), (14, "ldr: U staged"), (15, "mma: cycles waiting W")):
         print(f"{nm:24s}", " ".join(f"{int(t[e, s] - (0 if e == 15 else t0)):8d}" if t[e, s] else "       -" for s in range(0, 3 * K, 1))[:400])

@@ -136,6 +136,16 @@ def test_core_diffusion_golden(name, impl, lib, cuda_device):
         y2 = mod(torch.from_numpy(c["x"]).to(cuda_device), adj)     # cached plan, deterministic
     assert torch.equal(y, y2)
     close(y.cpu().numpy(), c["expected"]["y"], f"{name}[{impl}]")
+    if impl == "auto":
+        # the one-launch build (the cumulative SpMM inside the GRU kernel) does the same arithmetic in the same order: bit for
+        # bit the two-kernel result (for shapes it does not take the switch is a no-op)
+        lib.set_fusion(True)
+        try:
+            with torch.no_grad():
+                y3 = mod(torch.from_numpy(c["x"]).to(cuda_device), adj)
+        finally:
+            lib.set_fusion(False)
+        assert torch.equal(y, y3)
 
 
 @pytest.mark.parametrize("name", cases.golden_names("mlp"))
