@@ -641,8 +641,6 @@ __global__ void __launch_bounds__(Lay<CG, FUSED>::THREADS, 1) gru2_kernel(const 
                     float4 P = make_float4(0.f, 0.f, 0.f, 0.f), S = P;
                     int cur = 0, row = 0;
                     uint8_t* urow = img + (size_t)lrow0 * 16;
-                    const bool tr = p.trace && blockIdx.x == 0 && gw == 0 && tg < 64;   // trace: where this warp's cycles go
-                    long long t_wait = 0, t_flush = 0, t_issue = 0, t_meta = 0, t_pf = 0;
                     // close levels (S += P; U_level = relu(S) → scratch, split into bf16 hi / lo) and rows until the cursor stands
                     // at (trow, tlev); rows in between (without entries) get K zero levels.  The ONE place that stores.
                     auto flush_to = [&](int trow, int tlev) {
@@ -675,35 +673,6 @@ __global__ void __launch_bounds__(Lay<CG, FUSED>::THREADS, 1) gru2_kernel(const 
                             cur = 0;
                         }
                     };
-                    // The ring holds 5-10 rows per warp (≈ 23 KB per CTA) — at the ≈ 3 µs a random 512-byte row takes to arrive from
-                    // HBM under load that is 8 GB/s per SM, less than half of what hiding the gather under the GRU needs (measured:
-                    // 320 K cycles per tile against 135 K).  The missing bytes in flight cost neither shared memory nor registers
-                    // when they are L2 prefetches: a second cursor runs PF_DIST entries ahead of the consumer and pulls every
-                    // row's 128-byte lines into the L2 (one warp instruction = 8 rows × 4 lines), so that the cp.async above
-                    // sees L2 latency.
-                    constexpr int PF_DIST = 48;
-                    int pe = E0;                                // next entry to prefetch
-                    auto pf_col = [&](int e) { return e + (lane >> 2) < E1 ? __ldg(p.col + e + (lane >> 2)) : -1; };
-                    auto pf_rows = [&](int cj) {
-                        if (cj >= 0 && (lane & 3) * 32 < d) prefetch_l2(p.x + (int64_t)cj * p.ldx + (lane & 3) * 32);
-                    };
-                    {
-                        int c6[PF_DIST / 8];
-#pragma unroll
-                        for (int q = 0; q < PF_DIST / 8; ++q) c6[q] = pf_col(E0 + 8 * q);
-#pragma unroll
-                        for (int q = 0; q < PF_DIST / 8; ++q) pf_rows(c6[q]);
-                        pe = E0 + PF_DIST;
-                    }
-                    int cpf = pf_col(pe);                       // loaded one call ahead of its use
-                    auto pf_step = [&](int consumed) {          // warp-uniform condition
-                        if (pe < E1 && pe < consumed + PF_DIST) {
-                            const int cj = cpf;
-                            pe += 8;
-                            cpf = pf_col(pe);
-                            pf_rows(cj);
-                        }
-                    };
                     load_meta(0);
                     shift_meta();
                     load_meta(1);
@@ -718,68 +687,52 @@ __global__ void __launch_bounds__(Lay<CG, FUSED>::THREADS, 1) gru2_kernel(const 
 #pragma unroll 1
                         for (int g = 0; g < G_GROUPS; ++g) {
                             const int ebase = E0 + G_SLOTS * b + G_GROUP * g;
-                            long long c0 = tr ? clock64() : 0;
                             cp_async_wait<G_GROUPS - 1>();      // this lane's share of the group has landed
-                            if (tr) t_wait += clock64() - c0;
                             int cnt = E1 - ebase;
                             cnt = cnt > G_GROUP ? G_GROUP : cnt;
-                            // the group's five weights / metadata words / feature slices are fetched up front (independent shuffles
-                            // and shared-memory loads in flight together), then accumulated in order
-                            float wj[G_GROUP];
-                            int mj[G_GROUP];
-                            float4 xv[G_GROUP];
-#pragma unroll
-                            for (int i2 = 0; i2 < G_GROUP; ++i2) {
-                                wj[i2] = __shfl_sync(0xffffffffu, w_cur, G_GROUP * g + i2);
-                                mj[i2] = __shfl_sync(0xffffffffu, m_cur, G_GROUP * g + i2);
-                                xv[i2] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (lane_on) xv[i2] = *reinterpret_cast<const float4*>(ring_p + (G_GROUP * g + i2) * G_SLOT + 16 * lane);
-                            }
-#pragma unroll
-                            for (int i2 = 0; i2 < G_GROUP; ++i2) {
-                                if (i2 < cnt) {                     // warp-uniform
-                                    const int erow = mj[i2] >> 8, elev = mj[i2] & 127;
-                                    if (erow != row || elev != cur) {                      // fast path: same row, same level
-                                        c0 = tr ? clock64() : 0;
-                                        flush_to(erow, elev);
-                                        if (tr) t_flush += clock64() - c0;
-                                    }
-                                    if (mj[i2] & 128) {             // one-shot entry (present in A_level only): straight into S
-                                        S.x = fmaf(wj[i2], xv[i2].x, S.x);
-                                        S.y = fmaf(wj[i2], xv[i2].y, S.y);
-                                        S.z = fmaf(wj[i2], xv[i2].z, S.z);
-                                        S.w = fmaf(wj[i2], xv[i2].w, S.w);
-                                    } else {
-                                        P.x = fmaf(wj[i2], xv[i2].x, P.x);
-                                        P.y = fmaf(wj[i2], xv[i2].y, P.y);
-                                        P.z = fmaf(wj[i2], xv[i2].z, P.z);
-                                        P.w = fmaf(wj[i2], xv[i2].w, P.w);
-                                    }
+                            // software pipeline over the group's entries: the next entry's weight / metadata / feature slice are
+                            // fetched before the current one is accumulated
+                            float wj = 0.f;
+                            int mj = 0;
+                            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+                            auto fetch = [&](int i2, float& w_o, int& m_o, float4& x_o) {
+                                w_o = __shfl_sync(0xffffffffu, w_cur, G_GROUP * g + i2);
+                                m_o = __shfl_sync(0xffffffffu, m_cur, G_GROUP * g + i2);
+                                if (lane_on) x_o = *reinterpret_cast<const float4*>(ring_p + (G_GROUP * g + i2) * G_SLOT + 16 * lane);
+                            };
+                            if (cnt > 0) fetch(0, wj, mj, xv);
+#pragma unroll 1
+                            for (int i2 = 0; i2 < cnt; ++i2) {  // warp-uniform trip count
+                                float wn = 0.f;
+                                int mn = 0;
+                                float4 xn = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (i2 + 1 < cnt) fetch(i2 + 1, wn, mn, xn);
+                                const int erow = mj >> 8, elev = mj & 127;
+                                if (erow != row || elev != cur) flush_to(erow, elev);      // fast path: same row, same level
+                                if (mj & 128) {                     // one-shot entry (present in A_level only): straight into S
+                                    S.x = fmaf(wj, xv.x, S.x);
+                                    S.y = fmaf(wj, xv.y, S.y);
+                                    S.z = fmaf(wj, xv.z, S.z);
+                                    S.w = fmaf(wj, xv.w, S.w);
+                                } else {
+                                    P.x = fmaf(wj, xv.x, P.x);
+                                    P.y = fmaf(wj, xv.y, P.y);
+                                    P.z = fmaf(wj, xv.z, P.z);
+                                    P.w = fmaf(wj, xv.w, P.w);
                                 }
+                                wj = wn;
+                                mj = mn;
+                                xv = xn;
                             }
                             // the group's slots are free (every lane has read its own 16 bytes): refill them with the same group
                             // of the next batch; past the end an empty group keeps "one group behind" true
-                            c0 = tr ? clock64() : 0;
                             if (b + 1 < nbatch) issue(b + 1, g);
                             else cp_async_commit();
-                            if (tr) t_issue += clock64() - c0;
-                            c0 = tr ? clock64() : 0;
-                            pf_step(ebase + G_GROUP);
-                            if (tr) t_pf += clock64() - c0;
                         }
-                        const long long c1 = tr ? clock64() : 0;
                         shift_meta();                           // batch b + 2 (loaded one iteration ago) becomes "next"
                         load_meta(b + 3);
-                        if (tr) t_meta += clock64() - c1;
                     }
                     flush_to(nrows - 1, K);                     // close the last rows (and rows without entries)
-                    if (tr && lane == 0) {
-                        p.trace[27 * 64 + tg] = t_wait;
-                        p.trace[28 * 64 + tg] = t_flush;
-                        p.trace[29 * 64 + tg] = t_issue;
-                        p.trace[30 * 64 + tg] = t_meta;
-                        p.trace[31 * 64 + tg] = t_pf;
-                    }
                     cp_async_wait<0>();
                 }
                 // this warp's rows of the tile are in the scratch slot: hand them to warp 1 (bulk copies read them: async proxy)

@@ -19,6 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="cfg4", choices=["cfg4", "cfg2"])
     ap.add_argument("--gru-impl", default="auto")
+    ap.add_argument("--fused", action="store_true", help="profile the one-launch CoreDiffusion build instead")
     args = ap.parse_args()
     import __graft_entry__
     __graft_entry__.build()
@@ -35,6 +36,14 @@ def main():
     sd = {k: torch.from_numpy(v).to(dev) for k, v in cases.ctgcn_params(np.random.default_rng(0), d, d, d, 1, 1, 1, "C").items()}
     x = synth.features(n, d, 1000).to(dev)
     cd = "duffision_list.0.diffusion_list.0."
+    if args.fused:
+        _lib.set_fusion(True)
+        for it in range(2):
+            y = ops.core_diffusion(plan, x, sd[cd + "rnn.weight_ih_l0"], sd[cd + "rnn.weight_hh_l0"], sd[cd + "rnn.bias_ih_l0"],
+                                   sd[cd + "rnn.bias_hh_l0"], sd[cd + "norm.weight"], sd[cd + "norm.bias"], 1e-5)
+            torch.cuda.synchronize()
+        print("ok fused", tuple(y.shape))
+        return
     for it in range(2):
         h = ops.linear(x, sd["mlp_list.0.linear.weight"], sd["mlp_list.0.linear.bias"], _lib.ACT_NONE)
         u = ops.cumspmm(plan, h)
