@@ -45,6 +45,12 @@ CONFIGS = {
     # the 256-d layers run on the fp32 SIMT sequence kernel and the row-chunked CoreDiffusion (U would be 102 GB per snapshot)
     "cfg5": dict(kind="powerlaw", n=5_000_000, m=50_000_000, K=20, T=16, D=256, levels="loader", min_gpus=2,
                  name="synthetic power-law (Chung-Lu, exponent 2.3) 5M nodes / 50M edges, cores 20..1, T=16 snapshots, 256-d"),
+    # stand-in for BASELINE.json configs[2] (config/facebook.json CTGCN-S, T = 12; the Facebook data is not in the reference
+    # checkout): Facebook's statistics (README.md:173 — 60 730 nodes, 607 487 edges over 27 snapshots, max degree 203, max core 9),
+    # CTGCN-S: dense 'gaussian' degree features [N, 204], MLP 3 layers 'N' 204→500→500→128, one CoreDiffusion layer, loader levels
+    "cfg3": dict(kind="powerlaw", n=60_730, m=22_500, K=9, T=12, D=128, levels="loader", d_feat=204, hid=500, trans_num=3, act="N",
+                 model_type="S",
+                 name="Facebook-like stand-in (power-law 60 730 nodes / 22 500 edges per snapshot, cores 9..1), CTGCN-S, T=12, 128-d"),
     "tiny": dict(kind="er", n=4_000, m=30_000, K=4, T=8, D=128, name="tiny ER smoke workload"),
 }
 
@@ -123,14 +129,16 @@ class CpuReference:
         adj, st = synth_np.make_adj_list(cfg["kind"], n, m, cfg["K"], seed=0, levels=cfg.get("levels", "top"))
         self.setup_s = time.perf_counter() - t0
         self.e_agg = st["edges_aggregated"]
-        x = synth_np.features(n, d, 1000)
-        sd = {k: torch.from_numpy(v) for k, v in cases.ctgcn_params(np.random.default_rng(0), d, d, d, 1, 1, 1, "C").items()}
+        d_feat, hid, tn = cfg.get("d_feat", d), cfg.get("hid", d), cfg.get("trans_num", 1)
+        act, mt = cfg.get("act", "L"), cfg.get("model_type", "C")
+        x = synth_np.features(n, d_feat, 1000)
+        sd = {k: torch.from_numpy(v) for k, v in cases.ctgcn_params(np.random.default_rng(0), d_feat, hid, d, tn, 1, 1, mt).items()}
         rows_t = max(n // T, 1)
         seq = torch.randn(rows_t, T, d, generator=torch.Generator().manual_seed(7))
 
         def run():
             with torch.no_grad():
-                h = oracle_torch.mlp(x, sd, "mlp_list.0.", 1, "L")
+                h = oracle_torch.mlp(x, sd, "mlp_list.0.", tn, act)
                 y = oracle_torch.cdn(h, adj, sd, "duffision_list.0.", 1)
                 o = oracle_torch._gru_all_outputs(seq, sd, "")
                 o = torch.nn.functional.layer_norm(o, (d,), sd["norm.weight"], sd["norm.bias"], 1e-5)
@@ -292,12 +300,14 @@ def main():
     for t in owned:
         snap = synth.make_snapshot(cfg["kind"], n, cfg["m"], K, seed=t, levels=cfg.get("levels", "top"))
         plans[t] = snap.plan(dev)
-        x_host[t] = synth.features(n, d, 1000 + t).pin_memory()
+        x_host[t] = synth.features(n, cfg.get("d_feat", d), 1000 + t).pin_memory()
         x_dev[t] = x_host[t].to(dev)
         stats[t] = dict(k=snap.k, entries=snap.entries, e_agg=snap.edges_aggregated)
         del snap
     torch.manual_seed(0)
-    model = pkg.CTGCN(d, d, d, 1, 1, T, model_type="C", trans_activate_type="L").to(dev).eval()
+    model = pkg.CTGCN(cfg.get("d_feat", d), cfg.get("hid", d), d, cfg.get("trans_num", 1), 1, T, model_type=cfg.get("model_type", "C"),
+                      trans_activate_type=cfg.get("act", "L")).to(dev).eval()
+    emb_only = (lambda r: r[0]) if cfg.get("model_type", "C") == "S" else (lambda r: r)   # 'S' also returns the MLP outputs
     model.snapshot_parallel = world > 1
     model.gather_output = False      # every rank keeps (and, in e2e, reads back) its node slice of the output
     model.exchange = args.exchange
@@ -317,7 +327,7 @@ def main():
 
     def step_resident():
         with torch.no_grad():
-            return model(x_dev, plans)
+            return emb_only(model(x_dev, plans))
 
     out_pinned, e2e_state = {}, {"i": 0}
     d2h_stream = torch.cuda.Stream(device=dev)
@@ -327,7 +337,7 @@ def main():
         # the kernels.  The embeddings are read back on a third stream into double-buffered pinned memory, so that the D2H
         # of step k overlaps the H2D + kernels of step k+1 (PCIe is full duplex); every step still moves all its bytes.
         with torch.no_grad():
-            out = model(x_host, plans)
+            out = emb_only(model(x_host, plans))
         base = out.transpose(0, 1)                      # the contiguous [rows, T, D] tensor behind the returned view
         key = tuple(base.shape)
         if key not in out_pinned:
@@ -388,7 +398,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _, _ = timed(step_e2e, args.steps, 3, finish=finish_e2e)
     launches_total = int(tot(launches))
-    h2d = tot(len(owned) * n * d * 4)          # collectives stay above the rank-0-only reporting below
+    h2d = tot(len(owned) * n * cfg.get("d_feat", d) * 4)          # collectives stay above the rank-0-only reporting below
 
     # ---- correctness guard on the measured configuration: finite output of the right shape
     out = step_resident()
@@ -408,7 +418,7 @@ def main():
             tq = 1                                                  # owned by rank 1
             snap = synth.make_snapshot(cfg["kind"], n, cfg["m"], K, seed=tq, levels=cfg.get("levels", "top"))
             with torch.no_grad():
-                trans = model.mlp_list[tq](synth.features(n, d, 1000 + tq).to(dev))
+                trans = model.mlp_list[tq](synth.features(n, cfg.get("d_feat", d), 1000 + tq).to(dev))
                 emb = model.duffision_list[tq].forward_into(trans, snap.plan(dev))
                 got = model._exchanged[:, tq, :]
                 same = bool(torch.equal(emb[rows[0]:rows[1]], got))
@@ -470,7 +480,9 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["name"], "config": args.config, "parallelism": f"snapshot-parallel x{world}, exchange={args.exchange}",
-                   "layers": f"MLP 1x({d}->{d},'L') + CDN 1 layer + temporal GRU", "edges_aggregated_per_step": e_agg,
+                   "layers": (f"MLP {cfg.get('trans_num', 1)}x({cfg.get('d_feat', d)}->{cfg.get('hid', d) if cfg.get('trans_num', 1) > 1 else d}"
+                              f"->{d},'{cfg.get('act', 'L')}') + CDN 1 layer + temporal GRU, CTGCN-{cfg.get('model_type', 'C')}"),
+                   "edges_aggregated_per_step": e_agg,
                    "union_entries_total": entries_total, "cores_per_snapshot": [s["k"] for s in stats.values()],
                    "l2": "per-step inputs (features + graph plans + per-core sums) exceed the 126 MB L2 several times over; no flush",
                    "gru_impl": args.gru_impl, "host_numa": host_numa, "setup_s": round(setup_s, 1)},
