@@ -66,6 +66,10 @@ int launch_core_diffusion_fused(const ctgcn_plan* plan, int64_t row0, int64_t ro
 // tcgen05 dense layer (linear_tc.cu); returns 1 when the shape is not supported by it
 int launch_linear_tc(const float* x, int64_t ldx, int64_t n, int64_t d_in, const float* w, const float* b, int64_t d_out,
                      int act, float* y, int64_t ldy, void* ws, cudaStream_t st);
+// tcgen05 dense layer for arbitrary widths (linear_gen_tc.cu: both operands streamed); returns 1 when the shape is not supported
+int launch_linear_gen_tc(const float* x, int64_t ldx, int64_t n, int64_t d_in, const float* w, const float* b, int64_t d_out, int act,
+                         float* y, int64_t ldy, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t linear_gen_tc_workspace_bytes(int64_t d_in, int64_t d_out);
 
 }  // namespace ctgcn
 
@@ -384,7 +388,8 @@ extern "C" int ctgcn_core_diffusion_rnn_fwd(const ctgcn_plan* plan, int cell, co
 // ---- MLP layers
 extern "C" size_t ctgcn_linear_workspace_bytes(int64_t d_in, int64_t d_out) {
     if (d_in <= 0 || d_out <= 0) return 0;
-    return align_up((size_t)d_in * d_out * sizeof(float), 256);
+    const size_t a = (size_t)d_in * d_out * sizeof(float), g = linear_gen_tc_workspace_bytes(d_in, d_out);
+    return align_up(a > g ? a : g, 256);
 }
 
 extern "C" int ctgcn_linear_fwd(const float* x, int64_t ldx, int64_t n, int64_t d_in, const float* w, const float* b,
@@ -401,6 +406,7 @@ extern "C" int ctgcn_linear_fwd(const float* x, int64_t ldx, int64_t n, int64_t 
     cudaStream_t st = (cudaStream_t)stream;
     if (g_gru_impl.load() != CTGCN_IMPL_SIMT) {   // the implementation selector covers every tensor-core kernel
         int rc = launch_linear_tc(x, ldx, n, d_in, w, b, d_out, act, y, ldy, workspace, st);
+        if (rc == 1) rc = launch_linear_gen_tc(x, ldx, n, d_in, w, b, d_out, act, y, ldy, workspace, workspace_bytes, st);
         if (rc <= 0) return rc;                   // done or failed; 1 = shape not supported → SIMT kernel
     }
     float* wt = (float*)workspace;

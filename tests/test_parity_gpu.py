@@ -289,9 +289,12 @@ def test_core_diffusion_scatter(name, n_slices, impl, lib, cuda_device):
 
 # ----------------------------------------------------------------------------- dense layer kernels
 @pytest.mark.parametrize("n,d_in,d_out,act,bias", [(1000, 128, 128, "L", True), (77, 64, 128, "N", True), (300, 128, 64, "N", False),
-                                                   (5, 64, 64, "L", True), (40000, 128, 128, "N", True), (129, 100, 128, "L", True)])
+                                                   (5, 64, 64, "L", True), (40000, 128, 128, "N", True), (129, 100, 128, "L", True),
+                                                   (700, 204, 500, "N", True), (300, 500, 500, "N", True), (20000, 500, 128, "N", True),
+                                                   (130, 256, 256, "L", False), (64, 1024, 512, "L", True), (33, 12, 8, "N", True)])
 def test_linear_kernel(n, d_in, d_out, act, bias, impl, lib, cuda_device):
-    """layers.py:97-105 through ctgcn_linear_fwd: tcgen05 path for 64/128-wide layers (impl=auto), SIMT otherwise."""
+    """layers.py:97-105 through ctgcn_linear_fwd: tcgen05 paths (impl=auto: resident weights for 64/128-wide layers, streamed
+    operands for every other width up to 1024 → 512, e.g. the 204→500→500→128 MLP of CTGCN-S), fp32 kernel otherwise."""
     from ctgcn_b200 import ops
     rng = np.random.default_rng(n + d_in)
     sd = cases.linear_params(rng, "", d_in, d_out, bias)
