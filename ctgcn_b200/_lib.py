@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libctgcn_b200.so")
 OK, EINVAL, ECUDA, ENOMEM, ENODEV = 0, -1, -2, -3, -4
 ACT_NONE, ACT_SELU = 0, 1
 GRU_SUM_LN, GRU_EACH_LN = 0, 1
-IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, IMPL_TC_ONE_CTA_R1, IMPL_TC_UNPAIRED = 0, 1, 2, 3, 4
+IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, IMPL_TC_ONE_CTA_R1, IMPL_TC_UNPAIRED, IMPL_TC_WIDE = 0, 1, 2, 3, 4, 5
 CELL_GRU, CELL_LSTM = 0, 1
 CELLS = {"GRU": CELL_GRU, "LSTM": CELL_LSTM}
 MAX_CORES = 64

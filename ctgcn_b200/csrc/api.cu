@@ -56,6 +56,12 @@ int launch_gru_tc2(int cg, const float* seq, int64_t srs, int64_t sss, int64_t n
                    const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
                    int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* sc, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t gru_tc2_workspace_bytes(int d_in);
+// one launch per step, h in global memory / L2 (gru_wide_tc.cu): H = 256, 384, 512 (and 128, as a cross-check of the other kernels)
+int launch_gru_wide_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* w_ih,
+                       const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
+                       int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* sc, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t gru_wide_tc_workspace_bytes(int d_in, int h);
+bool gru_wide_tc_takes(int d_in, int h);
 bool gru_tc2_takes(int d_in, int h);
 // CoreDiffusion in ONE launch (gru_tc2.cu, fused build: the cumulative SpMM runs in gather warps of the GRU kernel)
 size_t core_diffusion_fused_workspace_bytes(int64_t n, int k, int d_in);
@@ -126,10 +132,12 @@ extern "C" int ctgcn_prof_collect(double* ms, int64_t* counts, int reset) {
 namespace ctgcn {
 void set_gru_trace(long long* buf);
 void set_gru2_trace(long long* buf);
+void set_gru_wide_trace(long long* buf);
 }
 extern "C" int ctgcn_debug_gru_trace(int64_t* device_buf) {
     set_gru_trace(reinterpret_cast<long long*>(device_buf));
     set_gru2_trace(reinterpret_cast<long long*>(device_buf));
+    set_gru_wide_trace(reinterpret_cast<long long*>(device_buf));
     return CTGCN_OK;
 }
 
@@ -139,7 +147,7 @@ extern "C" int ctgcn_set_fusion(int on) {
 }
 
 extern "C" int ctgcn_set_gru_impl(int impl) {
-    CTGCN_REQUIRE(impl >= CTGCN_IMPL_AUTO && impl <= CTGCN_IMPL_TC_UNPAIRED, "set_gru_impl: unknown implementation %d", impl);
+    CTGCN_REQUIRE(impl >= CTGCN_IMPL_AUTO && impl <= CTGCN_IMPL_TC_WIDE, "set_gru_impl: unknown implementation %d", impl);
     g_gru_impl.store(impl);
     return CTGCN_OK;
 }
@@ -186,7 +194,11 @@ static size_t rnn_ws_simt(int cell, int d_in, int h) {
 static size_t gru_ws_tc(int d_in, int h) {   // packed bf16 hi|lo weights + biases (one-CTA kernel) or + bias-fold images (pair kernel)
     const size_t r1 = align_up((size_t)3 * h * (d_in + h) * 2 * sizeof(uint16_t), 256) + 4096;
     const size_t r2 = gru_tc2_takes(d_in, h) ? gru_tc2_workspace_bytes(d_in) : 0;
-    return r1 > r2 ? r1 : r2;
+    // the wide kernel is the production path for H > 128 only; its (large, chunk-sized) workspace is not charged to 128-wide layers
+    // unless it has been selected explicitly (CTGCN_IMPL_TC_WIDE, tests)
+    const size_t r3 = (h > 128 || g_gru_impl.load() == CTGCN_IMPL_TC_WIDE) ? gru_wide_tc_workspace_bytes(d_in, h) : 0;
+    const size_t r12 = r1 > r2 ? r1 : r2;
+    return r12 > r3 ? r12 : r3;
 }
 
 extern "C" size_t ctgcn_rnn_workspace_bytes(int cell, int d_in, int h) {
@@ -216,7 +228,10 @@ static int rnn_seq_impl(int cell, const float* seq, int64_t srs, int64_t sss, in
     if (cell == CTGCN_CELL_GRU && impl != CTGCN_IMPL_SIMT) {
         char* tc_ws = (char*)workspace + rnn_ws_simt(cell, d_in, h);
         int rc = 1;
-        if (impl != CTGCN_IMPL_TC_ONE_CTA_R1)
+        if (impl == CTGCN_IMPL_TC_WIDE || ((impl == CTGCN_IMPL_AUTO || impl == CTGCN_IMPL_TCGEN05) && h > 128))
+            rc = launch_gru_wide_tc(seq, srs, sss, n, steps, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, sc,
+                                    tc_ws, gru_ws_tc(d_in, h), st);
+        else if (impl != CTGCN_IMPL_TC_ONE_CTA_R1)
             rc = launch_gru_tc2(impl == CTGCN_IMPL_TC_UNPAIRED ? 1 : 2, seq, srs, sss, n, steps, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w,
                                 ln_b, eps, mode, y, yrs, yss, sc, tc_ws, gru_ws_tc(d_in, h), st);
         if (rc == 1 && (impl == CTGCN_IMPL_TC_ONE_CTA_R1 || impl == CTGCN_IMPL_AUTO || impl == CTGCN_IMPL_TCGEN05))

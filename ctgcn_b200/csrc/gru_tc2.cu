@@ -195,17 +195,6 @@ struct Params2 {
         if (p.trace && blockIdx.x == 0 && (gs) < 64u) p.trace[(e) * 64 + (gs)] = clock64(); \
     } while (0)
 
-__device__ __forceinline__ float ex2_approx(float v) {
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-__device__ __forceinline__ float rcp_approx(float v) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-
 template <int CG>
 __device__ __forceinline__ void umma_cg(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     if constexpr (CG == 2) umma2_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
@@ -227,41 +216,6 @@ template <int CG>
 __device__ __forceinline__ void wait_pair(uint32_t bar, uint32_t parity) {
     if constexpr (CG == 2) mbar_wait_cluster(bar, parity);
     else mbar_wait(bar, parity);
-}
-
-// fp32 gate math of W pre-activation columns (complete: weights and biases, pre-scaled) → h_new.  Written stage by stage over
-// the W features so that the dependent chains (ex2 → rcp → ex2 → rcp) are interleaved.
-// sigmoid(a) = 1/(1 + 2^a'), tanh(s) = 1 − 2/(1 + 2^s'); one reciprocal serves r and z.
-template <int W>
-__device__ __forceinline__ void gate_math(float (&ea)[W], float (&eb)[W], float (&gi)[W], const float (&gh)[W], const float (&hold)[W],
-                                          float (&hn)[W]) {
-    float zz[W];
-#pragma unroll
-    for (int j = 0; j < W; ++j) {
-        ea[j] = ex2_approx(ea[j]);
-        eb[j] = ex2_approx(eb[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < W; ++j) {
-        ea[j] = 1.f + fminf(ea[j], 1e18f);     // clamped so that the product below stays finite
-        eb[j] = 1.f + fminf(eb[j], 1e18f);
-    }
-#pragma unroll
-    for (int j = 0; j < W; ++j) hn[j] = rcp_approx(ea[j] * eb[j]);
-#pragma unroll
-    for (int j = 0; j < W; ++j) {
-        zz[j] = hn[j] * ea[j];                                          // z
-        gi[j] = fmaf(hn[j] * eb[j], gh[j], gi[j]);                      // W_in x + b_in + r ⊙ (W_hn h + b_hn)
-    }
-#pragma unroll
-    for (int j = 0; j < W; ++j) gi[j] = ex2_approx(gi[j]);
-#pragma unroll
-    for (int j = 0; j < W; ++j) gi[j] = rcp_approx(1.f + gi[j]);
-#pragma unroll
-    for (int j = 0; j < W; ++j) {
-        const float nn = fmaf(-2.f, gi[j], 1.f);                        // tanh
-        hn[j] = fmaf(zz[j], hold[j] - nn, nn);                          // (1 − z) n + z h
-    }
 }
 
 // SLICED (d_in > 128, e.g. the 500 → 128 first CoreDiffusion layer of every shipped CTGCN-C config, models.py:228): a 128-row U tile

@@ -1,0 +1,524 @@
+// tcgen05 GRU over a short sequence for WIDE hidden states (H = 128·u, u ≤ 4; d_in ≤ 1024, a multiple of 4): BASELINE.json
+// configs[4] (256-d CoreDiffusion + temporal GRU, layers.py:59-62 / models.py:249-250), which the 128-wide kernels of gru_tc2.cu do
+// not take — their design keeps U, h and both gate accumulator sets of a 128-row tile on the SM, and at H = 256 neither the
+// operands (h alone is 128 KB as bf16 hi|lo planes) nor the accumulators (r, z, n_x, n_h × 256 = 1024 TMEM columns) fit.
+//
+// So the recurrence runs ONE STEP PER LAUNCH with h in global memory, over row chunks small enough that the two h buffers and the
+// Σh buffer of a chunk stay in the 126 MB L2 (148·8 work units per launch; h never goes to DRAM), and a launch is a GEMM with a
+// fused gate epilogue:
+//   work unit = (128-row tile, 128 hidden features j ∈ [128u, 128u+128)); TMEM: r | z | n_x | n_h, 128 columns each (all 512)
+//   for slice s of [x_i | h_{i-1}] (64 columns, fp32 rows → bf16 hi|lo planes by the loader warps):
+//     for gate g ∈ {r, z, n}: D_g += A_s · W_{g,u,s}ᵀ    (4 K-steps × 3 split MMAs, M = 128, N = 128; the n gate of an h slice goes
+//                                                         to its own columns: n = tanh(n_x + b_in + r ⊙ (n_h + b_hn)))
+//   epilogue (8 warps, thread = row, 64 columns each): + biases, ex2/rcp gate math (tc_common.cuh, shared with gru_tc2.cu),
+//     h_i = (1 − z) n + z h_{i-1} → global, Σh accumulated in place.
+// Weights (pre-scaled by −log2e / 2·log2e, packed once per call) stream from the L2 through a 4-stage ring of 32 KB chunks; every
+// unit re-reads its (d_in + H)·384·4 B — the L2 → SM stream (≈ 57 B/cycle/SM at the tensor peak against ≈ 42 available) and the
+// un-overlapped epilogue (TMEM is full) bound this kernel.  Measured at 256 → 256 (profiles/r02_experiments.md): 38.5 K cycles per
+// unit = 24.7 K MMA phase (18.4 K at the tensor peak; 5-6 K of it waiting for weights / slices) + 10.4 K epilogue + 2-3 K hand-over;
+// 272-285 TFLOP/s algorithmic (≈ 0.2 of the dense bf16 peak with 3 MMAs per product), 12× the fp32 kernel.  A fifth stage (biases
+// through the L1 instead of shared memory) changed nothing: the weight stream is bandwidth-, not latency-bound; the next step is
+// the CTA pairing of gru_tc2.cu (each CTA loads half of every chunk).
+// LayerNorm (of Σh, or of every h_i in place for the temporal mode) is a separate row kernel per chunk.
+//   warp 0       weight producer (cp.async.bulk + mbarrier tx)
+//   warp 1       MMA issuer
+//   warps 4-11   loaders (16 rows each)
+//   warps 12-19  gate epilogue
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <stdlib.h>
+
+namespace ctgcn {
+namespace {
+using namespace tc;
+
+constexpr int TILE_M = 128, SLICE_K = 64, UNIT_N = 128, STAGES = 4, MAX_H = 512;
+constexpr int PLANE = TILE_M * SLICE_K * 2;          // 16 KB: one bf16 plane of a 128 × 64 operand block
+constexpr int BLOCK = 2 * PLANE;                     // hi | lo
+constexpr int SM_A = 0;                              // 2 slots
+constexpr int SM_B = SM_A + 2 * BLOCK;               // ring
+constexpr int SM_BIAS = SM_B + STAGES * BLOCK;       // [4][MAX_H] floats: b_r, b_z, b_in, b_hn (pre-scaled)
+constexpr int SM_BAR = SM_BIAS + 4 * MAX_H * 4;
+enum { A_READY = 0, A_FREE = 2, B_FULL = 4, B_EMPTY = 4 + STAGES, ACC_FULL = 4 + 2 * STAGES, ACC_FREE = 5 + 2 * STAGES, NUM_BARS = 6 + 2 * STAGES };
+constexpr int SM_TMEM_PTR = SM_BAR + NUM_BARS * 8;
+constexpr int SMEM_BYTES = SM_TMEM_PTR + 16;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+constexpr int NUM_LOADER_WARPS = 8, NUM_EPI_WARPS = 8, FIRST_LOADER_WARP = 4, FIRST_EPI_WARP = 12, THREADS = 640;
+constexpr int REG_WG0 = 40, REG_LOAD = 64, REG_EPI = 152;      // setmaxnreg budgets out of 640 × 96
+static_assert(128 * REG_WG0 + 256 * REG_LOAD + 256 * REG_EPI <= THREADS * 96, "register pool");
+constexpr int MAX_UNITS_PER_CTA = 8, SM_COUNT_SIZING = 148;    // rows of a chunk: 148·units_per_cta() units (workspace sizing is device-independent)
+
+__host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Packed weights: chunk (u, s, g) at ((u·(nx + nh) + s)·3 + g)·BLOCK, s < nx: W_ih columns [64s, 64s+64) (zero-padded), else W_hh;
+// rows = the 128 features of unit u of gate g ∈ {r, z, n}; element (row, k) of a plane at (k/8)·2048 + row·16 + (k%8)·2.
+// bias4 [4][MAX_H]: (b_ir + b_hr)·(−log2e), (b_iz + b_hz)·(−log2e), b_in·2log2e, b_hn·2log2e.
+__global__ void pack_wide_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b_ih,
+                                 const float* __restrict__ b_hh, int d_in, int h, int nx, int nh, uint8_t* __restrict__ packed,
+                                 float* __restrict__ bias4) {
+    constexpr float kLog2e = 1.4426950408889634f;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 4 * MAX_H) {
+        const int g4 = t / MAX_H, f = t % MAX_H;
+        float bv = 0.f;
+        if (b_ih && f < h) {
+            if (g4 == 0) bv = (b_ih[f] + b_hh[f]) * -kLog2e;
+            else if (g4 == 1) bv = (b_ih[h + f] + b_hh[h + f]) * -kLog2e;
+            else if (g4 == 2) bv = b_ih[2 * h + f] * (2.f * kLog2e);
+            else bv = b_hh[2 * h + f] * (2.f * kLog2e);
+        }
+        bias4[t] = bv;
+    }
+    constexpr int UNITS = UNIT_N * (SLICE_K / 8);     // 16-byte units of one plane of a chunk
+    const int nu = h / UNIT_N, ns = nx + nh;
+    if (t >= nu * ns * 3 * UNITS) return;
+    const int chunk = t / UNITS, unit = t % UNITS;
+    const int g = chunk % 3, s = (chunk / 3) % ns, u = chunk / (3 * ns);
+    const int kb = unit / UNIT_N, row = unit % UNIT_N;
+    const bool is_x = s < nx;
+    const int ktot = is_x ? d_in : h, k0 = (is_x ? s : s - nx) * SLICE_K + kb * 8;
+    const float* src = (is_x ? w_ih : w_hh) + (int64_t)(g * h + u * UNIT_N + row) * ktot + k0;
+    const float scale = g < 2 ? -kLog2e : 2.f * kLog2e;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = k0 + i < ktot ? src[i] * scale : 0.f;
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    uint8_t* dst = packed + (size_t)chunk * BLOCK + kb * (UNIT_N * 16) + row * 16;
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + PLANE) = lo;
+}
+
+struct ParamsW {
+    const float* x;          // step input rows [n, d_in]
+    int64_t ldx;
+    const float* hprev;      // [n, h] or NULL (first step: h = 0)
+    int64_t ldh;
+    float* hnew;             // [n, h] or NULL (last step of the Σ mode)
+    int64_t ldn;
+    float* sum;              // [n, h] running Σh, or NULL
+    int64_t lds;
+    int sum_add;             // 0: store, 1: add
+    int64_t n;
+    int d_in, h, nx, nh, ns_packed, nu;   // nh = 0 at the first step; ns_packed = slices per unit in the packed image
+    const uint8_t* packed;
+    const float* bias4;
+    int num_units;
+    long long* trace;        // optional [32 events][64 units] clock64 stamps of block 0 (ctgcn_debug_gru_trace), else NULL
+};
+
+#define WIDE_TRACE(e, t)                                                                       \
+    do {                                                                                       \
+        if (p.trace && blockIdx.x == 0 && (t) < 64) p.trace[(e) * 64 + (t)] = clock64();       \
+    } while (0)
+#define WIDE_TRACE_ADD(e, t, v)                                                                \
+    do {                                                                                       \
+        if (p.trace && blockIdx.x == 0 && (t) < 64) p.trace[(e) * 64 + (t)] = (v);             \
+    } while (0)
+
+__global__ void __launch_bounds__(THREADS, 1) gru_wide_step_kernel(const ParamsW p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto bar = [&](int i) { return sbase + SM_BAR + 8u * i; };
+    const int my_units = (p.num_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int ns = p.nx + p.nh;
+    if (threadIdx.x == 0) WIDE_TRACE(10, 0);
+
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar(A_READY + b), NUM_LOADER_WARPS);
+            mbar_init(bar(A_FREE + b), 1);
+        }
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar(B_FULL + s), 1);
+            mbar_init(bar(B_EMPTY + s), 1);
+        }
+        mbar_init(bar(ACC_FULL), 1);
+        mbar_init(bar(ACC_FREE), NUM_EPI_WARPS);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < 4 * MAX_H; i += THREADS) reinterpret_cast<float*>(smem + SM_BIAS)[i] = p.bias4[i];
+    if (warp == 1) tmem_alloc(sbase + SM_TMEM_PTR, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM_PTR);
+
+    if (warp < FIRST_LOADER_WARP) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_WG0));
+        if (warp == 0) {
+            // ================================================= weight producer
+            if (lane == 0) {
+                uint32_t stage = 0, phase = 0;
+                for (int t = 0; t < my_units; ++t) {
+                    const int u = ((int)blockIdx.x + t * (int)gridDim.x) % p.nu;
+                    const uint8_t* src = p.packed + (size_t)u * p.ns_packed * 3 * BLOCK;
+                    for (int c = 0; c < ns * 3; ++c) {
+                        mbar_wait(bar(B_EMPTY + stage), phase ^ 1);
+                        mbar_expect_tx(bar(B_FULL + stage), BLOCK);
+                        bulk_g2s(sbase + SM_B + stage * BLOCK, src + (size_t)c * BLOCK, BLOCK, bar(B_FULL + stage));
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // ================================================= MMA issuer
+            constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, UNIT_N);
+            constexpr uint32_t K_STEP = (2 * TILE_M * 16) >> 4, PL = PLANE >> 4;
+            uint32_t stage = 0, phase = 0, use = 0;              // use: running slice counter (slot = use & 1)
+            for (int t = 0; t < my_units; ++t) {
+                mbar_wait(bar(ACC_FREE), (t & 1) ^ 1);
+                tc_fence_after();
+                WIDE_TRACE(0, t);
+                long long wait_a = 0, wait_b = 0;
+                for (int s = 0; s < ns; ++s, ++use) {
+                    long long c0 = p.trace ? clock64() : 0;
+                    mbar_wait(bar(A_READY + (use & 1)), (use >> 1) & 1);
+                    tc_fence_after();
+                    if (p.trace) wait_a += clock64() - c0;
+                    if (s == 0) WIDE_TRACE(1, t);
+                    const uint32_t a0 = desc_lo(sbase + SM_A + (use & 1) * BLOCK, TILE_M * 16);
+                    for (int g = 0; g < 3; ++g) {
+                        c0 = p.trace ? clock64() : 0;
+                        mbar_wait(bar(B_FULL + stage), phase);
+                        tc_fence_after();
+                        if (p.trace) wait_b += clock64() - c0;
+                        if (elect_one()) {
+                            const uint32_t b0 = desc_lo(sbase + SM_B + stage * BLOCK, UNIT_N * 16);
+                            const bool hn = g == 2 && s >= p.nx;                          // recurrent part of the n gate: own columns
+                            const uint32_t d = tmem + (hn ? 3 : g) * UNIT_N;
+                            const bool opens = hn ? s == p.nx : s == 0;
+#pragma unroll
+                            for (int ks = 0; ks < SLICE_K / 16; ++ks) {
+                                const uint64_t ah = desc64(a0 + ks * K_STEP), al = desc64(a0 + PL + ks * K_STEP);
+                                const uint64_t bh = desc64(b0 + ks * K_STEP), bl = desc64(b0 + PL + ks * K_STEP);
+                                umma_bf16(d, al, bh, idesc, (opens && ks == 0) ? 0u : 1u);  // small terms first
+                                umma_bf16(d, ah, bl, idesc, 1u);
+                                umma_bf16(d, ah, bh, idesc, 1u);
+                            }
+                            umma_commit(bar(B_EMPTY + stage));
+                        }
+                        __syncwarp();
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    if (elect_one()) umma_commit(bar(A_FREE + (use & 1)));
+                    __syncwarp();
+                }
+                if (elect_one()) umma_commit(bar(ACC_FULL));
+                __syncwarp();
+                if (lane == 0) {
+                    WIDE_TRACE(2, t);
+                    WIDE_TRACE_ADD(8, t, wait_a);
+                    WIDE_TRACE_ADD(9, t, wait_b);
+                }
+            }
+        }
+    } else if (warp < FIRST_EPI_WARP) {
+        // ===================================================== loaders: 16 tile rows per warp, one 64-column slice at a time
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_LOAD));
+        const int r8 = lane & 7, c4 = lane >> 3;
+        const int row_base = 16 * (warp - FIRST_LOADER_WARP);
+        uint32_t use = 0;
+        for (int t = 0; t < my_units; ++t) {
+            const int64_t tile_row0 = (int64_t)(((int)blockIdx.x + t * (int)gridDim.x) / p.nu) * TILE_M;
+            for (int s = 0; s < ns; ++s, ++use) {
+                const bool is_x = s < p.nx;
+                const float* base = is_x ? p.x : p.hprev;
+                const int64_t ld = is_x ? p.ldx : p.ldh;
+                const int width = is_x ? p.d_in : p.h, col0 = (is_x ? s : s - p.nx) * SLICE_K;
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {                   // (row group of 8, k-group of 4 k-blocks): 2 × 2
+                    const int rg = u & 1, kg = u >> 1;
+                    const int64_t srow = tile_row0 + row_base + 8 * rg + r8;
+                    const int c0 = col0 + (4 * kg + c4) * 8;
+                    const float* src = base + srow * ld + c0;
+                    const bool ok = srow < p.n;
+                    v[2 * u] = ok && c0 + 4 <= width ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[2 * u + 1] = ok && c0 + 8 <= width ? __ldg(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (warp == FIRST_LOADER_WARP && lane == 0 && s == 0) WIDE_TRACE(6, t);
+                mbar_wait(bar(A_FREE + (use & 1)), ((use >> 1) & 1) ^ 1);
+                uint8_t* slot = smem + SM_A + (use & 1) * BLOCK;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int rg = u & 1, kg = u >> 1;
+                    const int m = row_base + 8 * rg + r8, kb = 4 * kg + c4;
+                    const float f8[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w, v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
+                    uint4 hi, lo;
+                    split8(f8, hi, lo);
+                    *reinterpret_cast<uint4*>(slot + kb * (TILE_M * 16) + m * 16) = hi;
+                    *reinterpret_cast<uint4*>(slot + PLANE + kb * (TILE_M * 16) + m * 16) = lo;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(A_READY + (use & 1)));
+                if (warp == FIRST_LOADER_WARP && lane == 0 && s == ns - 1) WIDE_TRACE(7, t);
+            }
+        }
+    } else {
+        // ===================================================== gate epilogue: thread = tile row, 64 of the unit's 128 features per warp
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_EPI));
+        const int q = warp & 3, half = (warp - FIRST_EPI_WARP) >> 2;
+        const int m = 32 * q + lane;
+        const float* bias = reinterpret_cast<const float*>(smem + SM_BIAS);
+        const uint32_t tmem_lane = tmem + ((uint32_t)(32 * q) << 16);
+        for (int t = 0; t < my_units; ++t) {
+            const int v = (int)blockIdx.x + t * (int)gridDim.x;
+            const int u = v % p.nu;
+            const int64_t row = (int64_t)(v / p.nu) * TILE_M + m;
+            const bool ok = row < p.n;
+            const int f0 = u * UNIT_N + 64 * half;              // first hidden feature of this warp's columns
+            const float* hp = p.hprev ? p.hprev + row * p.ldh + f0 : nullptr;
+            float* hn_out = p.hnew ? p.hnew + row * p.ldn + f0 : nullptr;
+            float* sm = p.sum ? p.sum + row * p.lds + f0 : nullptr;
+            // h_{i-1} of this thread's 64 features: fetched while the MMAs of the unit run (a load issued inside the gate loop waits a
+            // full memory round trip under the loaders' traffic — 2-3 K cycles per 8 columns, measured as 30 K cycles per unit)
+            float hold_all[64];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float4 hv = ok && hp ? __ldg(reinterpret_cast<const float4*>(hp + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                hold_all[4 * j] = hv.x;
+                hold_all[4 * j + 1] = hv.y;
+                hold_all[4 * j + 2] = hv.z;
+                hold_all[4 * j + 3] = hv.w;
+            }
+            if (warp == FIRST_EPI_WARP && lane == 0) WIDE_TRACE(3, t);
+            mbar_wait(bar(ACC_FULL), t & 1);
+            tc_fence_after();
+            if (warp == FIRST_EPI_WARP && lane == 0) WIDE_TRACE(4, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = 64 * half + 8 * j;                // column inside the unit
+                float ea[8], eb[8], gi[8], gh[8], hold[8], hn8[8];
+                tmem_ld8(tmem_lane + c, ea);
+                tmem_ld8(tmem_lane + UNIT_N + c, eb);
+                tmem_ld8(tmem_lane + 2 * UNIT_N + c, gi);
+                if (p.nh) tmem_ld8(tmem_lane + 3 * UNIT_N + c, gh);
+                const int f = u * UNIT_N + c;
+                const float4 br0 = *reinterpret_cast<const float4*>(bias + f), br1 = *reinterpret_cast<const float4*>(bias + f + 4);
+                const float4 bz0 = *reinterpret_cast<const float4*>(bias + MAX_H + f), bz1 = *reinterpret_cast<const float4*>(bias + MAX_H + f + 4);
+                const float4 bi0 = *reinterpret_cast<const float4*>(bias + 2 * MAX_H + f), bi1 = *reinterpret_cast<const float4*>(bias + 2 * MAX_H + f + 4);
+                const float4 bh0 = *reinterpret_cast<const float4*>(bias + 3 * MAX_H + f), bh1 = *reinterpret_cast<const float4*>(bias + 3 * MAX_H + f + 4);
+                const float br[8] = {br0.x, br0.y, br0.z, br0.w, br1.x, br1.y, br1.z, br1.w};
+                const float bz[8] = {bz0.x, bz0.y, bz0.z, bz0.w, bz1.x, bz1.y, bz1.z, bz1.w};
+                const float bi[8] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
+                const float bh[8] = {bh0.x, bh0.y, bh0.z, bh0.w, bh1.x, bh1.y, bh1.z, bh1.w};
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    ea[i] += br[i];
+                    eb[i] += bz[i];
+                    gi[i] += bi[i];
+                    gh[i] = p.nh ? gh[i] + bh[i] : bh[i];
+                    hold[i] = hold_all[8 * j + i];
+                }
+                gate_math<8>(ea, eb, gi, gh, hold, hn8);
+                if (ok) {
+                    if (hn_out) {
+                        *reinterpret_cast<float4*>(hn_out + 8 * j) = make_float4(hn8[0], hn8[1], hn8[2], hn8[3]);
+                        *reinterpret_cast<float4*>(hn_out + 8 * j + 4) = make_float4(hn8[4], hn8[5], hn8[6], hn8[7]);
+                    }
+                    if (sm) {                                   // Σh: one writer per element and launch → a reduction without a return value
+                        if (p.sum_add) {
+                            red_add4(sm + 8 * j, hn8[0], hn8[1], hn8[2], hn8[3]);
+                            red_add4(sm + 8 * j + 4, hn8[4], hn8[5], hn8[6], hn8[7]);
+                        } else {
+                            *reinterpret_cast<float4*>(sm + 8 * j) = make_float4(hn8[0], hn8[1], hn8[2], hn8[3]);
+                            *reinterpret_cast<float4*>(sm + 8 * j + 4) = make_float4(hn8[4], hn8[5], hn8[6], hn8[7]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (warp == FIRST_EPI_WARP && lane == 0) WIDE_TRACE(5, t);
+            if (lane == 0) mbar_arrive(bar(ACC_FREE));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) WIDE_TRACE(11, 0);
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// LayerNorm of rows of width h (a multiple of 128, ≤ 512), one warp per row: src row r at src + (r / inner)·srs + (r % inner)·sss,
+// dst likewise (in place allowed) or through the row scatter (Σ mode with a fused snapshot exchange).
+__global__ void __launch_bounds__(256) ln_rows_wide_kernel(const float* src, int64_t srs, int64_t sss, int inner, int64_t rows,
+                                                           int h, const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps,
+                                                           float* dst, int64_t drs, int64_t dss, const RowScatter sc) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int64_t outer = r / inner, in = r % inner;
+    const float* s = src + outer * srs + in * sss;
+    float4 v[MAX_H / 128];
+    const int nv = h / 128;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_H / 128; ++i)
+        if (i < nv) {
+            v[i] = *reinterpret_cast<const float4*>(s + 128 * i + 4 * lane);
+            acc += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const float mean = acc / (float)h;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_H / 128; ++i)
+        if (i < nv) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            var += (a * a + b * b) + (c * c + d * d);
+        }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var / (float)h + eps);
+    float* d = sc.slices ? sc.row_ptr(r) : dst + outer * drs + in * dss;
+#pragma unroll
+    for (int i = 0; i < MAX_H / 128; ++i)
+        if (i < nv) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(ln_w + 128 * i + 4 * lane));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ln_b + 128 * i + 4 * lane));
+            float4 o;
+            o.x = (v[i].x - mean) * rstd * w.x + b.x;
+            o.y = (v[i].y - mean) * rstd * w.y + b.y;
+            o.z = (v[i].z - mean) * rstd * w.z + b.z;
+            o.w = (v[i].w - mean) * rstd * w.w + b.w;
+            float* q = d + 128 * i + 4 * lane;
+            if ((reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+                *reinterpret_cast<float4*>(q) = o;
+            } else {                                             // caller's [n, h] view with an odd row stride
+                q[0] = o.x;
+                q[1] = o.y;
+                q[2] = o.z;
+                q[3] = o.w;
+            }
+        }
+}
+
+// EXPERIMENT KNOB (to be fixed): work units per CTA and launch — small keeps the chunk's h / Σh buffers in the L2, large amortises launches
+int units_per_cta() {
+    static const int v = [] {
+        const char* e = getenv("CTGCN_WIDE_UNITS");
+        const int u = e ? atoi(e) : 4;
+        return u < 1 ? 1 : (u > MAX_UNITS_PER_CTA ? MAX_UNITS_PER_CTA : u);
+    }();
+    return v;
+}
+long long* g_wide_trace = nullptr;
+int64_t chunk_rows_of(int h, int upc) { return (int64_t)SM_COUNT_SIZING * upc * TILE_M / (h / UNIT_N); }
+size_t packed_bytes(int d_in, int h) { return (size_t)(h / UNIT_N) * (ceil_div(d_in, SLICE_K) + h / SLICE_K) * 3 * BLOCK; }
+
+}  // namespace
+
+void set_gru_wide_trace(long long* buf) { g_wide_trace = buf; }
+
+bool gru_wide_tc_takes(int d_in, int h) {
+    return h >= UNIT_N && h <= MAX_H && h % UNIT_N == 0 && d_in >= 8 && d_in <= 1024 && (d_in & 3) == 0;
+}
+// packed weights | bias4 | h ping-pong (2 × chunk × h) | Σh (chunk × h)
+size_t gru_wide_tc_workspace_bytes(int d_in, int h) {
+    if (!gru_wide_tc_takes(d_in, h)) return 0;
+    return align_up(packed_bytes(d_in, h), 256) + 4 * MAX_H * sizeof(float) + 3 * (size_t)chunk_rows_of(h, MAX_UNITS_PER_CTA) * h * sizeof(float);
+}
+
+// returns 0 = done, <0 = error, 1 = shape / alignment not supported by this path
+int launch_gru_wide_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* w_ih,
+                       const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
+                       int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* sc, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!gru_wide_tc_takes(d_in, h)) return 1;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (!al16(seq) || (srs & 3) || (sss & 3) || !al16(ln_w) || !al16(ln_b)) return 1;
+    // temporal mode: the output slots are the h buffers of the recurrence (vector access); Σ mode: only the LayerNorm kernel writes y
+    if (mode == CTGCN_GRU_EACH_LN && (!y || (sc && sc->slices) || !al16(y) || (yrs & 3) || (yss & 3))) return 1;
+    const size_t need = gru_wide_tc_workspace_bytes(d_in, h);
+    CTGCN_REQUIRE(ws && ws_bytes >= need, "gru_wide_tc: workspace of %zu bytes, need %zu", ws_bytes, need);
+
+    const int nx = ceil_div(d_in, SLICE_K), nh = h / SLICE_K, nu = h / UNIT_N;
+    uint8_t* packed = (uint8_t*)ws;
+    float* bias4 = (float*)(packed + align_up(packed_bytes(d_in, h), 256));
+    const int64_t chunk = chunk_rows_of(h, units_per_cta());
+    float* hbuf[2] = {bias4 + 4 * MAX_H, bias4 + 4 * MAX_H + chunk * h};
+    float* sumbuf = hbuf[1] + chunk * h;
+    {
+        ProfScope prof(PROF_PACK, st);
+        int units = nu * (nx + nh) * 3 * UNIT_N * (SLICE_K / 8);
+        if (units < 4 * MAX_H) units = 4 * MAX_H;
+        pack_wide_kernel<<<(units + 255) / 256, 256, 0, st>>>(w_ih, w_hh, b_ih, b_hh, d_in, h, nx, nh, packed, bias4);
+        CTGCN_LAUNCH_OK("pack_wide_kernel");
+    }
+    int dev = 0, sm_count = 0;
+    CTGCN_CUDA_OK(cudaGetDevice(&dev));
+    CTGCN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    CTGCN_CUDA_OK(cudaFuncSetAttribute(gru_wide_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    const bool each = mode == CTGCN_GRU_EACH_LN;
+    ProfScope prof(PROF_GRU, st);
+    for (int64_t row0 = 0; row0 < n; row0 += chunk) {
+        const int64_t rows = n - row0 < chunk ? n - row0 : chunk;
+        ParamsW p;
+        p.n = rows;
+        p.d_in = d_in;
+        p.h = h;
+        p.nx = nx;
+        p.ns_packed = nx + nh;
+        p.nu = nu;
+        p.packed = packed;
+        p.bias4 = bias4;
+        p.num_units = (int)((rows + TILE_M - 1) / TILE_M) * nu;
+        p.trace = g_wide_trace;
+        const int grid = p.num_units < sm_count ? p.num_units : sm_count;
+        for (int i = 0; i < steps; ++i) {
+            p.x = seq + row0 * srs + (int64_t)i * sss;
+            p.ldx = srs;
+            p.nh = i ? nh : 0;
+            if (each) {
+                float* yc = y + row0 * yrs;
+                p.hprev = i ? yc + (int64_t)(i - 1) * yss : nullptr;
+                p.ldh = yrs;
+                p.hnew = yc + (int64_t)i * yss;
+                p.ldn = yrs;
+                p.sum = nullptr;
+                p.lds = 0;
+                p.sum_add = 0;
+            } else {
+                p.hprev = i ? hbuf[(i - 1) & 1] : nullptr;
+                p.ldh = h;
+                p.hnew = i + 1 < steps ? hbuf[i & 1] : nullptr;
+                p.ldn = h;
+                p.sum = sumbuf;
+                p.lds = h;
+                p.sum_add = i ? 1 : 0;
+            }
+            gru_wide_step_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p);
+            CTGCN_LAUNCH_OK("gru_wide_step_kernel");
+        }
+        const int64_t ln_rows = each ? rows * steps : rows;
+        const int blocks = (int)((ln_rows + 7) / 8);
+        if (each) {
+            float* yc = y + row0 * yrs;
+            ln_rows_wide_kernel<<<blocks, 256, 0, st>>>(yc, yrs, yss, steps, ln_rows, h, ln_w, ln_b, eps, yc, yrs, yss, RowScatter());
+        } else {
+            RowScatter s2;
+            if (sc && sc->slices) {
+                s2 = *sc;
+                s2.row_off += row0;
+            }
+            ln_rows_wide_kernel<<<blocks, 256, 0, st>>>(sumbuf, h, 0, 1, ln_rows, h, ln_w, ln_b, eps, y ? y + row0 * yrs : nullptr, yrs, 0, s2);
+        }
+        CTGCN_LAUNCH_OK("ln_rows_wide_kernel");
+    }
+    return CTGCN_OK;
+}
+
+}  // namespace ctgcn

@@ -185,5 +185,52 @@ __device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float (&
 }
 
 
+// ------------------------------------------------------------------------------------------------ GRU gate math
+__device__ __forceinline__ float ex2_approx(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// fp32 gate math of W pre-activation columns (complete: weights and biases, pre-scaled) → h_new.  Written stage by stage over
+// the W features so that the dependent chains (ex2 → rcp → ex2 → rcp) are interleaved.
+// sigmoid(a) = 1/(1 + 2^a'), tanh(s) = 1 − 2/(1 + 2^s'); one reciprocal serves r and z.
+template <int W>
+__device__ __forceinline__ void gate_math(float (&ea)[W], float (&eb)[W], float (&gi)[W], const float (&gh)[W], const float (&hold)[W],
+                                          float (&hn)[W]) {
+    float zz[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        ea[j] = ex2_approx(ea[j]);
+        eb[j] = ex2_approx(eb[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        ea[j] = 1.f + fminf(ea[j], 1e18f);     // clamped so that the product below stays finite
+        eb[j] = 1.f + fminf(eb[j], 1e18f);
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) hn[j] = rcp_approx(ea[j] * eb[j]);
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        zz[j] = hn[j] * ea[j];                                          // z
+        gi[j] = fmaf(hn[j] * eb[j], gh[j], gi[j]);                      // W_in x + b_in + r ⊙ (W_hn h + b_hn)
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) gi[j] = ex2_approx(gi[j]);
+#pragma unroll
+    for (int j = 0; j < W; ++j) gi[j] = rcp_approx(1.f + gi[j]);
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        const float nn = fmaf(-2.f, gi[j], 1.f);                        // tanh
+        hn[j] = fmaf(zz[j], hold[j] - nn, nn);                          // (1 − z) n + z h
+    }
+}
+
 }  // namespace tc
 }  // namespace ctgcn

@@ -45,13 +45,16 @@ extern "C" {
 
 /* implementation selector (ctgcn_set_gru_impl): all are CUDA.  AUTO picks the fastest tensor-core kernel the shapes allow
  * (the CTA-pair kernel of csrc/gru_tc2.cu, else the fp32 sequence kernel); TCGEN05 = AUTO but an error instead of the
- * fp32 kernel when no tensor-core kernel takes the shape.  The last two select one specific tensor-core build (A/B measurements
- * and tests): the one-CTA kernel of round 1 (csrc/gru_tc.cu) and the round-2 kernel built WITHOUT pairing (cta_group::1). */
+ * fp32 kernel when no tensor-core kernel takes the shape.  The last three select one specific tensor-core build (A/B measurements
+ * and tests): the one-CTA kernel of round 1 (csrc/gru_tc.cu), the round-2 kernel built WITHOUT pairing (cta_group::1), and the
+ * step-per-launch kernel for wide hidden states (csrc/gru_wide_tc.cu: what AUTO runs for H = 256 / 384 / 512) on every shape it
+ * takes, H = 128 included.  Workspace queries depend on the selection: set it before asking. */
 #define CTGCN_IMPL_AUTO 0
 #define CTGCN_IMPL_SIMT 1
 #define CTGCN_IMPL_TCGEN05 2
 #define CTGCN_IMPL_TC_ONE_CTA_R1 3
 #define CTGCN_IMPL_TC_UNPAIRED 4
+#define CTGCN_IMPL_TC_WIDE 5
 
 /* recurrent cell of the sequence kernels: the reference's rnn_type (layers.py:26-30, models.py:232-237) */
 #define CTGCN_CELL_GRU 0

@@ -17,6 +17,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--d-in", type=int, default=128)
+    ap.add_argument("--h", type=int, default=128)
+    ap.add_argument("--core-steps", type=int, default=10)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--impls", default="one_cta_r1,unpaired,auto")
     args = ap.parse_args()
@@ -25,19 +27,19 @@ def main():
     from ctgcn_b200 import _lib, ops
     from oracle import cases
     dev = torch.device("cuda:0")
-    n, d, h = args.n, args.d_in, 128
+    n, d, h = args.n, args.d_in, args.h
     rng = np.random.default_rng(0)
     sd = cases.gru_params(rng, "rnn.", d, h)
     sd.update(cases.norm_params(rng, "norm.", h))
     sd = {k: torch.from_numpy(v).to(dev) for k, v in sd.items()}
     w = (sd["rnn.weight_ih_l0"], sd["rnn.weight_hh_l0"], sd["rnn.bias_ih_l0"], sd["rnn.bias_hh_l0"], sd["norm.weight"], sd["norm.bias"], 1e-5)
     codes = {"simt": _lib.IMPL_SIMT, "auto": _lib.IMPL_AUTO, "unpaired": _lib.IMPL_TC_UNPAIRED, "one_cta_r1": _lib.IMPL_TC_ONE_CTA_R1,
-             }
+             "wide": _lib.IMPL_TC_WIDE}
 
     def select(name):
         _lib.set_gru_impl(codes[name])
 
-    for steps, mode, label in ((10, _lib.GRU_SUM_LN, "core GRU  K=10 SUM_LN "), (8, _lib.GRU_EACH_LN, "temporal  T=8  EACH_LN")):
+    for steps, mode, label in ((args.core_steps, _lib.GRU_SUM_LN, f"core GRU  K={args.core_steps} SUM_LN "), (8, _lib.GRU_EACH_LN, "temporal  T=8  EACH_LN")):
         seq = torch.randn(n, steps, d, device=dev).abs_()
         small = seq[:20_000].contiguous()
         _lib.set_gru_impl(_lib.IMPL_SIMT)
@@ -62,7 +64,7 @@ def main():
                                  capture_output=True, text=True).stdout.strip()
             ms = e0.elapsed_time(e1) / args.iters
             same = ""
-            if name != "one_cta_r1":             # the gru_tc2 builds do the same arithmetic in the same order: any difference is a race
+            if name not in ("one_cta_r1", "wide", "simt"):             # the gru_tc2 builds do the same arithmetic in the same order: any difference is a race
                 if first_out is None:
                     first_out = out.clone()
                 else:

@@ -37,10 +37,10 @@ def xin(x, dev):
     return torch.from_numpy(x).to(dev) if isinstance(x, np.ndarray) else oracle_torch.to_torch_coo(x).to(dev)
 
 
-@pytest.fixture(scope="module", params=["simt", "auto", "unpaired", "one_cta_r1"])
+@pytest.fixture(scope="module", params=["simt", "auto", "unpaired", "one_cta_r1", "wide"])
 def impl(request, lib, cuda_device):
     lib.set_gru_impl({"simt": lib.IMPL_SIMT, "auto": lib.IMPL_AUTO, "unpaired": lib.IMPL_TC_UNPAIRED,
-                      "one_cta_r1": lib.IMPL_TC_ONE_CTA_R1}[request.param])
+                      "one_cta_r1": lib.IMPL_TC_ONE_CTA_R1, "wide": lib.IMPL_TC_WIDE}[request.param])
     yield request.param
     lib.set_gru_impl(lib.IMPL_AUTO)
 
@@ -236,10 +236,14 @@ def test_umma_selftest(lib, cuda_device):
 @pytest.mark.parametrize("n,steps,d_in,h,bias", [(300, 5, 128, 128, True), (77, 1, 128, 128, True), (130, 12, 128, 128, False),
                                                  (65, 3, 500, 128, True), (40, 4, 20, 24, True), (257, 7, 64, 32, True),
                                                  (129, 2, 256, 256, True), (300, 5, 192, 128, True), (129, 2, 260, 128, False),
-                                                 (200, 3, 512, 128, True), (140, 4, 96, 128, True)])
+                                                 (200, 3, 512, 128, True), (140, 4, 96, 128, True),
+                                                 (300, 4, 256, 256, True), (150, 3, 128, 256, False), (200, 2, 500, 256, True),
+                                                 (131, 3, 384, 384, True), (140, 2, 512, 512, True), (70, 3, 72, 256, True)])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_gru_seq_kernel(n, steps, d_in, h, bias, mode, impl, lib, cuda_device):
     from ctgcn_b200 import ops
+    if h > 256 and impl not in ("auto", "wide"):
+        pytest.skip("the fp32 sequence kernel keeps both weight matrices in shared memory: H ≤ 256")
     rng = np.random.default_rng(n + steps)
     sd = cases.gru_params(rng, "rnn.", d_in, h, bias)
     sd.update(cases.norm_params(rng, "norm.", h))
