@@ -157,6 +157,50 @@ __global__ void max_row_kernel(const int32_t* __restrict__ rowptr, int64_t n_row
     if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
 }
 
+// Rows above HUB_THRESHOLD entries → segments (see ctgcn_plan in common.cuh).  One-off host pass over the row pointers.
+static int build_hub_split(ctgcn_plan* p, cudaStream_t st) {
+    constexpr int T = ctgcn_plan::HUB_THRESHOLD;
+    if (p->max_row_entries <= T) return CTGCN_OK;
+    std::vector<int32_t> rp((size_t)p->n_rows + 1);
+    CTGCN_CUDA_OK(cudaMemcpyAsync(rp.data(), p->rowptr, rp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CTGCN_CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<int32_t> row_end(rp.begin() + 1, rp.end()), seg_start, seg_end;
+    p->h_hub_rows.clear();
+    p->h_hub_seg_ptr.assign(1, 0);
+    for (int64_t r = 0; r < p->n_rows; ++r) {
+        const int32_t a = rp[r], b = rp[r + 1];
+        if (b - a <= T) continue;
+        row_end[r] = a;
+        for (int32_t s = a; s < b; s += T) {
+            seg_start.push_back(s);
+            seg_end.push_back(s + T < b ? s + T : b);
+        }
+        p->h_hub_rows.push_back((int32_t)r);
+        p->h_hub_seg_ptr.push_back((int32_t)seg_start.size());
+    }
+    const size_t n_seg = seg_start.size(), n_hub = p->h_hub_rows.size();
+    const size_t scratch = n_seg * (size_t)p->k * ctgcn_plan::HUB_DMAX * sizeof(float);
+    if (scratch > ((size_t)1 << 30)) {   // pathological (dense-ish) input: keep the one-warp-per-row pass
+        p->h_hub_rows.clear();
+        p->h_hub_seg_ptr.clear();
+        return CTGCN_OK;
+    }
+    auto up = [&](int32_t** dst, const std::vector<int32_t>& v) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, v.size() * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+        return e;
+    };
+    CTGCN_CUDA_OK(up(&p->row_end, row_end));
+    CTGCN_CUDA_OK(up(&p->seg_start, seg_start));
+    CTGCN_CUDA_OK(up(&p->seg_end, seg_end));
+    CTGCN_CUDA_OK(up(&p->hub_rows, p->h_hub_rows));
+    CTGCN_CUDA_OK(up(&p->hub_seg_ptr, p->h_hub_seg_ptr));
+    CTGCN_CUDA_OK(cudaMalloc(&p->hub_scratch, scratch));
+    CTGCN_CUDA_OK(cudaStreamSynchronize(st));   // the host vectors go away
+    p->bytes += (size_t)p->n_rows * 4 + n_seg * 8 + n_hub * 8 + 4 + scratch;
+    return CTGCN_OK;
+}
+
 // longest row of the finished CSR → p->max_row_entries (synchronises the stream)
 static int measure_rows(ctgcn_plan* p, cudaStream_t st) {
     p->max_row_entries = 0;
@@ -178,7 +222,7 @@ static int measure_rows(ctgcn_plan* p, cudaStream_t st) {
         return CTGCN_ECUDA;
     }
     p->max_row_entries = h;
-    return CTGCN_OK;
+    return build_hub_split(p, st);
 }
 
 static int alloc_plan_arrays(ctgcn_plan* p) {
@@ -453,6 +497,9 @@ extern "C" int ctgcn_plan_destroy(ctgcn_plan* p) {
     if (p->col) cudaFree(p->col);
     if (p->val) cudaFree(p->val);
     if (p->lvl) cudaFree(p->lvl);
+    for (void* q : {(void*)p->row_end, (void*)p->seg_start, (void*)p->seg_end, (void*)p->hub_rows, (void*)p->hub_seg_ptr,
+                    (void*)p->hub_scratch})
+        if (q) cudaFree(q);
     if (cur != p->device) cudaSetDevice(cur);
     delete p;
     return CTGCN_OK;

@@ -11,6 +11,7 @@
 // warp and broadcast with shuffles; per entry one feature row of x (4·D bytes) read with 128-bit loads,
 // UNROLL rows in flight per lane; per (row, level) one coalesced 4·D-byte store.
 #include "common.cuh"
+#include <algorithm>
 
 namespace ctgcn {
 namespace {
@@ -39,14 +40,14 @@ __device__ __forceinline__ void fma4(float4& a, float w, const float4& x) {
 // cfg 4 (2.96 vs 3.16 ms, bit-identical; profiles/r02_experiments.md) — more warps in flight hide the gather latency.
 template <int NV, int UNROLL, bool RELU, int MINB>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB)
-    cumspmm_vec_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+    cumspmm_vec_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rowend, const int32_t* __restrict__ col,
                        const float* __restrict__ val, const uint8_t* __restrict__ lvl, const float* __restrict__ x,
                        int64_t ldx, int d, int k, int64_t n_rows, float* __restrict__ u) {
     const int lane = threadIdx.x & 31;
     const int64_t row = blockIdx.x * (int64_t)WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (row >= n_rows) return;
     const int d4 = d >> 2;
-    const int start = rowptr[row], end = rowptr[row + 1];
+    const int start = rowptr[row], end = rowend[row];   // rowend = rowptr + 1, or the plan's row_end / segment ends (hub rows)
 
     float4 P[NV], S[NV];
 #pragma unroll
@@ -301,20 +302,67 @@ __global__ void transpose_kernel(const float* __restrict__ src, int64_t rows, in
     }
 }
 
+// Hub rows: u[hub row − row0, i, :] = relu?(Σ_segments partial[seg, i, :]), segments added in order.  Block = (hub row, level).
+template <bool RELU>
+__global__ void __launch_bounds__(128) hub_combine_kernel(const float* __restrict__ partial, const int32_t* __restrict__ hub_rows,
+                                                          const int32_t* __restrict__ hub_seg_ptr, int h0, int s0, int64_t row0, int d, int k,
+                                                          float* __restrict__ u) {
+    const int hidx = h0 + blockIdx.x, i = blockIdx.y;
+    const int sa = hub_seg_ptr[hidx] - s0, sb = hub_seg_ptr[hidx + 1] - s0;
+    float* dst = u + ((int64_t)(hub_rows[hidx] - row0) * k + i) * d;
+    for (int f = 4 * threadIdx.x; f < d; f += 4 * blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = sa; s < sb; ++s) {
+            const float4 v = *reinterpret_cast<const float4*>(partial + ((int64_t)s * k + i) * d + f);
+            acc.x += v.x;
+            acc.y += v.y;
+            acc.z += v.z;
+            acc.w += v.w;
+        }
+        if (RELU) {
+            acc.x = fmaxf(acc.x, 0.f);
+            acc.y = fmaxf(acc.y, 0.f);
+            acc.z = fmaxf(acc.z, 0.f);
+            acc.w = fmaxf(acc.w, 0.f);
+        }
+        *reinterpret_cast<float4*>(dst + f) = acc;
+    }
+}
+
+template <int NV, int UNROLL, bool RELU>
+void launch_vec_one(const int32_t* rowptr, const int32_t* rowend, const ctgcn_plan* p, const float* x, int64_t ldx, int d, float* u,
+                    cudaStream_t st, int64_t rows) {
+    const unsigned blocks = (unsigned)((rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    constexpr int MINB = NV == 1 ? 4 : 1;
+    cumspmm_vec_kernel<NV, UNROLL, RELU, MINB><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(rowptr, rowend, p->col, p->val, p->lvl, x, ldx, d,
+                                                                                       p->k, rows, u);
+}
+
 // Row range [row0, row0 + rows): the kernels index rows locally, so the range is selected by shifting the row-pointer array
 // (entry offsets stay absolute) — u is the chunk's own [rows, K, d] buffer.
 template <int NV, int UNROLL>
 int launch_vec(const ctgcn_plan* p, const float* x, int64_t ldx, int d, float* u, bool relu, cudaStream_t st, int64_t row0,
                int64_t rows) {
-    const unsigned blocks = (unsigned)((rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    constexpr int MINB = NV == 1 ? 4 : 1;
-    if (relu)
-        cumspmm_vec_kernel<NV, UNROLL, true, MINB><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p->rowptr + row0, p->col, p->val, p->lvl,
-                                                                                            x, ldx, d, p->k, rows, u);
-    else
-        cumspmm_vec_kernel<NV, UNROLL, false, MINB><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p->rowptr + row0, p->col, p->val, p->lvl,
-                                                                                             x, ldx, d, p->k, rows, u);
+    // hub rows of the range (plan.cu: build_hub_split): emptied in the main pass, then segments → partial sums → combine
+    int h0 = 0, h1 = 0;
+    const bool hubs = p->hub_scratch && d <= ctgcn_plan::HUB_DMAX;
+    if (hubs) {
+        h0 = (int)(std::lower_bound(p->h_hub_rows.begin(), p->h_hub_rows.end(), (int32_t)row0) - p->h_hub_rows.begin());
+        h1 = (int)(std::lower_bound(p->h_hub_rows.begin(), p->h_hub_rows.end(), (int32_t)(row0 + rows)) - p->h_hub_rows.begin());
+    }
+    const int32_t* rowend = hubs ? p->row_end + row0 : p->rowptr + row0 + 1;
+    if (relu) launch_vec_one<NV, UNROLL, true>(p->rowptr + row0, rowend, p, x, ldx, d, u, st, rows);
+    else launch_vec_one<NV, UNROLL, false>(p->rowptr + row0, rowend, p, x, ldx, d, u, st, rows);
     CTGCN_LAUNCH_OK("cumspmm_vec_kernel");
+    if (h1 > h0) {
+        const int s0 = p->h_hub_seg_ptr[h0], s1 = p->h_hub_seg_ptr[h1];
+        launch_vec_one<NV, UNROLL, false>(p->seg_start + s0, p->seg_end + s0, p, x, ldx, d, p->hub_scratch, st, s1 - s0);
+        CTGCN_LAUNCH_OK("cumspmm_vec_kernel (hub segments)");
+        const dim3 grid((unsigned)(h1 - h0), (unsigned)p->k);
+        if (relu) hub_combine_kernel<true><<<grid, 128, 0, st>>>(p->hub_scratch, p->hub_rows, p->hub_seg_ptr, h0, s0, row0, d, p->k, u);
+        else hub_combine_kernel<false><<<grid, 128, 0, st>>>(p->hub_scratch, p->hub_rows, p->hub_seg_ptr, h0, s0, row0, d, p->k, u);
+        CTGCN_LAUNCH_OK("hub_combine_kernel");
+    }
     return CTGCN_OK;
 }
 

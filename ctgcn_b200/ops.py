@@ -63,26 +63,6 @@ def cumspmm(plan: GraphPlan, x: torch.Tensor, relu: bool = True, out: torch.Tens
     return u
 
 
-def cumspmm_hubsplit(plan: GraphPlan, x: torch.Tensor, threshold: int = 4096) -> torch.Tensor:
-    """EXPERIMENTAL (unmeasured): cumspmm with hub rows (> threshold entries) cut into segments that run as rows of their own
-    (GraphPlan.hub_split).  Non-hub rows: the usual pass.  Hub rows: S_i of every segment without the relu, summed over the
-    row's segments in segment order (deterministic), then relu.  Same result as cumspmm up to fp32 summation order."""
-    parts = plan.hub_split(threshold)
-    if parts is None:
-        return cumspmm(plan, x)
-    u = cumspmm(parts["main"], x)                               # hub rows come out as zeros
-    s_seg = cumspmm(parts["hub"], x, relu=False)                # [n_seg, K, D]
-    hub_rows, seg_row, seg_in_row = parts["hub_rows"], parts["seg_row"], parts["seg_in_row"]
-    pos = torch.searchsorted(hub_rows, seg_row)                 # hub index of every segment
-    acc = torch.zeros(hub_rows.numel(), plan.k, x.shape[1], dtype=torch.float32, device=x.device)
-    for j in range(parts["max_segs"]):                          # one segment per hub row and iteration: unique indices
-        sel = torch.nonzero(seg_in_row == j).flatten()
-        if sel.numel():
-            acc[pos[sel]] += s_seg[sel]
-    u[hub_rows] = torch.relu(acc)
-    return u
-
-
 def cumspmm_bwd(plan_t: GraphPlan, g: torch.Tensor) -> torch.Tensor:
     """dL/dx of the cumulative SpMM: g [M, K, D] = dL/dS_i (relu mask applied) → [N, D], over the plan of the transposed list."""
     if g.dim() != 3 or not g.is_cuda or g.dtype != torch.float32:

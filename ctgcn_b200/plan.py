@@ -56,20 +56,6 @@ class GraphPlan:
             self._t._t = self
         return self._t
 
-    def hub_split(self, threshold: int = 4096):
-        """EXPERIMENTAL: (main plan, hub plan, seg_row, seg_in_row, hub_rows, max_segs) of split_hub_rows, or None."""
-        key = ("_hub", threshold)
-        if getattr(self, "_hub_cache", {}).get(key, False) is False:
-            parts = split_hub_rows(self.n_rows, *self.arrays(), threshold)
-            if parts is not None:
-                n_seg = parts["seg_row"].numel()
-                parts = dict(parts, main=build_plan_csr(self.n_rows, self.n_cols, self.k, *parts["main"], self.nnz_raw_sum, self.device),
-                             hub=build_plan_csr(n_seg, self.n_cols, self.k, *parts["hub"], 0, self.device))
-            cache = dict(getattr(self, "_hub_cache", {}))
-            cache[key] = parts
-            self._hub_cache = cache
-        return self._hub_cache[key]
-
     def arrays(self):
         """Copies of (rowptr, col, val, level) as torch tensors (tests / inspection only)."""
         out = [torch.empty(cnt, dtype=dt, device=self.device)
@@ -93,40 +79,6 @@ def transpose_csr(n_rows, n_cols, rowptr, col, val, lvl):
     t_rowptr = torch.zeros(n_cols + 1, dtype=torch.int64, device=rowptr.device)
     t_rowptr[1:] = torch.cumsum(torch.bincount(c64, minlength=n_cols), 0)
     return t_rowptr.to(torch.int32), rows[order].to(torch.int32), val[order], lvl[order]
-
-
-def split_hub_rows(n_rows, rowptr, col, val, lvl, threshold):
-    """EXPERIMENTAL (power-law graphs, BASELINE.json configs[4]): the SpMM gives one warp to one row, so a hub row with 10^5
-    entries is a serial tail.  Rows with more than `threshold` entries are cut into segments of at most `threshold` entries
-    (entries stay in level order, so every segment is itself a valid level-sorted row):
-      main CSR — the original with the hub rows emptied;
-      hub  CSR — one virtual row per segment, plus seg_row[s] = the real row of segment s (segments of a row are consecutive).
-    The cumulative sums are additive over segments BEFORE the relu: S_i(row) = Σ_segments S_i(segment).
-    torch tensors in (any device), torch tensors out; returns None when no row exceeds the threshold."""
-    counts = (rowptr[1:] - rowptr[:-1]).to(torch.int64)
-    hub = torch.nonzero(counts > threshold).flatten()
-    if hub.numel() == 0:
-        return None
-    dev = rowptr.device
-    start = rowptr[:-1].to(torch.int64)
-    is_hub_entry = torch.repeat_interleave(counts > threshold, counts)
-    # main: hub rows emptied
-    keep = ~is_hub_entry
-    main_counts = torch.where(counts > threshold, torch.zeros_like(counts), counts)
-    main_rowptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
-    main_rowptr[1:] = torch.cumsum(main_counts, 0)
-    main = (main_rowptr.to(torch.int32), col[keep], val[keep], lvl[keep])
-    # hub: segments
-    segs_per_row = (counts[hub] + threshold - 1) // threshold
-    seg_row = torch.repeat_interleave(hub, segs_per_row)
-    first_seg = torch.cumsum(segs_per_row, 0) - segs_per_row
-    seg_in_row = torch.arange(seg_row.numel(), device=dev) - torch.repeat_interleave(first_seg, segs_per_row)
-    seg_len = torch.minimum(torch.full_like(seg_in_row, threshold), counts[seg_row] - seg_in_row * threshold)
-    hub_rowptr = torch.zeros(seg_row.numel() + 1, dtype=torch.int64, device=dev)
-    hub_rowptr[1:] = torch.cumsum(seg_len, 0)
-    # entries of hub rows in row order are exactly the concatenation of the segments in seg order
-    hub_csr = (hub_rowptr.to(torch.int32), col[is_hub_entry], val[is_hub_entry], lvl[is_hub_entry])
-    return dict(main=main, hub=hub_csr, seg_row=seg_row, seg_in_row=seg_in_row, hub_rows=hub, max_segs=int(segs_per_row.max()))
 
 
 def _coo_parts(m, device):

@@ -112,41 +112,6 @@ def test_cpu_tensors_fail_loudly(lib):
         mlp(torch.zeros(3, 4))
 
 
-def test_split_hub_rows_is_a_partition(lib):
-    """EXPERIMENTAL hub splitting (plan.split_hub_rows): main CSR + segments of the hub CSR hold every entry exactly once, in
-    level order, with at most `threshold` entries per segment; rows below the threshold are untouched."""
-    import numpy as np
-    from ctgcn_b200.plan import split_hub_rows
-    rng = np.random.default_rng(0)
-    n, k, th = 40, 5, 7
-    counts = rng.integers(0, 6, n)
-    counts[[3, 17, 39]] = [23, 7, 15]                      # 23 → 4 segments, 7 → not a hub (== threshold), 15 → 3 segments
-    rows = np.repeat(np.arange(n), counts)
-    lvl = np.concatenate([np.sort(rng.integers(0, k, c)) for c in counts]).astype(np.uint8)
-    lvl[::5] |= 128
-    col = rng.integers(0, n, rows.shape[0]).astype(np.int32)
-    val = rng.standard_normal(rows.shape[0]).astype(np.float32)
-    rowptr = np.zeros(n + 1, dtype=np.int32)
-    rowptr[1:] = np.cumsum(counts)
-    parts = split_hub_rows(n, torch.from_numpy(rowptr), torch.from_numpy(col), torch.from_numpy(val), torch.from_numpy(lvl), th)
-    assert parts["hub_rows"].tolist() == [3, 39] and parts["max_segs"] == 4
-    m_rowptr, m_col, m_val, m_lvl = [t.numpy() for t in parts["main"]]
-    h_rowptr, h_col, h_val, h_lvl = [t.numpy() for t in parts["hub"]]
-    seg_row, seg_in_row = parts["seg_row"].numpy(), parts["seg_in_row"].numpy()
-    assert seg_row.tolist() == [3] * 4 + [39] * 3 and seg_in_row.tolist() == [0, 1, 2, 3, 0, 1, 2]
-    assert np.diff(h_rowptr).tolist() == [7, 7, 7, 2, 7, 7, 1]
-    assert (np.diff(m_rowptr)[[3, 39]] == 0).all() and np.diff(m_rowptr)[17] == 7
-    for r in range(n):
-        want = list(zip(col[rowptr[r]:rowptr[r + 1]], val[rowptr[r]:rowptr[r + 1]], lvl[rowptr[r]:rowptr[r + 1]]))
-        got = list(zip(m_col[m_rowptr[r]:m_rowptr[r + 1]], m_val[m_rowptr[r]:m_rowptr[r + 1]], m_lvl[m_rowptr[r]:m_rowptr[r + 1]]))
-        for s in np.nonzero(seg_row == r)[0]:
-            seg = list(zip(h_col[h_rowptr[s]:h_rowptr[s + 1]], h_val[h_rowptr[s]:h_rowptr[s + 1]], h_lvl[h_rowptr[s]:h_rowptr[s + 1]]))
-            assert (np.diff([int(e[2]) & 127 for e in seg]) >= 0).all()
-            got += seg
-        assert got == want, r
-    assert split_hub_rows(n, torch.from_numpy(rowptr), torch.from_numpy(col), torch.from_numpy(val), torch.from_numpy(lvl), 100) is None
-
-
 def test_product_never_touches_the_oracle():
     """oracle/ is test infrastructure: nothing under ctgcn_b200/ may import or execute it, and bench.py only in its CPU legs."""
     import re

@@ -123,6 +123,60 @@ def test_cumspmm_against_fp64_oracle(name, lib, cuda_device):
     np.testing.assert_allclose(u.sum(axis=2).T, c["expected"]["u_sum"], rtol=2e-5, atol=2e-4)
 
 
+@pytest.mark.parametrize("d,relu,chunk", [(128, True, None), (256, False, None), (64, True, 4096), (20, True, None), (516, True, None)])
+def test_cumspmm_hub_rows(d, relu, chunk, lib, cuda_device):
+    """Rows above 4096 entries (power-law hubs, BASELINE.json configs[4]) are cut into segments whose per-level partial sums are
+    added up in a second kernel: same sums as the one-warp-per-row pass (fp64 oracle), also through row-chunked launches and
+    for widths that take the scalar kernel (20) or exceed the hub pass (516: plain pass)."""
+    from ctgcn_b200 import ops, plan as P
+    rng = np.random.default_rng(d)
+    n, k = 12000, 4
+    hubs = [3, 7000, 11999]
+    rows, cols, lev = [], [], []
+    for h, deg in zip(hubs, (11000, 4097, 9000)):                 # hub edges spread over the levels
+        nb = rng.choice(np.setdiff1d(np.arange(n), hubs), size=deg, replace=False)
+        rows.append(np.full(deg, h)); cols.append(nb); lev.append(rng.integers(0, k, size=deg))
+    m = 30000                                                     # background edges
+    a, b = rng.integers(0, n, m), rng.integers(0, n, m)
+    keep = (a != b) & ~np.isin(a, hubs) & ~np.isin(b, hubs)
+    rows.append(a[keep]); cols.append(b[keep]); lev.append(rng.integers(0, k, size=int(keep.sum())))
+    r, c, l = np.concatenate(rows), np.concatenate(cols), np.concatenate(lev)
+    key = np.unique(np.minimum(r, c) * n + np.maximum(r, c), return_index=True)[1]
+    r, c, l = r[key], c[key], l[key]
+    mats = []
+    for i in range(k):                                            # nested list: matrix i holds every edge of level ≤ i, symmetric
+        sel = l <= i
+        rr, cc = np.concatenate([r[sel], c[sel]]), np.concatenate([c[sel], r[sel]])
+        if i == 0:
+            rr, cc = np.concatenate([rr, np.arange(n)]), np.concatenate([cc, np.arange(n)])   # + I on the first matrix only
+        mats.append(sp.coo_matrix((np.ones(rr.shape[0], dtype=np.float32), (rr, cc)), shape=(n, n)))
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    plan = P.build_plan_coo(coo(mats, cuda_device), cuda_device)
+    acc, sums = 0, []
+    for a in mats:                                                # layers.py:41-47 in fp64 (oracle_np.cumulative_core_sums applies the relu)
+        acc = acc + sp.csr_matrix(a).astype(np.float64) @ x.astype(np.float64)
+        sums.append(acc)
+    ref = np.stack(sums, axis=1)                                  # [N, K, D]
+    if relu:
+        ref = np.maximum(ref, 0)
+        np.testing.assert_array_equal(ref, oracle_np.cumulative_core_sums(x.astype(np.float64), mats).transpose(1, 0, 2))
+    xd = torch.from_numpy(x).to(cuda_device)
+    if chunk is None:
+        u = ops.cumspmm(plan, xd, relu=relu).cpu().numpy()
+        close(u, ref, f"hub rows d={d}")
+    else:                                                         # row-chunked CoreDiffusion (ctgcn_set_workspace_cap) against the unchunked one
+        import ctgcn_b200 as pkg
+        mod = pkg.CoreDiffusion(d, 128).to(cuda_device)
+        with torch.no_grad():
+            y0 = mod(xd, plan)
+            lib.set_workspace_cap(chunk * k * d * 4)
+            try:
+                y1 = mod(xd, plan)
+            finally:
+                lib.set_workspace_cap(0)
+        assert torch.equal(y0, y1)
+
+
 @pytest.mark.parametrize("name", cases.golden_names("core_diffusion"))
 def test_core_diffusion_golden(name, impl, lib, cuda_device):
     import ctgcn_b200 as pkg
