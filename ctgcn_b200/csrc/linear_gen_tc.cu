@@ -51,7 +51,8 @@ __device__ __forceinline__ void split3_8(const float (&v)[8], uint4& hi, uint4& 
 constexpr int SM_A = 0;                              // 2 slots
 constexpr int SM_B = SM_A + 2 * BLOCK;               // ring
 constexpr int SM_BIAS = SM_B + STAGES * BLOCK;       // 512 floats
-constexpr int SM_BAR = SM_BIAS + 512 * 4;
+constexpr int SM_STAGE = SM_BIAS + 512 * 4;          // epilogue staging: 4 warps × 32 rows × 64 B (see linear_tc.cu)
+constexpr int SM_BAR = SM_STAGE + 4 * 2048;
 enum { A_READY = 0, A_FREE = 2, B_FULL = 4, B_EMPTY = 4 + STAGES, ACC_FULL = 4 + 2 * STAGES, ACC_FREE = 6 + 2 * STAGES, NUM_BARS = 8 + 2 * STAGES };
 constexpr int SM_TMEM_PTR = SM_BAR + NUM_BARS * 8;
 constexpr int SMEM_BYTES = SM_TMEM_PTR + 16;
@@ -226,16 +227,15 @@ __global__ void __launch_bounds__(THREADS, 1) linear_gen_kernel(const ParamsG p)
     } else {
         // ===================================================== epilogue: thread = tile row
         const int q = warp & 3;
-        const int m = 32 * q + lane;
         const float* bias = reinterpret_cast<const float*>(smem + SM_BIAS);
         const uint32_t tmem_lane = tmem + ((uint32_t)(32 * q) << 16);
         for (int t = 0; t < my_tiles; ++t) {
             const int b = nbuf == 2 ? (t & 1) : 0;
             const uint32_t acc_par = nbuf == 2 ? ((t >> 1) & 1) : (t & 1);
-            const int64_t row = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + m;
             mbar_wait(bar(ACC_FULL + b), acc_par);
             tc_fence_after();
-            float* dst = p.y + row * p.ldy;
+            uint8_t* stage = smem + SM_STAGE + q * 2048;
+            const int64_t warp_row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + 32 * q;
             for (int c = 0; c < p.d_out; c += 16) {
                 float v0[8], v1[8];
                 tmem_ld8(tmem_lane + b * 256 + c, v0);
@@ -248,15 +248,24 @@ __global__ void __launch_bounds__(THREADS, 1) linear_gen_kernel(const ParamsG p)
                     o[8 + j] = v1[j] + bias[c + 8 + j];
                 }
                 if (p.act == CTGCN_ACT_SELU) {
-                    const float alpha = 1.6732632423543772848170429916717f, scale = 1.0507009873554804934193349852946f;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = scale * (o[j] > 0.f ? o[j] : alpha * expm1f(o[j]));
+                    for (int j = 0; j < 16; ++j) o[j] = selu_fast(o[j]);
                 }
-                if (row < p.n) {
+                // row-major through the warp's staging tile (XOR-swizzled 16-byte pieces): 8 rows × 64 B per store instruction
+                // instead of 32 rows × 16 B
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        if (c + j < p.d_out) *reinterpret_cast<float4*>(dst + c + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                for (int pc = 0; pc < 4; ++pc)
+                    *reinterpret_cast<float4*>(stage + lane * 64 + ((pc ^ ((lane >> 1) & 3)) << 4)) =
+                        make_float4(o[4 * pc], o[4 * pc + 1], o[4 * pc + 2], o[4 * pc + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = 8 * i + (lane >> 2), pc = lane & 3;
+                    const float4 v = *reinterpret_cast<const float4*>(stage + r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
+                    if (warp_row0 + r < p.n && c + 4 * pc < p.d_out)
+                        *reinterpret_cast<float4*>(p.y + (warp_row0 + r) * p.ldy + c + 4 * pc) = v;
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();

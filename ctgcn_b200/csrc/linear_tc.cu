@@ -21,7 +21,8 @@ constexpr int A_PLANE = TILE_M * MAX_D * 2;   // 32 KB
 constexpr int SM_A = 0;                       // 2 buffers × (hi | lo)
 constexpr int SM_B = SM_A + 4 * A_PLANE;      // weights hi | lo (plane = d_out·d_in·2 ≤ 32 KB)
 constexpr int SM_BIAS = SM_B + 2 * A_PLANE;
-constexpr int SM_BAR = SM_BIAS + MAX_D * 4;
+constexpr int SM_STAGE = SM_BIAS + MAX_D * 4;  // epilogue staging: 4 warps × 32 rows × 64 B (16 output columns at a time)
+constexpr int SM_BAR = SM_STAGE + 4 * 2048;
 constexpr int NUM_BARS = 9;                   // a_ready[2] a_free[2] acc_full[2] acc_free[2] w_full
 constexpr int SM_TMEM_PTR = SM_BAR + NUM_BARS * 8;
 constexpr int SMEM_BYTES = SM_TMEM_PTR + 16;
@@ -175,10 +176,13 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const Params p) {
         const uint32_t tmem_lane = tmem + ((uint32_t)(32 * q) << 16);
         for (int t = 0; t < my_tiles; ++t) {
             const int b = t & 1;
-            const int64_t row = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + m;
             mbar_wait(bar(BAR_ACC_FULL + b), (t >> 1) & 1);
             tc_fence_after();
-            float* dst = p.y + row * p.ldy;
+            // Stores go through a 2 KB staging tile per warp: a thread owns a ROW of the accumulator, so direct stores touch 32
+            // different 128-byte lines per instruction (16 bytes each); re-read row-major, an instruction covers 8 rows × 64 B.
+            // 16-byte pieces are XOR-swizzled by row pair: both the writes (lane = row) and the reads are bank-conflict-free.
+            uint8_t* stage = smem + SM_STAGE + q * 2048;
+            const int64_t warp_row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + 32 * q;
             for (int c = 0; c < p.d_out; c += 16) {
                 float v0[8], v1[8];
                 tmem_ld8(tmem_lane + b * 128 + c, v0);
@@ -191,15 +195,21 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const Params p) {
                     o[8 + j] = v1[j] + bias[c + 8 + j];
                 }
                 if (p.act == CTGCN_ACT_SELU) {
-                    const float alpha = 1.6732632423543772848170429916717f, scale = 1.0507009873554804934193349852946f;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = scale * (o[j] > 0.f ? o[j] : alpha * expm1f(o[j]));
+                    for (int j = 0; j < 16; ++j) o[j] = selu_fast(o[j]);
                 }
-                if (row < p.n) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(dst + c + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                for (int pc = 0; pc < 4; ++pc)
+                    *reinterpret_cast<float4*>(stage + lane * 64 + ((pc ^ ((lane >> 1) & 3)) << 4)) =
+                        make_float4(o[4 * pc], o[4 * pc + 1], o[4 * pc + 2], o[4 * pc + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = 8 * i + (lane >> 2), pc = lane & 3;
+                    const float4 v = *reinterpret_cast<const float4*>(stage + r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
+                    if (warp_row0 + r < p.n) *reinterpret_cast<float4*>(p.y + (warp_row0 + r) * p.ldy + c + 4 * pc) = v;
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
