@@ -75,10 +75,11 @@ struct ctgcn_plan {
     uint8_t* lvl = nullptr;     // [entries]  bits 0..6 level, bit 7 one-shot
     size_t bytes = 0;
     // Hub rows (power-law graphs, BASELINE.json configs[4]): the gather kernel gives one warp to one row, so a row with 10^5
-    // entries would keep one warp busy long after the other rows are done.  Rows above HUB_THRESHOLD entries are cut into
-    // segments of HUB_THRESHOLD entries that run as rows of their own (partial sums per level, no relu) and are then added up
-    // in segment order (deterministic) — see launch_cumspmm.  All NULL / 0 when the plan has no such row.
-    static constexpr int HUB_THRESHOLD = 4096, HUB_DMAX = 512;
+    // entries would keep one warp busy long after the other rows are done.  Rows above hub_threshold entries (512 … : chosen at
+    // plan build, plan.cu) are cut into segments of that many entries that run as rows of their own (partial sums per level, no
+    // relu) and are then added up in segment order (deterministic) — see launch_cumspmm.  All NULL / 0 when the plan has no such row.
+    static constexpr int HUB_THRESHOLD_MIN = 512, HUB_DMAX = 512;
+    int hub_threshold = 0;
     int32_t* row_end = nullptr;   // [n_rows] rowptr[r + 1], but rowptr[r] for hub rows (emptied in the main pass)
     int32_t* seg_start = nullptr; // [n_seg] entry range of every segment
     int32_t* seg_end = nullptr;

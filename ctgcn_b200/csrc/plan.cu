@@ -8,6 +8,8 @@
 // finalisation.  Not on the timed path.
 #include <cub/cub.cuh>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ctgcn {
@@ -157,13 +159,28 @@ __global__ void max_row_kernel(const int32_t* __restrict__ rowptr, int64_t n_row
     if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
 }
 
-// Rows above HUB_THRESHOLD entries → segments (see ctgcn_plan in common.cuh).  One-off host pass over the row pointers.
+// Rows above the hub threshold → segments (see ctgcn_plan in common.cuh).  One-off host pass over the row pointers.
+// Threshold: measured at cfg5s (power-law 1 M / 10 M, 256-d, K = 20) 8192 / 4096 / 2048 / 1024 / 512 entries per segment give
+// 8.70 / 6.07 / 4.79 / 4.04 / 3.75 ms per launch, so the smallest of those whose partial-sum scratch stays below 512 MB is taken.
 static int build_hub_split(ctgcn_plan* p, cudaStream_t st) {
-    constexpr int T = ctgcn_plan::HUB_THRESHOLD;
-    if (p->max_row_entries <= T) return CTGCN_OK;
+    if (p->max_row_entries <= ctgcn_plan::HUB_THRESHOLD_MIN) return CTGCN_OK;
     std::vector<int32_t> rp((size_t)p->n_rows + 1);
     CTGCN_CUDA_OK(cudaMemcpyAsync(rp.data(), p->rowptr, rp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CTGCN_CUDA_OK(cudaStreamSynchronize(st));
+    int T = 0;
+    for (int cand = ctgcn_plan::HUB_THRESHOLD_MIN; cand < p->max_row_entries; cand *= 2) {
+        size_t segs = 0;
+        for (int64_t r = 0; r < p->n_rows; ++r) {
+            const int32_t len = rp[r + 1] - rp[r];
+            if (len > cand) segs += (size_t)(len + cand - 1) / cand;
+        }
+        if (segs * (size_t)p->k * ctgcn_plan::HUB_DMAX * sizeof(float) <= ((size_t)512 << 20)) {
+            T = cand;
+            break;
+        }
+    }
+    if (!T) return CTGCN_OK;   // dense-ish input: keep the one-warp-per-row pass
+    p->hub_threshold = T;
     std::vector<int32_t> row_end(rp.begin() + 1, rp.end()), seg_start, seg_end;
     p->h_hub_rows.clear();
     p->h_hub_seg_ptr.assign(1, 0);
@@ -180,11 +197,6 @@ static int build_hub_split(ctgcn_plan* p, cudaStream_t st) {
     }
     const size_t n_seg = seg_start.size(), n_hub = p->h_hub_rows.size();
     const size_t scratch = n_seg * (size_t)p->k * ctgcn_plan::HUB_DMAX * sizeof(float);
-    if (scratch > ((size_t)1 << 30)) {   // pathological (dense-ish) input: keep the one-warp-per-row pass
-        p->h_hub_rows.clear();
-        p->h_hub_seg_ptr.clear();
-        return CTGCN_OK;
-    }
     auto up = [&](int32_t** dst, const std::vector<int32_t>& v) -> cudaError_t {
         cudaError_t e = cudaMalloc(dst, v.size() * sizeof(int32_t));
         if (e == cudaSuccess) e = cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st);

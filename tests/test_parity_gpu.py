@@ -125,7 +125,7 @@ def test_cumspmm_against_fp64_oracle(name, lib, cuda_device):
 
 @pytest.mark.parametrize("d,relu,chunk", [(128, True, None), (256, False, None), (64, True, 4096), (20, True, None), (516, True, None)])
 def test_cumspmm_hub_rows(d, relu, chunk, lib, cuda_device):
-    """Rows above 4096 entries (power-law hubs, BASELINE.json configs[4]) are cut into segments whose per-level partial sums are
+    """Rows above the hub threshold (512 entries or more; power-law hubs, BASELINE.json configs[4]) are cut into segments whose per-level partial sums are
     added up in a second kernel: same sums as the one-warp-per-row pass (fp64 oracle), also through row-chunked launches and
     for widths that take the scalar kernel (20) or exceed the hub pass (516: plain pass)."""
     from ctgcn_b200 import ops, plan as P
