@@ -32,22 +32,6 @@ constexpr int TILE_M = 128, SLICE_K = 64, NCHUNK = 128, STAGES = 2;
 constexpr int PLANE = TILE_M * SLICE_K * 2;          // 16 KB: one bf16 plane of a 128 × 64 operand block (A slice or B chunk)
 constexpr int BLOCK = 3 * PLANE;                     // hi | mid | lo
 
-// a ≈ hi + mid + lo with bf16 planes (packed pairs): 24 significant bits
-__device__ __forceinline__ void split3_2(float a, float b, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
-    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-    hi = *reinterpret_cast<const uint32_t*>(&h2);
-    const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
-    const __nv_bfloat162 m2 = __floats2bfloat162_rn(ra, rb);
-    mid = *reinterpret_cast<const uint32_t*>(&m2);
-    const __nv_bfloat162 l2 = __floats2bfloat162_rn(ra - __uint_as_float(mid << 16), rb - __uint_as_float(mid & 0xffff0000u));
-    lo = *reinterpret_cast<const uint32_t*>(&l2);
-}
-__device__ __forceinline__ void split3_8(const float (&v)[8], uint4& hi, uint4& mid, uint4& lo) {
-    split3_2(v[0], v[1], hi.x, mid.x, lo.x);
-    split3_2(v[2], v[3], hi.y, mid.y, lo.y);
-    split3_2(v[4], v[5], hi.z, mid.z, lo.z);
-    split3_2(v[6], v[7], hi.w, mid.w, lo.w);
-}
 constexpr int SM_A = 0;                              // 2 slots
 constexpr int SM_B = SM_A + 2 * BLOCK;               // ring
 constexpr int SM_BIAS = SM_B + STAGES * BLOCK;       // 512 floats
@@ -189,36 +173,19 @@ __global__ void __launch_bounds__(THREADS, 1) linear_gen_kernel(const ParamsG p)
         // idle
     } else if (warp < FIRST_EPI_WARP) {
         // ===================================================== loaders: 16 tile rows per warp, one 64-column slice at a time
-        const int r8 = lane & 7, c4 = lane >> 3;
-        const int row_base = 16 * (warp - FIRST_LOADER_WARP);
+        // one 32-row × 32-column block per warp and slice (StageBlock, tc_common.cuh): row group w % 4, column half w / 4
+        const int lw = warp - FIRST_LOADER_WARP, g = lw & 3, half = lw >> 2;
         uint32_t use = 0;
         for (int t = 0; t < my_tiles; ++t) {
-            const int64_t tile_row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M;
+            const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + 32 * g;
+            const int64_t left = p.n - row0;
+            const int rows_ok = left > 32 ? 32 : (int)left;
             for (int s = 0; s < p.nslices; ++s, ++use) {
-                float4 v[8];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {                   // (row group of 8, k-group of 4 k-blocks): 2 × 2
-                    const int rg = u & 1, kg = u >> 1;
-                    const int64_t srow = tile_row0 + row_base + 8 * rg + r8;
-                    const int c0 = s * SLICE_K + (4 * kg + c4) * 8;
-                    const float* src = p.x + srow * p.ldx + c0;
-                    const bool ok = srow < p.n;
-                    v[2 * u] = ok && c0 + 4 <= p.d_in ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    v[2 * u + 1] = ok && c0 + 8 <= p.d_in ? __ldg(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                const int c0 = s * SLICE_K + 32 * half;
+                StageBlock blk;
+                blk.load(p.x + row0 * p.ldx + c0, p.ldx, rows_ok, p.d_in - c0, lane);
                 mbar_wait(bar(A_FREE + (use & 1)), ((use >> 1) & 1) ^ 1);
-                uint8_t* slot = smem + SM_A + (use & 1) * BLOCK;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int rg = u & 1, kg = u >> 1;
-                    const int m = row_base + 8 * rg + r8, kb = 4 * kg + c4;
-                    const float f8[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w, v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
-                    uint4 hi, mid, lo;
-                    split3_8(f8, hi, mid, lo);
-                    *reinterpret_cast<uint4*>(slot + kb * (TILE_M * 16) + m * 16) = hi;
-                    *reinterpret_cast<uint4*>(slot + PLANE + kb * (TILE_M * 16) + m * 16) = mid;
-                    *reinterpret_cast<uint4*>(slot + 2 * PLANE + kb * (TILE_M * 16) + m * 16) = lo;
-                }
+                blk.store<3>(smem + SM_A + (use & 1) * BLOCK + (4 * half) * (TILE_M * 16) + (32 * g) * 16, PLANE, TILE_M * 16, lane);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(A_READY + (use & 1)));
@@ -241,27 +208,30 @@ __global__ void __launch_bounds__(THREADS, 1) linear_gen_kernel(const ParamsG p)
                 tmem_ld8(tmem_lane + b * 256 + c, v0);
                 tmem_ld8(tmem_lane + b * 256 + c + 8, v1);
                 tmem_ld_wait();
-                float o[16];
+                // raw accumulators row-major through the warp's staging tile (XOR-swizzled 16-byte pieces): 8 rows × 64 B per store
+                // instruction instead of 32 rows × 16 B; bias and activation after the read-back (a lane owns 4 fixed columns there)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    o[j] = v0[j] + bias[c + j];
-                    o[8 + j] = v1[j] + bias[c + 8 + j];
+                for (int pc = 0; pc < 4; ++pc) {
+                    const float* o = pc < 2 ? v0 + 4 * pc : v1 + 4 * (pc - 2);
+                    *reinterpret_cast<float4*>(stage + lane * 64 + ((pc ^ ((lane >> 1) & 3)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
                 }
-                if (p.act == CTGCN_ACT_SELU) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = selu_fast(o[j]);
-                }
-                // row-major through the warp's staging tile (XOR-swizzled 16-byte pieces): 8 rows × 64 B per store instruction
-                // instead of 32 rows × 16 B
-#pragma unroll
-                for (int pc = 0; pc < 4; ++pc)
-                    *reinterpret_cast<float4*>(stage + lane * 64 + ((pc ^ ((lane >> 1) & 3)) << 4)) =
-                        make_float4(o[4 * pc], o[4 * pc + 1], o[4 * pc + 2], o[4 * pc + 3]);
                 __syncwarp();
+                const int pc = lane & 3;
+                const float4 b4 = *reinterpret_cast<const float4*>(bias + c + 4 * pc);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int r = 8 * i + (lane >> 2), pc = lane & 3;
-                    const float4 v = *reinterpret_cast<const float4*>(stage + r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
+                    const int r = 8 * i + (lane >> 2);
+                    float4 v = *reinterpret_cast<const float4*>(stage + r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
+                    v.x += b4.x;
+                    v.y += b4.y;
+                    v.z += b4.z;
+                    v.w += b4.w;
+                    if (p.act == CTGCN_ACT_SELU) {
+                        v.x = selu_fast(v.x);
+                        v.y = selu_fast(v.y);
+                        v.z = selu_fast(v.z);
+                        v.w = selu_fast(v.w);
+                    }
                     if (warp_row0 + r < p.n && c + 4 * pc < p.d_out)
                         *reinterpret_cast<float4*>(p.y + (warp_row0 + r) * p.ldy + c + 4 * pc) = v;
                 }

@@ -128,41 +128,32 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const Params p) {
     } else if (warp < FIRST_EPI_WARP) {
         // ===================================================== loaders: 16 tile rows per warp, the whole tile in flight
         asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
-        const int r8 = lane & 7, c4 = lane >> 3;
-        const int row_base = 16 * (warp - FIRST_LOADER_WARP);
-        const int nkg = p.d_in / 32;          // k-groups of 4 k-blocks
-        const int nit = 2 * nkg;              // (row-group of 8, k-group) iterations: 8 for d_in = 128
+        // 32-row × 32-column blocks (StageBlock, tc_common.cuh): warp w takes row group w % 4 and the column spans w / 4, w / 4 + 2
+        const int lw = warp - FIRST_LOADER_WARP, g = lw & 3;
+        const int nspans = p.d_in / 32, per_warp = nspans / 2;      // 2 (d_in = 128) or 1 (d_in = 64)
+        // Software pipeline: the loads of tile t+1 are issued block by block as soon as the block's registers have been stored for
+        // tile t, so a whole tile (64 KB per SM) stays in flight while the previous one is converted.
+        StageBlock blk[2];
+        auto issue = [&](int t, int u) {
+            const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + 32 * g;
+            const int64_t left = p.n - row0;
+            blk[u].load(p.x + row0 * p.ldx + 32 * ((lw >> 2) + 2 * u), p.ldx, left > 32 ? 32 : (int)left, 32, lane);
+        };
+        if (my_tiles > 0) {
+            issue(0, 0);
+            if (per_warp > 1) issue(0, 1);
+        }
         for (int t = 0; t < my_tiles; ++t) {
             const int b = t & 1;
-            const int64_t tile_row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M;
             uint8_t* a_hi = smem + SM_A + b * 2 * A_PLANE;
-            float4 v[16];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int rg = u & 1, kg = u >> 1;
-                const int64_t srow = tile_row0 + row_base + 8 * rg + r8;
-                if (u < nit && srow < p.n) {
-                    const float* src = p.x + srow * p.ldx + (4 * kg + c4) * 8;
-                    v[2 * u] = __ldg(reinterpret_cast<const float4*>(src));
-                    v[2 * u + 1] = __ldg(reinterpret_cast<const float4*>(src + 4));
-                } else {
-                    v[2 * u] = v[2 * u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
             mbar_wait(bar(BAR_A_FREE + b), ((t >> 1) & 1) ^ 1);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (u < nit) {
-                    const int rg = u & 1, kg = u >> 1;
-                    const int m = row_base + 8 * rg + r8, kb = 4 * kg + c4;
-                    const float f8[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w,
-                                         v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
-                    uint4 hi, lo;
-                    split8(f8, hi, lo);
-                    *reinterpret_cast<uint4*>(a_hi + kb * (TILE_M * 16) + m * 16) = hi;
-                    *reinterpret_cast<uint4*>(a_hi + A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
+            for (int u = 0; u < 2; ++u)
+                if (u < per_warp) {
+                    const int sp = (lw >> 2) + 2 * u;
+                    blk[u].store(a_hi + (4 * sp) * (TILE_M * 16) + (32 * g) * 16, A_PLANE, TILE_M * 16, lane);
+                    if (t + 1 < my_tiles) issue(t + 1, u);
                 }
-            }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(BAR_A_READY + b));
@@ -188,25 +179,30 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const Params p) {
                 tmem_ld8(tmem_lane + b * 128 + c, v0);
                 tmem_ld8(tmem_lane + b * 128 + c + 8, v1);
                 tmem_ld_wait();
-                float o[16];
+                // raw accumulators through the staging tile; bias and activation are applied after the transposed read-back, where a
+                // lane owns 4 fixed columns of 4 rows: one 128-bit bias load per lane and column group instead of 16 broadcast loads
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    o[j] = v0[j] + bias[c + j];
-                    o[8 + j] = v1[j] + bias[c + 8 + j];
+                for (int pc = 0; pc < 4; ++pc) {
+                    const float* o = pc < 2 ? v0 + 4 * pc : v1 + 4 * (pc - 2);
+                    *reinterpret_cast<float4*>(stage + lane * 64 + ((pc ^ ((lane >> 1) & 3)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
                 }
-                if (p.act == CTGCN_ACT_SELU) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = selu_fast(o[j]);
-                }
-#pragma unroll
-                for (int pc = 0; pc < 4; ++pc)
-                    *reinterpret_cast<float4*>(stage + lane * 64 + ((pc ^ ((lane >> 1) & 3)) << 4)) =
-                        make_float4(o[4 * pc], o[4 * pc + 1], o[4 * pc + 2], o[4 * pc + 3]);
                 __syncwarp();
+                const int pc = lane & 3;
+                const float4 b4 = *reinterpret_cast<const float4*>(bias + c + 4 * pc);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int r = 8 * i + (lane >> 2), pc = lane & 3;
-                    const float4 v = *reinterpret_cast<const float4*>(stage + r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
+                    const int r = 8 * i + (lane >> 2);
+                    float4 v = *reinterpret_cast<const float4*>(stage + r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
+                    v.x += b4.x;
+                    v.y += b4.y;
+                    v.z += b4.z;
+                    v.w += b4.w;
+                    if (p.act == CTGCN_ACT_SELU) {
+                        v.x = selu_fast(v.x);
+                        v.y = selu_fast(v.y);
+                        v.z = selu_fast(v.z);
+                        v.w = selu_fast(v.w);
+                    }
                     if (warp_row0 + r < p.n) *reinterpret_cast<float4*>(p.y + (warp_row0 + r) * p.ldy + c + 4 * pc) = v;
                 }
                 __syncwarp();

@@ -185,6 +185,95 @@ __device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float (&
 }
 
 
+// a ≈ hi + mid + lo with bf16 planes (packed pairs): 24 significant bits
+__device__ __forceinline__ void split3_2(float a, float b, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 m2 = __floats2bfloat162_rn(ra, rb);
+    mid = *reinterpret_cast<const uint32_t*>(&m2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(ra - __uint_as_float(mid << 16), rb - __uint_as_float(mid & 0xffff0000u));
+    lo = *reinterpret_cast<const uint32_t*>(&l2);
+}
+__device__ __forceinline__ void split3_8(const float (&v)[8], uint4& hi, uint4& mid, uint4& lo) {
+    split3_2(v[0], v[1], hi.x, mid.x, lo.x);
+    split3_2(v[2], v[3], hi.y, mid.y, lo.y);
+    split3_2(v[4], v[5], hi.z, mid.z, lo.z);
+    split3_2(v[6], v[7], hi.w, mid.w, lo.w);
+}
+
+// ------------------------------------------------------------------------------------------------ operand staging (loader warps)
+// One warp turns a block of 32 rows × 32 fp32 columns of a row-major matrix into the bf16 hi | lo operand image
+// (unit (row, kb) of 8 consecutive k = 16 bytes at kb·(rows·16) + row·16 of a plane).
+// Why not "lane = (row, 8 columns)": a 128-bit load / store is processed per QUARTER-warp, and every distinct line a quarter touches
+// is a wavefront of the L1 data pipe — that mapping reads 8 rows per quarter = 32 wavefronts per instruction, and ncu showed the
+// LSU data pipe (l1tex__data_pipe_lsu_wavefronts) at 84 % in linear_tc_kernel (56 % with this mapping).  Used by the dense-layer
+// kernels only: in the GRU kernels the LSU pipe is not what binds (48 % in gru2_kernel) and the extra shuffles / selects sit on the
+// loaders' critical path — gru2_kernel measured 4.6 → 5.1 ms with this block and with a lighter 8-row variant (r02_experiments.md).
+// Here a quarter reads 128 contiguous bytes of ONE row (2 wavefronts):
+//   load (b, i), b < 4, i < 2: quarter q = lane/8 reads row 8q + 2b + i, lane piece p = lane%8 → columns 4p … 4p+3;
+//   lane pairs swap halves (4 shuffles per b): the even lane now owns unit (row 8q + 2b, kb = p/2), the odd one (row 8q + 2b + 1, kb);
+//   the four units of a lane are rotated by kb (two select stages) so that store j writes row 8q + 2·((j + kb) mod 4) + parity:
+//   a quarter's 8 lanes hit 8 different rows mod 8 = all 32 banks once (conflict-free 128-bit stores).
+struct StageBlock {
+    float4 a[4][2];
+    // src: first element of the block (row 0, column 0); rows_ok: rows of the block that exist (≤ 0: none); cols_ok: columns that exist
+    __device__ __forceinline__ void load(const float* __restrict__ src, int64_t ld, int rows_ok, int cols_ok, int lane) {
+        const int q = lane >> 3, p = lane & 7;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int row = 8 * q + 2 * b + i;
+                a[b][i] = (row < rows_ok && 4 * p + 4 <= cols_ok) ? __ldg(reinterpret_cast<const float4*>(src + (int64_t)row * ld + 4 * p))
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+    }
+    // planes: hi plane base of the block's row 0 / k-block 0 (byte pointer); next plane at +plane_bytes; kb_stride = rows_of_operand·16
+    // PLANES = 2: hi | lo (16 significant bits), 3: hi | mid | lo (24)
+    template <int PLANES = 2>
+    __device__ __forceinline__ void store(uint8_t* hi_base, uint32_t plane_bytes, uint32_t kb_stride, int lane) const {
+        const int q = lane >> 3, m = (lane & 7) >> 1, par = lane & 1;
+        float v[4][8];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const float4 send = par ? a[b][0] : a[b][1];
+            float4 recv;
+            recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+            recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+            recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1);
+            recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+            const float4 lo4 = par ? recv : a[b][0], hi4 = par ? a[b][1] : recv;   // columns 8kb … 8kb+3 | 8kb+4 … 8kb+7 of the lane's row
+            v[b][0] = lo4.x; v[b][1] = lo4.y; v[b][2] = lo4.z; v[b][3] = lo4.w;
+            v[b][4] = hi4.x; v[b][5] = hi4.y; v[b][6] = hi4.z; v[b][7] = hi4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float w[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float r1a = (m & 1) ? v[(j + 1) & 3][e] : v[j][e];
+                const float r1b = (m & 1) ? v[(j + 3) & 3][e] : v[(j + 2) & 3][e];
+                w[e] = (m & 2) ? r1b : r1a;                                  // = v[(j + m) & 3][e]
+            }
+            const int row = 8 * q + 2 * ((j + m) & 3) + par;
+            uint8_t* dst = hi_base + (uint32_t)m * kb_stride + row * 16;
+            if constexpr (PLANES == 2) {
+                uint4 hi, lo;
+                split8(w, hi, lo);
+                *reinterpret_cast<uint4*>(dst) = hi;
+                *reinterpret_cast<uint4*>(dst + plane_bytes) = lo;
+            } else {
+                uint4 hi, mid, lo;
+                split3_8(w, hi, mid, lo);
+                *reinterpret_cast<uint4*>(dst) = hi;
+                *reinterpret_cast<uint4*>(dst + plane_bytes) = mid;
+                *reinterpret_cast<uint4*>(dst + 2 * plane_bytes) = lo;
+            }
+        }
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ GRU gate math
 __device__ __forceinline__ float ex2_approx(float v) {
     float r;
