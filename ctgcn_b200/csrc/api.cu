@@ -57,7 +57,7 @@ int launch_gru_tc2(int cg, const float* seq, int64_t srs, int64_t sss, int64_t n
                    int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* sc, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t gru_tc2_workspace_bytes(int d_in);
 // one launch per step, h in global memory / L2 (gru_wide_tc.cu): H = 256, 384, 512 (and 128, as a cross-check of the other kernels)
-int launch_gru_wide_tc(const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* w_ih,
+int launch_gru_wide_tc(int cg, const float* seq, int64_t srs, int64_t sss, int64_t n, int steps, int d_in, int h, const float* w_ih,
                        const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_w, const float* ln_b, float eps,
                        int mode, float* y, int64_t yrs, int64_t yss, const RowScatter* sc, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t gru_wide_tc_workspace_bytes(int d_in, int h);
@@ -228,8 +228,8 @@ static int rnn_seq_impl(int cell, const float* seq, int64_t srs, int64_t sss, in
     if (cell == CTGCN_CELL_GRU && impl != CTGCN_IMPL_SIMT) {
         char* tc_ws = (char*)workspace + rnn_ws_simt(cell, d_in, h);
         int rc = 1;
-        if (impl == CTGCN_IMPL_TC_WIDE || ((impl == CTGCN_IMPL_AUTO || impl == CTGCN_IMPL_TCGEN05) && h > 128))
-            rc = launch_gru_wide_tc(seq, srs, sss, n, steps, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, sc,
+        if (impl == CTGCN_IMPL_TC_WIDE || ((impl == CTGCN_IMPL_AUTO || impl == CTGCN_IMPL_TCGEN05 || impl == CTGCN_IMPL_TC_UNPAIRED) && h > 128))
+            rc = launch_gru_wide_tc(impl == CTGCN_IMPL_TC_UNPAIRED ? 1 : 2, seq, srs, sss, n, steps, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, y, yrs, yss, sc,
                                     tc_ws, gru_ws_tc(d_in, h), st);
         else if (impl != CTGCN_IMPL_TC_ONE_CTA_R1)
             rc = launch_gru_tc2(impl == CTGCN_IMPL_TC_UNPAIRED ? 1 : 2, seq, srs, sss, n, steps, d_in, h, w_ih, w_hh, b_ih, b_hh, ln_w,

@@ -195,29 +195,6 @@ struct Params2 {
         if (p.trace && blockIdx.x == 0 && (gs) < 64u) p.trace[(e) * 64 + (gs)] = clock64(); \
     } while (0)
 
-template <int CG>
-__device__ __forceinline__ void umma_cg(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    if constexpr (CG == 2) umma2_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
-    else umma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
-}
-template <int CG>
-__device__ __forceinline__ void commit_cg(uint32_t bar) {
-    if constexpr (CG == 2) umma2_commit(bar);
-    else umma_commit(bar);
-}
-// arrive on a barrier that lives in the pair's LEADER (rank 0)
-template <int CG>
-__device__ __forceinline__ void arrive_leader(uint32_t bar, uint32_t rank) {
-    if (CG == 2 && rank != 0) mbar_arrive_remote(bar, 0);
-    else mbar_arrive(bar);
-}
-// leader-side wait on a barrier with arrivals from both CTAs
-template <int CG>
-__device__ __forceinline__ void wait_pair(uint32_t bar, uint32_t parity) {
-    if constexpr (CG == 2) mbar_wait_cluster(bar, parity);
-    else mbar_wait(bar, parity);
-}
-
 // SLICED (d_in > 128, e.g. the 500 → 128 first CoreDiffusion layer of every shipped CTGCN-C config, models.py:228): a 128-row U tile
 // of that width does not fit next to h, so the input part runs slice-major — the loaders stage 64 input columns at a time into
 // one of two 32 KB slots while the MMAs of BOTH blocks consume the other (accumulating across slices), then the recurrent parts

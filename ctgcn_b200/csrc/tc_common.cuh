@@ -156,6 +156,30 @@ __device__ __forceinline__ void umma2_commit(uint32_t bar) {   // arrives on `ba
                  : "memory");
 }
 
+// CG-generic forms (CG = CTAs per MMA): used by gru_tc2.cu and gru_wide_tc.cu
+template <int CG>
+__device__ __forceinline__ void umma_cg(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CG == 2) umma2_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
+    else umma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+template <int CG>
+__device__ __forceinline__ void commit_cg(uint32_t bar) {
+    if constexpr (CG == 2) umma2_commit(bar);
+    else umma_commit(bar);
+}
+// arrive on a barrier that lives in the pair's LEADER (rank 0)
+template <int CG>
+__device__ __forceinline__ void arrive_leader(uint32_t bar, uint32_t rank) {
+    if (CG == 2 && rank != 0) mbar_arrive_remote(bar, 0);
+    else mbar_arrive(bar);
+}
+// leader-side wait on a barrier with arrivals from both CTAs
+template <int CG>
+__device__ __forceinline__ void wait_pair(uint32_t bar, uint32_t parity) {
+    if constexpr (CG == 2) mbar_wait_cluster(bar, parity);
+    else mbar_wait(bar, parity);
+}
+
 
 // ------------------------------------------------------------------------------------------------ bf16 split
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
