@@ -25,7 +25,6 @@
 //   warps 12-19  gate epilogue
 #include "common.cuh"
 #include "tc_common.cuh"
-#include <stdlib.h>
 
 namespace ctgcn {
 namespace {
@@ -57,7 +56,7 @@ struct WL {
 constexpr int NUM_LOADER_WARPS = 8, NUM_EPI_WARPS = 8, FIRST_LOADER_WARP = 4, FIRST_EPI_WARP = 12, THREADS = 640;
 constexpr int REG_WG0 = 40, REG_LOAD = 64, REG_EPI = 152;      // setmaxnreg budgets out of 640 × 96
 static_assert(128 * REG_WG0 + 256 * REG_LOAD + 256 * REG_EPI <= THREADS * 96, "register pool");
-constexpr int MAX_UNITS_PER_CTA = 8, SM_COUNT_SIZING = 148;    // rows of a chunk: 148·units_per_cta() units (workspace sizing is device-independent)
+constexpr int SM_COUNT_SIZING = 148;                            // rows of a chunk: 148·UNITS_PER_CTA units (workspace sizing is device-independent)
 
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
@@ -457,15 +456,10 @@ __global__ void __launch_bounds__(256) ln_rows_wide_kernel(const float* src, int
         }
 }
 
-// EXPERIMENT KNOB (to be fixed): work units per CTA and launch — small keeps the chunk's h / Σh buffers in the L2, large amortises launches
-int units_per_cta() {
-    static const int v = [] {
-        const char* e = getenv("CTGCN_WIDE_UNITS");
-        const int u = e ? atoi(e) : 4;
-        return u < 1 ? 1 : (u > MAX_UNITS_PER_CTA ? MAX_UNITS_PER_CTA : u);
-    }();
-    return v;
-}
+// Work units per CTA and launch: measured 2 / 3 / 4 / 6 / 8 → 239 / 239 / 244 / 243.5 / 244 TFLOP/s (first version, 256 → 256): launch
+// overhead is not what binds, so the smallest value on the plateau — the chunk's h / Σh buffers (38 MB each at H = 256) stay in the L2.
+constexpr int UNITS_PER_CTA = 4;
+int units_per_cta() { return UNITS_PER_CTA; }
 long long* g_wide_trace = nullptr;
 int64_t chunk_rows_of(int h, int upc) { return (int64_t)SM_COUNT_SIZING * upc * TILE_M / (h / UNIT_N); }
 size_t packed_bytes(int d_in, int h) { return (size_t)(h / UNIT_N) * (ceil_div(d_in, SLICE_K) + h / SLICE_K) * 3 * BLOCK; }
@@ -475,7 +469,7 @@ bool wide_takes(int d_in, int h) {
 }
 size_t wide_workspace(int d_in, int h) {
     if (!wide_takes(d_in, h)) return 0;
-    return align_up(packed_bytes(d_in, h), 256) + 4 * MAX_H * sizeof(float) + 3 * (size_t)chunk_rows_of(h, MAX_UNITS_PER_CTA) * h * sizeof(float);
+    return align_up(packed_bytes(d_in, h), 256) + 4 * MAX_H * sizeof(float) + 3 * (size_t)chunk_rows_of(h, 4) * h * sizeof(float);
 }
 
 template <int CG>

@@ -35,7 +35,7 @@ def main():
     sd.update(cases.norm_params(rng, "norm.", args.h))
     sd = {k: torch.from_numpy(v).to(dev) for k, v in sd.items()}
     # the last chunk of the call is a full one: its last launch is what the trace shows
-    units = int(os.environ.get("CTGCN_WIDE_UNITS", "4"))
+    units = 4                                                   # UNITS_PER_CTA of gru_wide_tc.cu
     chunk = 148 * units * 128 // (args.h // 128)
     n = max(1, args.n // chunk) * chunk
     seq = torch.randn(n, args.steps, args.d_in, device=dev).abs()

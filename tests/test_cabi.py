@@ -34,6 +34,16 @@ def test_argument_validation_without_gpu(lib):
     assert L.ctgcn_set_gru_impl(7) == lib.EINVAL
     assert L.ctgcn_set_gru_impl(lib.IMPL_AUTO) == 0
     assert L.ctgcn_gru_workspace_bytes(128, 128) > 0
+    # the selector codes of include/ctgcn_b200.h and of the binding agree, and the wide-state kernel's chunk buffers are only
+    # charged to layers that use it (H > 128, or selected explicitly)
+    hdr = open(os.path.join(ROOT, "include", "ctgcn_b200.h")).read()
+    for name in ("AUTO", "SIMT", "TCGEN05", "TC_ONE_CTA_R1", "TC_UNPAIRED", "TC_WIDE"):
+        assert int(re.search(rf"#define CTGCN_IMPL_{name} (\d+)", hdr).group(1)) == getattr(lib, f"IMPL_{name}")
+    small, wide = L.ctgcn_gru_workspace_bytes(128, 128), L.ctgcn_gru_workspace_bytes(256, 256)
+    assert small < (8 << 20) and (100 << 20) < wide < (160 << 20)
+    assert L.ctgcn_set_gru_impl(lib.IMPL_TC_WIDE) == 0
+    assert L.ctgcn_gru_workspace_bytes(128, 128) > (100 << 20)
+    assert L.ctgcn_set_gru_impl(lib.IMPL_AUTO) == 0
     assert L.ctgcn_linear_workspace_bytes(10, 20) >= 800
     assert L.ctgcn_cumspmm_fwd(None, None, 0, 4, None, None) == lib.EINVAL
     assert L.ctgcn_plan_destroy(None) == 0
