@@ -270,7 +270,11 @@ __global__ void __launch_bounds__(THREADS, 1) gru_wide_step_kernel(const ParamsW
     } else if (warp < FIRST_EPI_WARP) {
         // ===================================================== loaders: 16 tile rows per warp, one 64-column slice at a time
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_LOAD));
-        const int r8 = lane & 7, c4 = lane >> 3;
+        // A quarter-warp reads 128 contiguous bytes of ONE row (lane = 16-byte piece): 8 L1 data-pipe wavefronts per load instruction
+        // instead of 32 for "8 rows per quarter" — this kernel is bound by the LSU data pipe (profiles/r02_experiments.md).  A lane then
+        // holds half an operand unit and stores it with 64-bit stores (4-way bank conflicts: 8 wavefronts per store instruction,
+        // 48 per KB of input in all against 72, without shuffles or extra latency).
+        const int q4 = lane >> 3, p8 = lane & 7;
         const int row_base = 16 * (warp - FIRST_LOADER_WARP);
         uint32_t use = 0;
         for (int t = 0; t < my_units; ++t) {
@@ -282,27 +286,24 @@ __global__ void __launch_bounds__(THREADS, 1) gru_wide_step_kernel(const ParamsW
                 const int width = is_x ? p.d_in : p.h, col0 = (is_x ? s : s - p.nx) * SLICE_K;
                 float4 v[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {                   // (row group of 8, k-group of 4 k-blocks): 2 × 2
-                    const int rg = u & 1, kg = u >> 1;
-                    const int64_t srow = tile_row0 + row_base + 8 * rg + r8;
-                    const int c0 = col0 + (4 * kg + c4) * 8;
-                    const float* src = base + srow * ld + c0;
-                    const bool ok = srow < p.n;
-                    v[2 * u] = ok && c0 + 4 <= width ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    v[2 * u + 1] = ok && c0 + 8 <= width ? __ldg(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int u = 0; u < 8; ++u) {                   // (row group of 4, 32-column half of the slice): 4 × 2
+                    const int64_t srow = tile_row0 + row_base + 4 * (u & 3) + q4;
+                    const int c0 = col0 + 32 * (u >> 2) + 4 * p8;
+                    v[u] = srow < p.n && c0 + 4 <= width ? __ldg(reinterpret_cast<const float4*>(base + srow * ld + c0))
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 if (warp == FIRST_LOADER_WARP && lane == 0 && s == 0) WIDE_TRACE(6, t);
                 mbar_wait(bar(L::A_FREE + (use & 1)), ((use >> 1) & 1) ^ 1);
                 uint8_t* slot = smem + L::SM_A + (use & 1) * BLOCK;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int rg = u & 1, kg = u >> 1;
-                    const int m = row_base + 8 * rg + r8, kb = 4 * kg + c4;
-                    const float f8[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w, v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
-                    uint4 hi, lo;
-                    split8(f8, hi, lo);
-                    *reinterpret_cast<uint4*>(slot + kb * (TILE_M * 16) + m * 16) = hi;
-                    *reinterpret_cast<uint4*>(slot + PLANE + kb * (TILE_M * 16) + m * 16) = lo;
+                for (int u = 0; u < 8; ++u) {
+                    const int m = row_base + 4 * (u & 3) + q4, kb = 4 * (u >> 2) + (p8 >> 1);
+                    uint2 hi, lo;
+                    split2(v[u].x, v[u].y, hi.x, lo.x);
+                    split2(v[u].z, v[u].w, hi.y, lo.y);
+                    uint8_t* dst = slot + kb * (TILE_M * 16) + m * 16 + 8 * (p8 & 1);
+                    *reinterpret_cast<uint2*>(dst) = hi;
+                    *reinterpret_cast<uint2*>(dst + PLANE) = lo;
                 }
                 fence_proxy_async();
                 __syncwarp();
