@@ -747,33 +747,32 @@ __global__ void __launch_bounds__(Lay<CG, FUSED>::THREADS, 1) gru2_kernel(const 
                 const int64_t tile_row0 = tile_of(t) * TILE_M;
                 for (int i = 0; i < p.steps; ++i, ++gs) {
                     const float* base = p.seq + (int64_t)i * p.sss;
+                    // A quarter-warp reads 128 contiguous bytes of ONE row (lane = 16-byte piece p8 of row q4 of a 4-row group): 8 L1
+                    // data-pipe wavefronts per load instead of 32 for the former "8 rows per quarter" mapping; a lane then holds half
+                    // an operand unit and stores it with 64-bit stores.  An "iteration" = two such loads (the lane's float4 pair).
                     float4 v[16];
+                    const int q4 = lane >> 3, p8 = lane & 7;
                     auto load_batch = [&](int it0, int cnt) {   // up to 8 iterations = 16 LDG.128 in flight per lane
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int it = it0 + u, rg = it & 3, kg = it >> 2;
-                            const int64_t srow = tile_row0 + row_base + 8 * rg + r8;
-                            if (u < cnt && srow < p.n) {
-                                const float* src = base + srow * p.srs + (4 * kg + c4) * 8;
-                                v[2 * u] = __ldg(reinterpret_cast<const float4*>(src));
-                                v[2 * u + 1] = __ldg(reinterpret_cast<const float4*>(src + 4));
-                            } else {
-                                v[2 * u] = v[2 * u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            }
+                        for (int u = 0; u < 16; ++u) {
+                            const int e = 2 * it0 + u, rgrp = e & 7, span = e >> 3;      // (row group of 4: 8 per warp, 32-column span)
+                            const int64_t srow = tile_row0 + row_base + 4 * rgrp + q4;
+                            v[u] = (u < 2 * cnt && srow < p.n) ? __ldg(reinterpret_cast<const float4*>(base + srow * p.srs + 32 * span + 4 * p8))
+                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                     };
-                    auto store_batch = [&](int it0, int cnt) {  // fp32 → bf16 hi/lo planes, 8 k-elements (16 B) per store
+                    auto store_batch = [&](int it0, int cnt) {  // fp32 → bf16 hi/lo planes, 4 k-elements (8 B) per store
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            if (u < cnt) {
-                                const int it = it0 + u, rg = it & 3, kg = it >> 2;
-                                const int m = row_base + 8 * rg + r8, kb = 4 * kg + c4;
-                                const float f8[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w,
-                                                     v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
-                                uint4 hi, lo;
-                                split8(f8, hi, lo);
-                                *reinterpret_cast<uint4*>(u_hi + kb * (TILE_M * 16) + m * 16) = hi;
-                                *reinterpret_cast<uint4*>(u_hi + A_PLANE + kb * (TILE_M * 16) + m * 16) = lo;
+                        for (int u = 0; u < 16; ++u) {
+                            if (u < 2 * cnt) {
+                                const int e = 2 * it0 + u, rgrp = e & 7, span = e >> 3;
+                                const int m = row_base + 4 * rgrp + q4, kb = 4 * span + (p8 >> 1);
+                                uint2 hi, lo;
+                                split2(v[u].x, v[u].y, hi.x, lo.x);
+                                split2(v[u].z, v[u].w, hi.y, lo.y);
+                                uint8_t* dst = u_hi + kb * (TILE_M * 16) + m * 16 + 8 * (p8 & 1);
+                                *reinterpret_cast<uint2*>(dst) = hi;
+                                *reinterpret_cast<uint2*>(dst + A_PLANE) = lo;
                             }
                         }
                     };
