@@ -1,6 +1,6 @@
 set -u
 mkdir -p gpurun_out
-out=gpurun_out/r02H
+out=gpurun_out/r02U
 free -g > "${out}_mem.log"; nvidia-smi --query-gpu=memory.total --format=csv >> "${out}_mem.log"
 avail=$(awk '/MemAvailable/ {print int($2/1048576)}' /proc/meminfo)
 echo "MemAvailable ${avail} GB" | tee -a "${out}_summary.log"
