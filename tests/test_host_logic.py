@@ -221,3 +221,45 @@ def test_plan_cache_holds_no_strong_references(lib, monkeypatch):
     finally:
         P.set_cache_limits(device_bytes=16 << 30)
         P.clear_cache()
+
+
+def test_operand_staging_lane_maps():
+    """The two lane → (row, column) maps the loader warps use (csrc/tc_common.cuh `StageBlock`; csrc/gru_wide_tc.cu / gru_tc2.cu
+    loaders), restated in numpy: every element of the block is loaded exactly once, every quarter-warp of a 128-bit load reads 128
+    contiguous bytes of ONE row (the property the L1 data pipe rewards), every 16-byte operand unit is written exactly once, and the
+    128-bit shared-memory stores of a quarter-warp hit 8 different rows mod 8 (all 32 banks once)."""
+    import numpy as np
+    lanes = np.arange(32)
+    # ---- StageBlock: 32 rows × 32 columns, loads (b, i), pair swap, rotation by kb
+    q, p = lanes >> 3, lanes & 7
+    seen = np.zeros((32, 32), dtype=int)
+    for b in range(4):
+        for i in range(2):
+            rows, cols = 8 * q + 2 * b + i, 4 * p
+            for qq in range(4):                                  # a quarter-warp: one row, 32 consecutive columns
+                sel = q == qq
+                assert len(set(rows[sel])) == 1 and sorted(cols[sel]) == list(range(0, 32, 4))
+            for r, c in zip(rows, cols):
+                seen[r, c:c + 4] += 1
+    assert (seen == 1).all()
+    m, par = (lanes & 7) >> 1, lanes & 1
+    units = np.zeros((32, 4), dtype=int)                         # (row, k-block of 8 columns)
+    for j in range(4):
+        rows = 8 * q + 2 * ((j + m) & 3) + par
+        for qq in range(4):
+            assert sorted(rows[q == qq] % 8) == list(range(8))   # conflict-free 128-bit stores
+        # what the lane stores at step j is the unit it owns from load b = (j + m) % 4: row 8q + 2b + par, k-block m
+        for r, kb in zip(rows, m):
+            units[r, kb] += 1
+    assert (units == 1).all()
+    # ---- GRU loaders: lane = (row q4 of a 4-row group, 16-byte piece p8), 64-bit stores of half units
+    q4, p8 = lanes >> 3, lanes & 7
+    half_units = np.zeros((16, 8, 2), dtype=int)                 # 16 rows × 8 k-blocks × halves of a 16-row × 64-column slice part
+    for u in range(8):
+        rows, cols = 4 * (u & 3) + q4, 32 * (u >> 2) + 4 * p8
+        for qq in range(4):
+            sel = q4 == qq
+            assert len(set(rows[sel])) == 1 and sorted(cols[sel] % 32) == list(range(0, 32, 4))
+        for r, c in zip(rows, cols):
+            half_units[r, c // 8, (c // 4) & 1] += 1
+    assert (half_units == 1).all()
