@@ -175,20 +175,32 @@ __global__ void __launch_bounds__(THREADS, 1) linear_gen_kernel(const ParamsG p)
         // ===================================================== loaders: 16 tile rows per warp, one 64-column slice at a time
         // one 32-row × 32-column block per warp and slice (StageBlock, tc_common.cuh): row group w % 4, column half w / 4
         const int lw = warp - FIRST_LOADER_WARP, g = lw & 3, half = lw >> 2;
-        uint32_t use = 0;
-        for (int t = 0; t < my_tiles; ++t) {
+        // Software pipeline over the flattened (tile, slice) sequence: the loads of slice k+1 are issued before slice k is converted
+        // and stored, so a slice is always in flight (two register blocks, used alternately).
+        const int total = my_tiles * p.nslices;
+        auto issue = [&](int k, StageBlock& blk) {
+            const int t = k / p.nslices, s = k - t * p.nslices;
             const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + 32 * g;
             const int64_t left = p.n - row0;
-            const int rows_ok = left > 32 ? 32 : (int)left;
-            for (int s = 0; s < p.nslices; ++s, ++use) {
-                const int c0 = s * SLICE_K + 32 * half;
-                StageBlock blk;
-                blk.load(p.x + row0 * p.ldx + c0, p.ldx, rows_ok, p.d_in - c0, lane);
-                mbar_wait(bar(A_FREE + (use & 1)), ((use >> 1) & 1) ^ 1);
-                blk.store<3>(smem + SM_A + (use & 1) * BLOCK + (4 * half) * (TILE_M * 16) + (32 * g) * 16, PLANE, TILE_M * 16, lane);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(A_READY + (use & 1)));
+            const int c0 = s * SLICE_K + 32 * half;
+            blk.load(p.x + row0 * p.ldx + c0, p.ldx, left > 32 ? 32 : (int)left, p.d_in - c0, lane);
+        };
+        auto stage = [&](int k, const StageBlock& blk) {
+            const uint32_t use = (uint32_t)k;                    // running slice counter: slot = use & 1
+            mbar_wait(bar(A_FREE + (use & 1)), ((use >> 1) & 1) ^ 1);
+            blk.store<3>(smem + SM_A + (use & 1) * BLOCK + (4 * half) * (TILE_M * 16) + (32 * g) * 16, PLANE, TILE_M * 16, lane);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(A_READY + (use & 1)));
+        };
+        StageBlock ba, bb;
+        if (total > 0) issue(0, ba);
+        for (int k = 0; k < total; k += 2) {
+            if (k + 1 < total) issue(k + 1, bb);
+            stage(k, ba);
+            if (k + 1 < total) {
+                if (k + 2 < total) issue(k + 2, ba);
+                stage(k + 1, bb);
             }
         }
     } else {
