@@ -320,6 +320,35 @@ def test_gru_seq_kernel(n, steps, d_in, h, bias, mode, impl, lib, cuda_device):
     assert (out[:, 0] == 7.0).all() if mode else (out[:, h:] == 7.0).all()   # nothing written outside the view
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("cg", ["wide", "unpaired"])
+def test_gru_wide_row_chunks(mode, cg, lib, cuda_device):
+    """The step-per-launch kernel works through the rows in chunks of 148·4 work units (37 888 rows at H = 256, its h / Σh buffers
+    are chunk-sized): more than one chunk, a ragged last chunk and an odd tile count (the pair build's phantom tile) against the
+    fp32 sequence kernel on the same device — rows of every chunk, both output modes."""
+    from ctgcn_b200 import ops
+    n, steps, d_in, h = 37_888 * 2 + 5_000 + 77, 3, 192, 256
+    rng = np.random.default_rng(5)
+    sd = cases.gru_params(rng, "rnn.", d_in, h, True)
+    sd.update(cases.norm_params(rng, "norm.", h))
+    d = tsd(sd, cuda_device)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    seq = (torch.randn(n, steps, d_in, generator=g) * 2).clamp_(min=0).to(cuda_device)
+    args = (d["rnn.weight_ih_l0"], d["rnn.weight_hh_l0"], d["rnn.bias_ih_l0"], d["rnn.bias_hh_l0"], d["norm.weight"], d["norm.bias"], 1e-5, mode)
+    try:
+        lib.set_gru_impl(lib.IMPL_SIMT)
+        ref = ops.gru_seq(seq, *args)
+        lib.set_gru_impl(lib.IMPL_TC_WIDE if cg == "wide" else lib.IMPL_TC_UNPAIRED)
+        got = ops.gru_seq(seq, *args)
+        got2 = ops.gru_seq(seq, *args)
+    finally:
+        lib.set_gru_impl(lib.IMPL_AUTO)
+    assert torch.equal(got, got2)                                 # deterministic (Σh is a reduction with one writer per element)
+    for lo, hi in ((0, 4096), (37_888 - 64, 37_888 + 64), (2 * 37_888 - 64, 2 * 37_888 + 64), (n - 4096, n)):
+        close(got[lo:hi].cpu().numpy(), ref[lo:hi].cpu().numpy(), f"wide GRU rows [{lo}, {hi}) mode={mode} [{cg}]")
+    assert cases.relerr(got.cpu().numpy(), ref.cpu().numpy()) <= 1e-5
+
+
 # ----------------------------------------------------------------------------- fused exchange epilogue
 @pytest.mark.parametrize("name,n_slices", [("cd_nested_k5", 3), ("cd_nested_k5", 8), ("cd_general", 4), ("cd_uci_0404_500_128", 5)])
 def test_core_diffusion_scatter(name, n_slices, impl, lib, cuda_device):
