@@ -4,7 +4,7 @@
 // operands (h alone is 128 KB as bf16 hi|lo planes) nor the accumulators (r, z, n_x, n_h × 256 = 1024 TMEM columns) fit.
 //
 // So the recurrence runs ONE STEP PER LAUNCH with h in global memory, over row chunks small enough that the two h buffers and the
-// Σh buffer of a chunk stay in the 126 MB L2 (148·8 work units per launch; h never goes to DRAM), and a launch is a GEMM with a
+// Σh buffer of a chunk stay in the 126 MB L2 (148·4 work units per launch; h never goes to DRAM), and a launch is a GEMM with a
 // fused gate epilogue:
 //   work unit = (128-row tile, 128 hidden features j ∈ [128u, 128u+128)); TMEM: r | z | n_x | n_h, 128 columns each (all 512)
 //   for slice s of [x_i | h_{i-1}] (64 columns, fp32 rows → bf16 hi|lo planes by the loader warps):
