@@ -127,6 +127,47 @@ def rnn_seq_bwd(seq, cell, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, dy):
     return dseq, dw_ih, dw_hh, db_ih, db_hh, dln_w, dln_b
 
 
+# Bound on the recompute's intermediates (gate activations and their gradients of one row chunk), in bytes.  The forward honours
+# ctgcn_set_workspace_cap; without a bound here the backward of a bench-size layer (1 M rows × K = 10 × 128) kept > 60 GB of
+# [N, K, 3H] / [N, K, H] tensors alive (round-1 advice).  Rows are independent in the recurrence and in LayerNorm, so the backward
+# runs chunk by chunk: dseq rows are written in place, weight / bias / LayerNorm gradients are summed over the chunks.
+BWD_CHUNK_BYTES = 2 << 30
+
+
+def set_backward_chunk_bytes(nbytes: int) -> None:
+    global BWD_CHUNK_BYTES
+    BWD_CHUNK_BYTES = max(int(nbytes), 1 << 20)
+
+
+def _bwd_chunk_rows(L: int, d: int, H: int, G: int) -> int:
+    per_row = 4 * L * (2 * G * H + 6 * H + d)          # gi, dgi, the kept gate tensors and h, dseq
+    return max(256, BWD_CHUNK_BYTES // per_row)
+
+
+def rnn_seq_bwd_chunked(seq, cell, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, dy, max_rows=None):
+    """rnn_seq_bwd over row chunks of at most `max_rows` rows (default: from BWD_CHUNK_BYTES).  Same values as the unchunked call up
+    to the summation order of the parameter gradients; one chunk = exactly the unchunked call."""
+    n, L, d = seq.shape
+    H = w_hh.shape[1]
+    G = 4 if cell == _lib.CELL_LSTM else 3
+    rows = _bwd_chunk_rows(L, d, H, G) if max_rows is None else int(max_rows)
+    if n <= rows:
+        return rnn_seq_bwd(seq, cell, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, dy)
+    dseq = torch.empty_like(seq)
+    acc = None
+    for r0 in range(0, n, rows):
+        sl = slice(r0, min(n, r0 + rows))
+        out = rnn_seq_bwd(seq[sl], cell, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, eps, mode, dy[sl])
+        dseq[sl] = out[0]
+        if acc is None:
+            acc = [None if g is None else g.clone() for g in out[1:]]
+        else:
+            for a, g in zip(acc, out[1:]):
+                if a is not None:
+                    a += g
+    return (dseq, *acc)
+
+
 def selu_bwd_from_output(dy, y):
     """d selu / d pre-activation expressed through the OUTPUT y = selu(v): scale for v > 0, y + scale·alpha otherwise."""
     return dy * torch.where(y > 0, torch.full_like(y, SELU_SCALE), y + SELU_SCALE * SELU_ALPHA)
@@ -149,11 +190,13 @@ class CoreDiffusionFn(torch.autograd.Function):
         plan = ctx.plan
         with torch.no_grad():
             u = ops.cumspmm(plan, x)                                        # [N, K, D] = relu(S_i), recomputed
-            du, dw_ih, dw_hh, db_ih, db_hh, dln_w, dln_b = rnn_seq_bwd(u, ctx.cell, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b,
-                                                                       ctx.eps, _lib.GRU_SUM_LN, dy.contiguous())
+            du, dw_ih, dw_hh, db_ih, db_hh, dln_w, dln_b = rnn_seq_bwd_chunked(u, ctx.cell, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b,
+                                                                               ctx.eps, _lib.GRU_SUM_LN, dy.contiguous())
             dx = None
             if ctx.needs_input_grad[0]:
-                dx = ops.cumspmm_bwd(plan.transposed(), du * (u > 0))        # relu mask, then Σ_j A_jᵀ Σ_{i≥j} dS_i
+                du.mul_(u > 0)                                              # relu mask (in place: du is ours)
+                del u
+                dx = ops.cumspmm_bwd(plan.transposed(), du)                 # Σ_j A_jᵀ Σ_{i≥j} dS_i
         return dx, None, None, None, dw_ih, dw_hh, db_ih, db_hh, dln_w, dln_b
 
 
@@ -171,8 +214,8 @@ class RnnSeqFn(torch.autograd.Function):
     def backward(ctx, dy):
         seq, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b = ctx.saved_tensors
         with torch.no_grad():
-            dseq, dw_ih, dw_hh, db_ih, db_hh, dln_w, dln_b = rnn_seq_bwd(seq, ctx.cell, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b,
-                                                                         ctx.eps, _lib.GRU_EACH_LN, dy.contiguous())
+            dseq, dw_ih, dw_hh, db_ih, db_hh, dln_w, dln_b = rnn_seq_bwd_chunked(seq, ctx.cell, w_ih, w_hh, b_ih, b_hh, ln_w, ln_b,
+                                                                                 ctx.eps, _lib.GRU_EACH_LN, dy.contiguous())
         return dseq, None, None, dw_ih, dw_hh, db_ih, db_hh, dln_w, dln_b
 
 

@@ -44,6 +44,45 @@ def test_rnn_seq_bwd_matches_torch_autograd(cell_name, bias, mode, lib):
         assert float((a - b).norm() / b.norm()) < 1e-10
 
 
+@pytest.mark.parametrize("cell_name", ["GRU", "LSTM"])
+@pytest.mark.parametrize("bias", [True, False])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_rnn_seq_bwd_in_row_chunks(cell_name, bias, mode, lib):
+    """The backward runs over row chunks so that its intermediates stay bounded (round-1 advice): same dseq rows, parameter
+    gradients equal up to the order of the sums; a single chunk is exactly the unchunked call; the default bound gives whole-tensor
+    calls at test sizes and ≈ 32 K-row chunks at the bench shape."""
+    from ctgcn_b200 import autograd as ag
+    torch.manual_seed(7)
+    n, L, d, H = 53, 4, 10, 8
+    G = 4 if cell_name == "LSTM" else 3
+    w_ih, w_hh = torch.randn(G * H, d, dtype=torch.double) * 0.3, torch.randn(G * H, H, dtype=torch.double) * 0.3
+    b_ih, b_hh = (torch.randn(G * H, dtype=torch.double) * 0.1, torch.randn(G * H, dtype=torch.double) * 0.1) if bias else (None, None)
+    ln_w, ln_b = torch.rand(H, dtype=torch.double) + 0.5, torch.randn(H, dtype=torch.double) * 0.1
+    seq = torch.randn(n, L, d, dtype=torch.double)
+    dy = torch.randn(n, H, dtype=torch.double) if mode == 0 else torch.randn(n, L, H, dtype=torch.double)
+    args = (seq, lib.CELLS[cell_name], w_ih, w_hh, b_ih, b_hh, ln_w, ln_b, 1e-5, mode, dy)
+    whole = ag.rnn_seq_bwd(*args)
+    for max_rows in (7, 16, 52, 53, 1000):
+        part = ag.rnn_seq_bwd_chunked(*args, max_rows=max_rows)
+        assert len(part) == len(whole)
+        for a, b in zip(part, whole):
+            assert (a is None) == (b is None)
+            if a is not None:
+                if max_rows >= n:
+                    assert torch.equal(a, b)
+                else:
+                    assert float((a - b).norm() / b.norm()) < 1e-12
+    assert torch.equal(ag.rnn_seq_bwd_chunked(*args)[0], whole[0])            # default bound: one chunk at this size
+    assert 20_000 < ag._bwd_chunk_rows(10, 128, 128, 3) < 60_000              # cfg4's core GRU: chunks of a few 10^4 rows
+    ag.set_backward_chunk_bytes(1 << 20)
+    try:
+        small = ag.rnn_seq_bwd_chunked(*args)                                 # 1 MiB bound → the 256-row floor → still one chunk here
+        assert torch.equal(small[0], whole[0])
+        assert ag._bwd_chunk_rows(10, 128, 128, 3) == 256
+    finally:
+        ag.set_backward_chunk_bytes(2 << 30)
+
+
 def test_selu_bwd_from_output(lib):
     from ctgcn_b200 import autograd as ag
     v = torch.linspace(-4, 4, 101, dtype=torch.double, requires_grad=True)
