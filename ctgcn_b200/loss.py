@@ -68,14 +68,32 @@ class NegativeSamplingLoss(nn.Module):
         self._calls = 0
         self._host = [None] * len(node_pair_list)     # per snapshot (ptr, idx, freq) as numpy, built on first use
         self._dev = {}                                # (snapshot, device) → CUDA tensors
+        self.validate = True        # check index ranges before the kernels run (one device reduction + sync per call for the batch)
+
+    def _host_arrays(self, i):
+        if self._host[i] is None:
+            ptr, idx = _csr_from_rows(self.node_pair_list[i])
+            self._host[i] = (ptr, idx, np.asarray(self.neg_freq_list[i], dtype=np.int32))
+        return self._host[i]
+
+    def _check_ranges(self, i, n_rows_emb, batch):
+        """The kernels index the embedding with co-occurrence, negative-list and batch node ids without bounds checks; the reference
+        raises IndexError on any of them (metrics.py:56-57, 78-93).  Same here, before anything is launched."""
+        ptr, idx, freq = self._host_arrays(i)
+        hi = max(int(idx.max()) if idx.size else -1, int(freq.max()) if freq.size else -1)
+        lo = min(int(idx.min()) if idx.size else 0, int(freq.min()) if freq.size else 0)
+        if hi >= n_rows_emb or lo < 0:
+            raise IndexError(f"snapshot {i}: node ids of the co-occurrence / negative lists span [{lo}, {hi}], the embedding has {n_rows_emb} rows")
+        if self.validate and batch.numel():
+            bmin, bmax = int(batch.min()), int(batch.max())
+            if bmin < 0 or bmax >= n_rows_emb or bmax >= ptr.shape[0] - 1:
+                raise IndexError(f"snapshot {i}: batch node ids span [{bmin}, {bmax}]; the embedding has {n_rows_emb} rows, "
+                                 f"the co-occurrence list {ptr.shape[0] - 1}")
 
     def _arrays(self, i, device):
         key = (i, str(device))
         if key not in self._dev:
-            if self._host[i] is None:
-                ptr, idx = _csr_from_rows(self.node_pair_list[i])
-                self._host[i] = (ptr, idx, np.asarray(self.neg_freq_list[i], dtype=np.int32))
-            self._dev[key] = tuple(torch.from_numpy(a).to(device) for a in self._host[i])
+            self._dev[key] = tuple(torch.from_numpy(a).to(device) for a in self._host_arrays(i))
         return self._dev[key]
 
     def sample(self, i, batch_indices, seed):
@@ -94,6 +112,7 @@ class NegativeSamplingLoss(nn.Module):
         total = torch.zeros(1, dtype=torch.float32, device=batch.device)            # metrics.py:40
         for i in range(len(node_embedding)):
             emb = node_embedding[i]
+            self._check_ranges(i, emb.shape[0], batch)
             if emb.dtype != torch.float32 or emb.stride(-1) != 1:
                 emb = emb.float().contiguous()
             pos, count, neg = self.sample(i, batch, base * 1_000_003 + i)

@@ -151,3 +151,21 @@ def test_device_sampler_algorithm_is_uniform_and_meets_the_contract():
         oracle_loss.check_sample(z["batch"], z[f"pair_ptr{t}"], z[f"pair_idx{t}"], z[f"freq{t}"], meta["neg_num"], pos, count, neg)
         pos2, _, neg2 = oracle_loss.device_sample(z["batch"], z[f"pair_ptr{t}"], z[f"pair_idx{t}"], z[f"freq{t}"], meta["neg_num"], 100 + t)
         assert (pos != pos2).any() and (neg != neg2).any()           # another seed, another draw
+
+
+def test_module_rejects_out_of_range_node_ids(lib):
+    """The kernels index the embedding without bounds checks; like the reference (IndexError at metrics.py:56-57 / 78-93) the module
+    refuses node ids outside the embedding — from the co-occurrence lists, the negative list or the batch — before anything is
+    launched (no GPU needed for the refusal)."""
+    import torch
+    from ctgcn_b200.loss import NegativeSamplingLoss
+    pairs = [[[1, 2], [0], [0, 3], [2]]]                       # 4 nodes
+    emb = torch.zeros(4, 8)
+    with pytest.raises(IndexError, match="negative lists"):
+        NegativeSamplingLoss(pairs, [[0, 1, 2, 9]], neg_num=2)([emb, torch.tensor([0, 1])])
+    with pytest.raises(IndexError, match="co-occurrence"):
+        NegativeSamplingLoss([[[1, 7], [0], [0], [2]]], [[0, 1, 2, 3]], neg_num=2)([emb, torch.tensor([0, 1])])
+    with pytest.raises(IndexError, match="batch node ids"):
+        NegativeSamplingLoss(pairs, [[0, 1, 2, 3]], neg_num=2)([emb, torch.tensor([0, 4])])
+    with pytest.raises(IndexError, match="embedding has 3 rows"):
+        NegativeSamplingLoss(pairs, [[0, 1, 2, 3]], neg_num=2)([emb[:3], torch.tensor([0, 1])])
